@@ -1,0 +1,124 @@
+"""Generate tests/golden/*.npz with the UNMODIFIED reference (run in the build container).
+
+    python -m oracle.gen_golden
+
+Every array under an ``out_`` key is the return value of a reference function
+(pyGPA.geometric_phase_analysis / pyGPA.phase_unwrap imported from /root/reference);
+the ``in_`` keys are the exact inputs, so the fixtures do not depend on the synthetic
+generator staying bit-stable.  Fixtures are small (whole directory < 2 MB).
+"""
+import os
+import numpy as np
+
+from . import _refimport
+from pygpa_b200 import synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def main():
+    gpa, pu = _refimport.load()
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- adaptive sweep: wfr2_grad_opt + optwfr2, non-square frame, 3 peaks -------------
+    shape = (64, 48)
+    ks = synth.primary_ks(0.12, 7.0, 3)
+    u = synth.gaussian_bump(shape) * 0.6
+    img = synth.lattice_image(shape, ks, u, second_order=0.3, noise=0.25, seed=11)
+    img = img - img.mean()
+    sigma = 4
+    kw = float(np.linalg.norm(ks, axis=1).mean() / 2.5)
+    kstep = kw / 3                                    # the reference tests' choice (tests/...:87-89)
+    gs = [gpa.wfr2_grad_opt(img, sigma, k[0], k[1], kw, kstep) for k in ks]
+    g2 = gpa.optwfr2(img, sigma, ks[0][0], ks[0][1], kw, kstep)
+    np.savez_compressed(
+        os.path.join(OUT, "sweep_64x48.npz"),
+        in_image=img, in_ks=ks, in_sigma=sigma, in_kw=kw, in_kstep=kstep,
+        out_lockin=np.stack([g['lockin'] for g in gs]),
+        out_w=np.stack([g['w'] for g in gs]),
+        out_grad=np.stack([g['grad'] for g in gs]),
+        out_optwfr2_lockin=g2['lockin'], out_optwfr2_w=g2['w'])
+
+    # ---- wfr3 on an explicit k-list --------------------------------------------------------
+    rng = np.random.default_rng(5)
+    klist = ks[1] + 0.03 * rng.uniform(-1, 1, size=(9, 2))
+    g3 = gpa.wfr3(img, sigma, klist, ks[1])
+    np.savez_compressed(os.path.join(OUT, "wfr3_64x48.npz"), in_image=img, in_sigma=sigma,
+                        in_klist=klist, in_kref=ks[1], out_lockin=g3['lockin'], out_w=g3['w'])
+
+    # ---- adaptive tail: reconstruct_u_inv_from_phases / extract_displacement_field -----------
+    phases = np.stack([np.angle(g['lockin']) for g in gs])
+    weights = np.stack([np.abs(g['lockin']) for g in gs])
+    mask = np.zeros(shape)
+    mask[2 * sigma:-2 * sigma, 2 * sigma:-2 * sigma] = 1
+    weights_m = weights * (mask + 1e-6)
+    u_fp = gpa.reconstruct_u_inv_from_phases(ks, phases, weights_m)
+    u_fp_unw = gpa.reconstruct_u_inv_from_phases(ks, phases, weights_m, weighted_unwrap=False)
+    grads = np.stack([g['grad'] for g in gs])
+    u_fp_pre = gpa.reconstruct_u_inv_from_phases(ks, grads, weights_m, pre_diff=True)
+    u_edf = gpa.extract_displacement_field(img, ks, sigma=sigma)
+    np.savez_compressed(
+        os.path.join(OUT, "tail_64x48.npz"), in_ks=ks, in_phases=phases, in_weights=weights_m,
+        in_grads=grads, in_image=img, in_sigma=sigma,
+        out_u=u_fp, out_u_unweighted_unwrap=u_fp_unw, out_u_prediff=u_fp_pre, out_u_edf=u_edf)
+
+    # ---- fixed-reference path (config 1 in miniature) ------------------------------------------
+    shape1 = (64, 64)
+    ks1 = synth.primary_ks(0.1, 7.0, 3)
+    u1 = synth.gaussian_bump(shape1)
+    img1 = synth.lattice_image(shape1, ks1, u1, noise=0.1, seed=3)
+    sig1 = 6
+    rs = np.stack([gpa.optGPA(img1, k, sig1) for k in ks1])
+    amps = np.abs(rs)
+    unw = np.stack([pu.phase_unwrap(np.angle(r), np.sqrt(a / a.max()), kmax=25) for r, a in zip(rs, amps)])
+    wdef = amps.copy()
+    wdef[:, :3] = 0.0            # rank-0 pixels
+    wdef[1:, 3:6] = 0.0          # rank-1 pixels
+    np.savez_compressed(
+        os.path.join(OUT, "fixed_64x64.npz"), in_image=img1, in_ks=ks1, in_sigma=sig1,
+        in_weights_rankdef=wdef,
+        out_lockin=rs, out_unwrapped=unw,
+        out_u_unweighted=gpa.reconstruct_u_inv(ks1, unw),
+        out_u_weighted=gpa.reconstruct_u_inv(ks1, unw, amps),
+        out_u_rankdef=gpa.reconstruct_u_inv(ks1, unw, wdef),
+        out_u_two_ks=gpa.reconstruct_u_inv(ks1, unw, use_only_ks=[0, 2]))
+
+    # ---- phase unwrap known answers (tests/test_phase_unwrap.py, N reduced to 64) ---------------
+    n = 64
+    xx, yy = np.meshgrid(np.arange(n), np.arange(n), indexing='ij')
+    psi0 = (yy + xx) / (4 * np.sqrt(2))
+    psi = pu._wrapToPi(psi0)
+    gauss = np.exp(-((xx - n // 2) ** 2 + (yy - n // 2) ** 2) / (0.3 * n ** 2))
+    rng = np.random.default_rng(7)
+    shape_r = (40, 56)                                # non-square: exercises the swapped N/M scale
+    psi_r = pu._wrapToPi(3 * rng.normal(size=shape_r).cumsum(axis=0).cumsum(axis=1) / 20)
+    w_r = rng.uniform(0.05, 1, size=shape_r)
+    np.savez_compressed(
+        os.path.join(OUT, "unwrap.npz"), in_psi=psi, in_psi0=psi0, in_gauss=gauss,
+        in_psi_r=psi_r, in_w_r=w_r,
+        out_ramp_k1=pu.phase_unwrap(psi, np.ones_like(psi), kmax=1),
+        out_ramp_unweighted=pu.phase_unwrap(psi, None, kmax=30),
+        out_ramp_gauss=pu.phase_unwrap(psi, gauss),
+        out_r_k5=pu.phase_unwrap(psi_r, w_r, kmax=5),
+        out_r_k100=pu.phase_unwrap(psi_r, w_r, kmax=100),
+        out_r_unweighted=pu.phase_unwrap(psi_r, None),
+        out_r_prediff_k7=pu.phase_unwrap_prediff(np.diff(psi_r, axis=1), np.diff(psi_r, axis=0), w_r, kmax=7),
+        out_r_prediff_unweighted=pu.phase_unwrap_prediff(np.diff(psi_r, axis=1), np.diff(psi_r, axis=0)))
+
+    # ---- Lawler-Fujita ----------------------------------------------------------------------------
+    shape_l = (48, 40)
+    ks_l = synth.primary_ks(0.11, 7.0, 3)
+    u_l = synth.gaussian_bump(shape_l) * 0.8
+    u_l[1] = 0.4 * np.sin(2 * np.pi * np.arange(shape_l[0])[:, None] / shape_l[0]) * np.ones(shape_l)
+    img_l = synth.lattice_image(shape_l, ks_l, u_l)
+    np.savez_compressed(
+        os.path.join(OUT, "lawler_fujita_48x40.npz"), in_u=u_l, in_image=img_l,
+        out_invert_edge0=gpa.invert_u_overlap(u_l),
+        out_invert_edge3_it5=gpa.invert_u_overlap(u_l, iters=5, edge=3),
+        out_undistorted=gpa.undistort_image(img_l, u_l))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
