@@ -1,0 +1,138 @@
+/*
+ * gpa_b200.h — C ABI of libgpa_b200.so: the B200 (sm_100a) implementation of pyGPA's
+ * adaptive-GPA hot path.  Plain pointers and sizes only; no torch / CuPy types.
+ *
+ * The reference (TAdeJong/pyGPA) is pure Python and has no FFI: its boundary for this
+ * path is a set of module-level functions taking and returning NumPy arrays.  Each entry
+ * point below names the reference function(s) whose arithmetic it replaces
+ * (paths relative to the reference checkout).  pygpa_b200/*.py binds these with ctypes
+ * and re-exports the reference signatures; INTEGRATION.md shows the stub a pyGPA
+ * maintainer would add.
+ *
+ * Conventions
+ *   - images are row-major (N, M) with axis 0 = "x" (pyGPA's convention); k-vectors in
+ *     cycles/pixel, component 0 multiplies the axis-0 index.
+ *   - every pointer is a DEVICE pointer unless the parameter comment says "host".
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls return
+ *     after enqueueing (small host arrays are staged before return, so the caller may
+ *     free them immediately).
+ *   - return value: 0 on success, negative gpaStatus otherwise; gpa_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - no hidden device allocation: scratch comes from the caller through (ws, ws_bytes),
+ *     sized by the matching *_workspace_bytes().
+ */
+#ifndef GPA_B200_H
+#define GPA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GPA_OK = 0,
+    GPA_ERR_INVALID = -1,      /* bad argument                      */
+    GPA_ERR_WORKSPACE = -2,    /* workspace too small               */
+    GPA_ERR_CUDA = -3,         /* CUDA runtime error                */
+    GPA_ERR_UNSUPPORTED = -4   /* valid request this build cannot serve */
+} gpaStatus;
+
+/* candidate layout of a sweep */
+#define GPA_CAND_GRID 0   /* candidates = rows x planes, flat index ix*n_planes + iy (np.arange x np.arange,
+                             geometric_phase_analysis.py:803-804: wx outer, wy inner)                        */
+#define GPA_CAND_LIST 1   /* candidate i = (wx_rows[i], wy_planes[i]), flat index i (wfr3, :647-666)          */
+
+/* phase-gradient flavour of wfr2_grad_opt */
+#define GPA_GRAD_CENTRAL 0 /* np.gradient (geometric_phase_analysis.py:807; cuGPA.py:63-65)  */
+#define GPA_GRAD_FORWARD 1 /* grad='diff' (cuGPA.py:58-62): forward difference, NaN in the last row/column */
+#define GPA_GRAD_NONE 2    /* optwfr2 / wfr2 / wfr3: no gradient output */
+
+const char* gpa_last_error(void);
+int gpa_version(void);          /* 10000*major + 100*minor + patch */
+int gpa_device_sm_count(void);  /* of the current device; <0 on error */
+
+/* Staging helper for the host binding: the reference takes float64 images
+ * (cp.asarray(image), cuGPA.py:52); the kernels read float32. */
+int gpa_cast_f64_to_f32(const double* in, float* out, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 — spatial lock-in and the adaptive (windowed-Fourier-ridge) sweep.
+ *
+ * Replaces: GPA / optGPA / vecGPA (geometric_phase_analysis.py:20-89), cuGPA.cuGPA
+ * (cuGPA.py:11-38) for the fixed reference; wfr2_grad_opt / optwfr2 / wfr2 / wfr3 /
+ * wfr2_only_lockin (geometric_phase_analysis.py:583-813) and cuGPA.wfr2_grad_opt,
+ * wfr2_grad_single, wfr2_only_lockin, wfr2_only_grad (cuGPA.py:41-202) for the sweep.
+ *
+ * The reference's FFT low-pass is a circular convolution with a periodised Gaussian; here
+ * it is a separable, truncated, real-tap circular convolution of the demodulated samples:
+ *   plane_iy(x', y) = sum_d taps_y[d+Ry] * img(x', y+d) * exp(2 pi i wy (y+d))        (pass 1)
+ *   sf(x, y)        = sum_d taps_x[d+Rx] * exp(2 pi i wx (x+d)) * plane_iy(x+d, y)    (pass 2)
+ * indices wrapped into the frame BEFORE the carrier is evaluated (as the reference does).
+ * The caller supplies the taps (host float arrays of 2R+1 entries; the Python host derives
+ * them from scipy's exact transfer function, see pygpa_b200/_taps.py).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Scratch for a sweep / fixed lock-in over `n_rows` axis-0 carriers and `n_planes` first-pass
+ * planes, keeping `planes_in_flight` (1..n_planes) planes resident at a time.  Keeping all
+ * planes resident avoids recomputing pass 1 in gpa_sweep_finalize. */
+int gpa_lockin_workspace_bytes(int N, int M, int n_rows, int n_planes, int Rx, int Ry,
+                               int planes_in_flight, size_t* bytes);
+
+/* Output precision: the arithmetic is fp32 either way; out_f64 != 0 widens on store so the
+ * host binding can hand back the reference's float64 / complex128 arrays without a CPU pass. */
+
+/* Fixed-reference lock-in, one k-vector: out[x*M+y] = (re, im) of the complex lock-in signal
+ * (float2, or double2 when out_f64).
+ * Reference: optGPA (geometric_phase_analysis.py:48-76), cuGPA (cuGPA.py:11-38). */
+int gpa_lockin_fixed(const float* img, int N, int M, double kx, double ky,
+                     const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
+                     int out_f64, void* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Running arg-max of the sweep over planes [plane_begin, plane_end):
+ *   key[x*M+y] = max(key, (float_bits(|sf|^2) << 32) | (0xFFFFFFFF - flat_index))   (64-bit atomic max)
+ * so the largest amplitude wins and, on an exact tie, the LOWEST flat index — the
+ * reference's strict-'>' first-wins rule (geometric_phase_analysis.py:806).  Candidates with
+ * |sf| == 0 never win.  The caller zero-initialises key; keys from disjoint plane ranges
+ * (other calls, other GPUs) merge with a plain integer max. */
+int gpa_sweep_argmax(const float* img, int N, int M,
+                     const double* wx_rows /*host*/, int n_rows,
+                     const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                     int plane_begin, int plane_end,
+                     const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
+                     unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
+
+/* For every pixel whose winning candidate (decoded from key) lies in planes
+ * [plane_begin, plane_end): recompute that candidate's lock-in at the pixel and its four
+ * neighbours and write
+ *   lockin[x*M+y]   = sf * exp(-2 pi i ((wx-kref_x) x + (wy-kref_y) y))          (complex, :808)
+ *   grad[(x*M+y)*2] = wrapToPi(2 (grad(-angle sf) + 2 pi (k - kref)))/2          (2 reals, :807-812)
+ *   w[c*N*M+x*M+y]  = winning k-vector component c                               ((2,N,M), :809,811)
+ *   kidx[x*M+y]     = flat candidate index, -1 where no candidate ever won
+ * Other pixels are left untouched.  lockin/grad/w are float (c64) or, with out_f64, double
+ * (c128) arrays.  grad may be NULL with grad_mode GPA_GRAD_NONE; w and kidx may be NULL.  planes_valid != 0 promises that ws still holds the planes written by
+ * gpa_sweep_argmax for exactly this plane range (all resident); otherwise pass 1 is redone. */
+int gpa_sweep_finalize(const float* img, int N, int M,
+                       const double* wx_rows /*host*/, int n_rows,
+                       const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                       int plane_begin, int plane_end, int planes_valid,
+                       const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
+                       const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
+                       int out_f64, void* lockin, void* grad, void* w, int* kidx,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* One-GPU convenience: zero key, arg-max over all planes, finalize.  key is scratch+output
+ * ([N*M] u64).  Equivalent of one call of wfr2_grad_opt (cuGPA.py:41-87) minus host copies. */
+int gpa_wfr_sweep(const float* img, int N, int M,
+                  const double* wx_rows /*host*/, int n_rows,
+                  const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                  const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
+                  double kref_x, double kref_y, int grad_mode, int out_f64,
+                  unsigned long long* key, void* lockin, void* grad, void* w, int* kidx,
+                  void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPA_B200_H */

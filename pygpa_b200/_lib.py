@@ -1,0 +1,74 @@
+"""ctypes binding of libgpa_b200.so (C ABI declared in include/gpa_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception
+is raised.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C pygpa_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpa_b200.so")
+
+c_int, c_double, c_size_t, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p
+_pd = ctypes.POINTER(ctypes.c_double)
+_pf = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes).  Device pointers are passed as c_void_p integers.
+SIGNATURES = {
+    "gpa_last_error": (ctypes.c_char_p, []),
+    "gpa_version": (c_int, []),
+    "gpa_device_sm_count": (c_int, []),
+    "gpa_cast_f64_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_lockin_workspace_bytes": (c_int, [c_int] * 7 + [ctypes.POINTER(c_size_t)]),
+    "gpa_lockin_fixed": (c_int, [c_void_p, c_int, c_int, c_double, c_double, _pf, c_int, _pf, c_int,
+                                 c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_sweep_argmax": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int,
+                                 _pf, c_int, _pf, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_sweep_finalize": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int,
+                                   _pf, c_int, _pf, c_int, c_void_p, c_double, c_double, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_wfr_sweep": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int,
+                              _pf, c_int, _pf, c_int, c_double, c_double, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+class GpaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpaError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built "
+            "(run `make -C pygpa_b200/csrc`). pygpa_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().gpa_last_error()
+        raise GpaError(f"libgpa_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def as_pd(arr):
+    return arr.ctypes.data_as(_pd)
+
+
+def as_pf(arr):
+    return arr.ctypes.data_as(_pf)

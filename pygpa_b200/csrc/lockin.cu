@@ -1,0 +1,656 @@
+// K1 — spatial lock-in and adaptive (windowed-Fourier-ridge) sweep for sm_100a.
+//
+// Reference semantics: pyGPA/geometric_phase_analysis.py:48-76 (optGPA), 763-813
+// (wfr2_grad_opt), pyGPA/cuGPA.py:41-87.  See include/gpa_b200.h for the contract and
+// DESIGN.md for the derivation.  Structure:
+//
+//   k_build_phasors   fp64 range-reduced carrier tables  e^{2 pi i w x'}  (tiny)
+//   k_pass1           plane_iy = G_y * (img . e^{2 pi i wy y})      one launch per plane chunk
+//   k_pass2<ARGMAX>   for every candidate row ix: sf = G_x * (e^{2 pi i wx x} . plane_iy),
+//                     running arg-max of |sf|^2 in registers, one 64-bit atomicMax per pixel
+//   k_pass2<STORE>    same filter, writes sf (fixed-reference lock-in)
+//   k_finalize        re-evaluates the winner at the pixel and its 4 neighbours -> lock-in
+//                     re-referenced to kref, phase gradient, k-index
+//
+// Both filter kernels share one register-blocked FIR core: each thread owns P consecutive
+// outputs along the filter axis, keeps a P-deep rotating window of complex samples in
+// registers and issues P packed FFMA2 (fma.rn.f32x2: real tap x complex sample) per tap;
+// taps come from the kernel-parameter constant bank through uniform registers.
+#include "common.cuh"
+
+namespace gpa {
+
+constexpr int kMaxTaps = 448;      // 2R+1 <= kMaxTaps  (sigma <= 49 at 4.5 sigma); param space budget
+constexpr int kP = 16;             // outputs per thread along the filter axis
+constexpr int kWarps = 8;          // warps per CTA
+constexpr int kTile = kP * kWarps; // outputs per CTA along the filter axis (128)
+constexpr int kLanes = 32;         // outputs per CTA across the filter axis
+
+struct TapTable {
+    float2 g[kMaxTaps];            // (tap, tap): packed operand of FFMA2
+};
+
+struct WList {
+    double w[224];
+};
+
+// ---------------------------------------------------------------------------------------------
+// carrier tables
+// ---------------------------------------------------------------------------------------------
+// table[i][r] = exp(2 pi i w[i] * ((r - shift) mod period)),  r in [0, len)
+__global__ void k_build_phasors(float2* __restrict__ table, double* __restrict__ w_out,
+                                const __grid_constant__ WList wl, int n_w, int len, int shift,
+                                int period) {
+    const int i = blockIdx.y;
+    if (i >= n_w) return;
+    const double w = wl.w[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) w_out[i] = w;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < len; r += gridDim.x * blockDim.x) {
+        int xs = (r - shift) % period;
+        if (xs < 0) xs += period;
+        table[(size_t)i * len + r] = phasor_turns(w * (double)xs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-blocked FIR core
+// ---------------------------------------------------------------------------------------------
+// acc[p] = sum_{d<T} g[d] * sample(p + d),  p < P.   `load(j)` returns sample j; it is called
+// for j up to T + P - 1 (one past the last sample that is used), so that index must be readable.
+template <int P, typename Load>
+__device__ __forceinline__ void fir_block(float2 (&acc)[P], const TapTable& taps, int T, Load load) {
+    float2 win[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        win[p] = load(p);
+        acc[p] = make_float2(0.f, 0.f);
+    }
+    int d0 = 0;
+    for (; d0 + P <= T; d0 += P) {
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            const float2 g = taps.g[d0 + u];
+            const float2 nxt = load(d0 + u + P);
+#pragma unroll
+            for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
+            win[u] = nxt;
+        }
+    }
+    const int rem = T - d0;
+#pragma unroll
+    for (int u = 0; u < P - 1; ++u) {
+        if (u < rem) {  // warp-uniform
+            const float2 g = taps.g[d0 + u];
+            const float2 nxt = load(d0 + u + P);
+#pragma unroll
+            for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
+            win[u] = nxt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: filter along axis 1 (contiguous) of the demodulated real image
+// ---------------------------------------------------------------------------------------------
+struct Pass1Params {
+    const float* img;     // (N, M)
+    const float2* phy;    // [n_planes][M] carrier along axis 1
+    float2* planes;       // [chunk][n_alloc][pitch]
+    size_t plane_stride;  // elements
+    int N, M, pitch, n_rows_filled /* N + 2Rx */, Rx, Ry, T /* 2Ry+1 */, plane0 /* global index of chunk plane 0 */;
+};
+
+// CTA: 32 padded rows (one per lane) x kTile output columns (warp w owns columns [w*P, w*P+P)).
+// smem: demodulated samples s[j][lane], j in [0, kTile + T), row pitch 33 float2 (conflict-free
+// reads across lanes; the transposing fill is 2-way conflicted, once per tile).
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k_pass1(const Pass1Params prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    constexpr int SP = 33;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32;            // first padded row of the tile
+    const int y0 = blockIdx.y * kTile;         // first output column
+    const int pl = blockIdx.z;                 // plane within the chunk
+    const int T = prm.T, M = prm.M, N = prm.N;
+    const int n_samp = kTile + T;              // T-1 halo + 1 spare
+    const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
+
+    int cbase = (y0 - prm.Ry) % M;
+    if (cbase < 0) cbase += M;
+    for (int rr = warp; rr < 32; rr += kWarps) {
+        int xs = (r0 + rr - prm.Rx) % N;
+        if (xs < 0) xs += N;
+        const float* __restrict__ row = prm.img + (size_t)xs * M;
+        for (int j = lane; j < n_samp; j += 32) {
+            int c = cbase + j;
+            if (c >= M) c %= M;
+            const float v = __ldg(row + c);
+            const float2 ph = __ldg(phy + c);
+            smem[j * SP + rr] = make_float2(v * ph.x, v * ph.y);
+        }
+    }
+    __syncthreads();
+
+    const float2* col = smem + (warp * kP) * SP + lane;
+    float2 acc[kP];
+    fir_block<kP>(acc, taps, T, [&](int j) { return col[j * SP]; });
+
+    const int r = r0 + lane;
+    const int y = y0 + warp * kP;
+    if (r < prm.n_rows_filled) {
+        float2* out = prm.planes + (size_t)pl * prm.plane_stride + (size_t)r * prm.pitch + y;
+#pragma unroll
+        for (int p = 0; p < kP; p += 2) {
+            if (y + p + 1 < prm.pitch) {
+                *reinterpret_cast<float4*>(out + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
+            } else if (y + p < prm.pitch) {
+                out[p] = acc[p];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: filter along axis 0 with per-candidate demodulation; arg-max or store
+// ---------------------------------------------------------------------------------------------
+struct Pass2Params {
+    const float2* planes;   // [chunk][n_alloc][pitch]
+    size_t plane_stride;
+    const float2* phx;      // [n_rows][n_alloc] carrier along axis 0, indexed by PADDED row
+    unsigned long long* key;  // ARGMAX: (N, M)
+    void* out;                // STORE:  (N, M) float2 or double2
+    int out_f64;
+    int N, M, pitch, n_alloc, T /* 2Rx+1 */;
+    int plane0;             // global plane index of chunk plane 0
+    int n_cand;             // candidates per plane (grid: n_rows, list: 1)
+    int row_c, row_p;       // phasor row  = c*row_c + plane*row_p
+    int idx_c, idx_p;       // flat index  = c*idx_c + plane*idx_p
+};
+
+enum { kArgmax = 0, kStore = 1 };
+
+// CTA: kTile output rows (warp w owns rows [w*P, w*P+P)) x 32 columns (one per lane).
+// smem: the plane tile [kTile + T][32] complex, loaded once and reused by every candidate.
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = blockIdx.x * kLanes;
+    const int x0 = blockIdx.y * kTile;
+    const int pl = blockIdx.z;
+    const int plane = prm.plane0 + pl;
+    const int T = prm.T;
+    const int n_samp = kTile + T;
+
+    {   // tile fill: rows are 256 B, fully coalesced; pitch/n_alloc padding keeps it in bounds
+        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride +
+                                         (size_t)x0 * prm.pitch + y0 + lane;
+        for (int j = warp; j < n_samp; j += kWarps) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch);
+    }
+    __syncthreads();
+
+    const float2* col = smem + (warp * kP) * kLanes + lane;
+    float best[kP];
+    int bidx[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+        best[p] = 0.f;
+        bidx[p] = 0;
+    }
+
+    for (int c = 0; c < prm.n_cand; ++c) {
+        const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc +
+                                        x0 + warp * kP;
+        float2 acc[kP];
+        fir_block<kP>(acc, taps, T, [&](int j) { return cmul(col[j * kLanes], __ldg(ph + j)); });
+        if (MODE == kArgmax) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
+                if (a2 > best[p]) {   // strict: the earlier candidate keeps exact ties
+                    best[p] = a2;
+                    bidx[p] = c;
+                }
+            }
+        } else {
+            const int y = y0 + lane;
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int x = x0 + warp * kP + p;
+                if (x < prm.N && y < prm.M) {
+                    if (prm.out_f64) static_cast<double2*>(prm.out)[(size_t)x * prm.M + y] = make_double2(acc[p].x, acc[p].y);
+                    else static_cast<float2*>(prm.out)[(size_t)x * prm.M + y] = acc[p];
+                }
+            }
+        }
+    }
+
+    if (MODE == kArgmax) {
+        const int y = y0 + lane;
+        if (y < prm.M) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int x = x0 + warp * kP + p;
+                if (x < prm.N && best[p] > 0.f) {
+                    const unsigned idx = (unsigned)(bidx[p] * prm.idx_c + plane * prm.idx_p);
+                    const unsigned long long k =
+                        ((unsigned long long)__float_as_uint(best[p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+                    atomicMax(prm.key + (size_t)x * prm.M + y, k);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: winner's lock-in, phase gradient, k-index
+// ---------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const float2* planes;
+    size_t plane_stride;
+    const float2* phx;
+    const double* wx_rows;   // device copies of the candidate axes
+    const double* wy_planes;
+    const unsigned long long* key;
+    void* lockin;  // (N, M) complex, float2 or double2
+    void* grad;    // (N, M, 2) or null
+    void* w;       // (2, N, M) winning k-vector or null
+    int* kidx;     // may be null
+    double kref_x, kref_y;
+    int N, M, pitch, n_alloc, T, Rx;
+    int plane0, plane_begin, plane_end;
+    int list_mode, n_planes;
+    int grad_mode;
+};
+
+__device__ __forceinline__ double wrap_to_pi(double v) {
+    // (v + pi) mod 2 pi - pi with a non-negative modulo: mathtools.py:72-75
+    const double two_pi = 6.283185307179586476925286766559;
+    double t = (v + 3.141592653589793238462643383279) / two_pi;
+    t -= floor(t);
+    return t * two_pi - 3.141592653589793238462643383279;
+}
+
+__device__ __forceinline__ double neg_arg_conj(float2 a, float2 b) {
+    // -arg(a * conj(b)) = phi(a) - phi(b) (mod 2 pi) with phi = -angle
+    const float re = fmaf(a.x, b.x, a.y * b.y);
+    const float im = fmaf(a.y, b.x, -a.x * b.y);
+    return -(double)atan2f(im, re);
+}
+
+template <typename T2>
+struct real_of;
+template <>
+struct real_of<float2> { using type = float; };
+template <>
+struct real_of<double2> { using type = double; };
+
+template <typename T2>   // float2: c64 / f32 outputs, double2: c128 / f64 outputs (the reference's dtypes)
+__global__ void __launch_bounds__(256)
+k_finalize(const FinalizeParams prm, const __grid_constant__ TapTable taps) {
+    using R = typename real_of<T2>::type;
+    T2* const o_lockin = static_cast<T2*>(prm.lockin);
+    R* const o_grad = static_cast<R*>(prm.grad);
+    R* const o_w = static_cast<R*>(prm.w);
+    const size_t npix = (size_t)prm.N * prm.M;
+    const int y = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int x = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= prm.N || y >= prm.M) return;
+    const size_t pix = (size_t)x * prm.M + y;
+    const unsigned long long k = prm.key[pix];
+    if ((k >> 32) == 0ull) {   // nothing ever exceeded |0|: geometric_phase_analysis.py:806 keeps the zeros
+        T2 z;
+        z.x = 0;
+        z.y = 0;
+        o_lockin[pix] = z;
+        if (o_grad) {
+            o_grad[2 * pix] = 0;
+            o_grad[2 * pix + 1] = 0;
+        }
+        if (o_w) {
+            o_w[pix] = 0;
+            o_w[npix + pix] = 0;
+        }
+        if (prm.kidx) prm.kidx[pix] = -1;
+        return;
+    }
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    int plane, row;
+    if (prm.list_mode) {
+        plane = (int)idx;
+        row = plane;
+    } else {
+        plane = (int)(idx % (unsigned)prm.n_planes);
+        row = (int)(idx / (unsigned)prm.n_planes);
+    }
+    if (plane < prm.plane_begin || plane >= prm.plane_end) return;
+
+    const int N = prm.N, M = prm.M, T = prm.T;
+    const float2* __restrict__ A = prm.planes + (size_t)(plane - prm.plane0) * prm.plane_stride;
+    const float2* __restrict__ ph = prm.phx + (size_t)row * prm.n_alloc;
+    const int ym = max(y - 1, 0), yp = min(y + 1, M - 1);
+    const bool want_grad = o_grad != nullptr && prm.grad_mode != GPA_GRAD_NONE;
+
+    // padded row r holds frame row r - Rx; S(x + e) = sum_d g[d] b(x + e + d), e in {-1,0,1}
+    float2 s_m = make_float2(0.f, 0.f), s_0 = s_m, s_p = s_m, s_ym = s_m, s_yp = s_m;
+    const int r_last = N - 1 + 2 * prm.Rx;
+    for (int j = 0; j < T + 2; ++j) {
+        const int r = x - 1 + j;
+        if (r < 0 || r > r_last) continue;
+        const float2 c = __ldg(ph + r);
+        const float2 b0 = cmul(__ldg(A + (size_t)r * prm.pitch + y), c);
+        if (j >= 1 && j <= T) {
+            const float g = taps.g[j - 1].x;
+            s_0.x = fmaf(g, b0.x, s_0.x);
+            s_0.y = fmaf(g, b0.y, s_0.y);
+            if (want_grad) {
+                const float2 bm = cmul(__ldg(A + (size_t)r * prm.pitch + ym), c);
+                const float2 bp = cmul(__ldg(A + (size_t)r * prm.pitch + yp), c);
+                s_ym.x = fmaf(g, bm.x, s_ym.x);
+                s_ym.y = fmaf(g, bm.y, s_ym.y);
+                s_yp.x = fmaf(g, bp.x, s_yp.x);
+                s_yp.y = fmaf(g, bp.y, s_yp.y);
+            }
+        }
+        if (want_grad) {
+            if (j < T) {
+                const float g = taps.g[j].x;
+                s_m.x = fmaf(g, b0.x, s_m.x);
+                s_m.y = fmaf(g, b0.y, s_m.y);
+            }
+            if (j >= 2) {
+                const float g = taps.g[j - 2].x;
+                s_p.x = fmaf(g, b0.x, s_p.x);
+                s_p.y = fmaf(g, b0.y, s_p.y);
+            }
+        }
+    }
+
+    const double dkx = prm.wx_rows[row] - prm.kref_x;
+    const double dky = prm.wy_planes[plane] - prm.kref_y;
+    const float2 rot = phasor_turns(-(dkx * (double)x + dky * (double)y));
+    {
+        const float2 v = cmul(s_0, rot);
+        T2 o;
+        o.x = v.x;
+        o.y = v.y;
+        o_lockin[pix] = o;
+    }
+    if (o_w) {
+        o_w[pix] = (R)prm.wx_rows[row];
+        o_w[npix + pix] = (R)prm.wy_planes[plane];
+    }
+    if (prm.kidx) prm.kidx[pix] = (int)idx;
+    if (want_grad) {
+        const double four_pi = 12.566370614359172953850573533118;
+        double g0, g1;
+        if (prm.grad_mode == GPA_GRAD_CENTRAL) {
+            // np.gradient: central inside, one-sided (x2 after the final doubling) at the frame edge
+            double d0, d1;
+            if (x == 0) d0 = 2.0 * neg_arg_conj(s_p, s_0);
+            else if (x == N - 1) d0 = 2.0 * neg_arg_conj(s_0, s_m);
+            else d0 = neg_arg_conj(s_p, s_m);
+            if (y == 0) d1 = 2.0 * neg_arg_conj(s_yp, s_0);
+            else if (y == M - 1) d1 = 2.0 * neg_arg_conj(s_0, s_ym);
+            else d1 = neg_arg_conj(s_yp, s_ym);
+            g0 = 0.5 * wrap_to_pi(d0 + four_pi * dkx);
+            g1 = 0.5 * wrap_to_pi(d1 + four_pi * dky);
+        } else {
+            // cuGPA.py:58-62 grad='diff': forward difference, NaN past the end
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            g0 = (x == N - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_p, s_0) + four_pi * dkx);
+            g1 = (y == M - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_yp, s_0) + four_pi * dky);
+        }
+        o_grad[2 * pix] = (R)g0;
+        o_grad[2 * pix + 1] = (R)g1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Geometry {
+    int N, M, n_rows, n_planes, Rx, Ry, Tx, Ty;
+    int pitch, n_alloc, chunk;
+    size_t plane_stride;
+    // workspace carve-up
+    double *wx_d, *wy_d;
+    float2 *phx, *phy, *planes;
+};
+
+static int plan(Geometry& g, int N, int M, int n_rows, int n_planes, int Rx, int Ry) {
+    GPA_REQUIRE(N >= 2 && M >= 2, "frame must be at least 2x2 (got %dx%d)", N, M);
+    GPA_REQUIRE(n_rows >= 1 && n_planes >= 1, "empty candidate set");
+    GPA_REQUIRE(Rx >= 0 && Ry >= 0 && 2 * Rx + 1 <= kMaxTaps && 2 * Ry + 1 <= kMaxTaps,
+                "filter radius out of range (Rx=%d Ry=%d, at most %d taps)", Rx, Ry, kMaxTaps);
+    GPA_REQUIRE(2 * Rx + 1 <= N && 2 * Ry + 1 <= M,
+                "truncated filter (2R+1 = %d x %d) must fit the frame (%d x %d)", 2 * Rx + 1, 2 * Ry + 1, N, M);
+    g.N = N; g.M = M; g.n_rows = n_rows; g.n_planes = n_planes;
+    g.Rx = Rx; g.Ry = Ry; g.Tx = 2 * Rx + 1; g.Ty = 2 * Ry + 1;
+    g.pitch = (int)align_up((size_t)M, 32);
+    g.n_alloc = ceil_div(N, kTile) * kTile + g.Tx;   // every pass-2 tile reads kTile + Tx rows
+    g.plane_stride = (size_t)g.n_alloc * g.pitch;
+    return GPA_OK;
+}
+
+static size_t carve(Geometry& g, void* ws, size_t ws_bytes, int chunk) {
+    Arena a(ws, ws_bytes);
+    g.wx_d = a.take<double>(g.n_rows);
+    g.wy_d = a.take<double>(g.n_planes);
+    g.phx = a.take<float2>((size_t)g.n_rows * g.n_alloc);
+    g.phy = a.take<float2>((size_t)g.n_planes * g.M);
+    g.planes = a.take<float2>((size_t)chunk * g.plane_stride);
+    g.chunk = chunk;
+    return a.off;
+}
+
+// largest number of resident planes that fits ws_bytes
+static int fit_chunk(Geometry& g, void* ws, size_t ws_bytes, int want) {
+    size_t fixed = carve(g, nullptr, 0, 0);
+    size_t per_plane = g.plane_stride * sizeof(float2);
+    if (ws_bytes < fixed + per_plane + 256) return 0;
+    size_t c = (ws_bytes - fixed - 256) / per_plane;
+    int chunk = (int)(c < (size_t)want ? c : (size_t)want);
+    carve(g, ws, ws_bytes, chunk);
+    return chunk;
+}
+
+static int fill_taps(TapTable& t, const float* taps, int R) {
+    GPA_REQUIRE(taps != nullptr, "taps pointer is null");
+    std::memset(&t, 0, sizeof(t));
+    for (int i = 0; i < 2 * R + 1; ++i) t.g[i] = make_float2(taps[i], taps[i]);
+    return GPA_OK;
+}
+
+static int build_tables(const Geometry& g, const double* wx_rows, const double* wy_planes, cudaStream_t st) {
+    const int per = (int)(sizeof(WList) / sizeof(double));
+    for (int b = 0; b < g.n_rows; b += per) {
+        WList wl;
+        int n = g.n_rows - b < per ? g.n_rows - b : per;
+        std::memcpy(wl.w, wx_rows + b, n * sizeof(double));
+        dim3 grid(ceil_div(g.n_alloc, 256), n);
+        k_build_phasors<<<grid, 256, 0, st>>>(g.phx + (size_t)b * g.n_alloc, g.wx_d + b, wl, n, g.n_alloc, g.Rx, g.N);
+    }
+    for (int b = 0; b < g.n_planes; b += per) {
+        WList wl;
+        int n = g.n_planes - b < per ? g.n_planes - b : per;
+        std::memcpy(wl.w, wy_planes + b, n * sizeof(double));
+        dim3 grid(ceil_div(g.M, 256), n);
+        k_build_phasors<<<grid, 256, 0, st>>>(g.phy + (size_t)b * g.M, g.wy_d + b, wl, n, g.M, 0, g.M);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+static int launch_pass1(const Geometry& g, const float* img, const TapTable& ty, int plane0, int count, cudaStream_t st) {
+    Pass1Params p;
+    p.img = img; p.phy = g.phy; p.planes = g.planes; p.plane_stride = g.plane_stride;
+    p.N = g.N; p.M = g.M; p.pitch = g.pitch; p.n_rows_filled = g.N + 2 * g.Rx;
+    p.Rx = g.Rx; p.Ry = g.Ry; p.T = g.Ty; p.plane0 = plane0;
+    const size_t smem = (size_t)(kTile + g.Ty) * 33 * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(p.n_rows_filled, 32), ceil_div(g.pitch, kTile), count);
+    k_pass1<<<grid, kWarps * 32, smem, st>>>(p, ty);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+template <int MODE>
+static int launch_pass2(const Geometry& g, const TapTable& tx, int plane0, int count, int cand_mode,
+                        unsigned long long* key, void* out, int out_f64, cudaStream_t st) {
+    Pass2Params p;
+    p.planes = g.planes; p.plane_stride = g.plane_stride; p.phx = g.phx; p.key = key; p.out = out; p.out_f64 = out_f64;
+    p.N = g.N; p.M = g.M; p.pitch = g.pitch; p.n_alloc = g.n_alloc; p.T = g.Tx; p.plane0 = plane0;
+    if (cand_mode == GPA_CAND_GRID) {
+        p.n_cand = g.n_rows; p.row_c = 1; p.row_p = 0; p.idx_c = g.n_planes; p.idx_p = 1;
+    } else {
+        p.n_cand = 1; p.row_c = 0; p.row_p = 1; p.idx_c = 0; p.idx_p = 1;
+    }
+    const size_t smem = (size_t)(kTile + g.Tx) * kLanes * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(g.pitch / kLanes, ceil_div(g.N, kTile), count);
+    k_pass2<MODE><<<grid, kWarps * 32, smem, st>>>(p, tx);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+static int check_common(const float* img, const double* wx_rows, const double* wy_planes, int n_rows,
+                        int n_planes, int cand_mode, int plane_begin, int plane_end, void* ws) {
+    GPA_REQUIRE(img && wx_rows && wy_planes && ws, "null pointer argument");
+    GPA_REQUIRE(cand_mode == GPA_CAND_GRID || cand_mode == GPA_CAND_LIST, "bad cand_mode %d", cand_mode);
+    GPA_REQUIRE(cand_mode == GPA_CAND_GRID || n_rows == n_planes, "list mode needs n_rows == n_planes");
+    GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes,
+                "bad plane range [%d, %d) of %d", plane_begin, plane_end, n_planes);
+    GPA_REQUIRE(cand_mode == GPA_CAND_LIST || (long long)n_rows * n_planes < 0x7fffffffLL, "too many candidates");
+    return GPA_OK;
+}
+
+}  // namespace gpa
+
+using namespace gpa;
+
+extern "C" int gpa_lockin_workspace_bytes(int N, int M, int n_rows, int n_planes, int Rx, int Ry,
+                                          int planes_in_flight, size_t* bytes) {
+    Geometry g;
+    int rc = plan(g, N, M, n_rows, n_planes, Rx, Ry);
+    if (rc) return rc;
+    GPA_REQUIRE(bytes != nullptr, "bytes is null");
+    GPA_REQUIRE(planes_in_flight >= 1 && planes_in_flight <= n_planes, "planes_in_flight out of range");
+    *bytes = carve(g, nullptr, 0, planes_in_flight) + 256;
+    return GPA_OK;
+}
+
+extern "C" int gpa_lockin_fixed(const float* img, int N, int M, double kx, double ky,
+                                const float* taps_x, int Rx, const float* taps_y, int Ry,
+                                int out_f64, void* out, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = plan(g, N, M, 1, 1, Rx, Ry);
+    if (rc) return rc;
+    GPA_REQUIRE(img && out && ws, "null pointer argument");
+    if (fit_chunk(g, ws, ws_bytes, 1) < 1) {
+        set_error("workspace too small (%zu bytes)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    TapTable tx, ty;
+    if ((rc = fill_taps(tx, taps_x, Rx)) || (rc = fill_taps(ty, taps_y, Ry))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = build_tables(g, &kx, &ky, st))) return rc;
+    if ((rc = launch_pass1(g, img, ty, 0, 1, st))) return rc;
+    return launch_pass2<kStore>(g, tx, 0, 1, GPA_CAND_GRID, nullptr, out, out_f64, st);
+}
+
+extern "C" int gpa_sweep_argmax(const float* img, int N, int M, const double* wx_rows, int n_rows,
+                                const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
+                                int plane_end, const float* taps_x, int Rx, const float* taps_y, int Ry,
+                                unsigned long long* key, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = plan(g, N, M, n_rows, n_planes, Rx, Ry);
+    if (rc) return rc;
+    if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
+    GPA_REQUIRE(key != nullptr, "key is null");
+    if (plane_begin == plane_end) return GPA_OK;
+    const int chunk = fit_chunk(g, ws, ws_bytes, plane_end - plane_begin);
+    if (chunk < 1) {
+        set_error("workspace too small (%zu bytes)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    TapTable tx, ty;
+    if ((rc = fill_taps(tx, taps_x, Rx)) || (rc = fill_taps(ty, taps_y, Ry))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = build_tables(g, wx_rows, wy_planes, st))) return rc;
+    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
+        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
+        if ((rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
+        if ((rc = launch_pass2<kArgmax>(g, tx, p0, cnt, cand_mode, key, nullptr, 0, st))) return rc;
+    }
+    return GPA_OK;
+}
+
+extern "C" int gpa_sweep_finalize(const float* img, int N, int M, const double* wx_rows, int n_rows,
+                                  const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
+                                  int plane_end, int planes_valid, const float* taps_x, int Rx,
+                                  const float* taps_y, int Ry, const unsigned long long* key, double kref_x,
+                                  double kref_y, int grad_mode, int out_f64, void* lockin, void* grad, void* w,
+                                  int* kidx, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = plan(g, N, M, n_rows, n_planes, Rx, Ry);
+    if (rc) return rc;
+    if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
+    GPA_REQUIRE(key && lockin, "null output pointer");
+    GPA_REQUIRE(grad_mode == GPA_GRAD_CENTRAL || grad_mode == GPA_GRAD_FORWARD || grad_mode == GPA_GRAD_NONE,
+                "bad grad_mode %d", grad_mode);
+    GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr, "grad is null but a gradient was requested");
+    if (plane_begin == plane_end) return GPA_OK;
+    const int chunk = fit_chunk(g, ws, ws_bytes, plane_end - plane_begin);
+    if (chunk < 1) {
+        set_error("workspace too small (%zu bytes)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    const bool reuse = planes_valid && chunk == plane_end - plane_begin;
+    TapTable tx, ty;
+    if ((rc = fill_taps(tx, taps_x, Rx)) || (rc = fill_taps(ty, taps_y, Ry))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!reuse && (rc = build_tables(g, wx_rows, wy_planes, st))) return rc;
+    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
+        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
+        if (!reuse && (rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
+        FinalizeParams f;
+        f.planes = g.planes; f.plane_stride = g.plane_stride; f.phx = g.phx;
+        f.wx_rows = g.wx_d; f.wy_planes = g.wy_d; f.key = key;
+        f.lockin = lockin; f.grad = grad_mode == GPA_GRAD_NONE ? nullptr : grad; f.w = w; f.kidx = kidx;
+        f.kref_x = kref_x; f.kref_y = kref_y;
+        f.N = N; f.M = M; f.pitch = g.pitch; f.n_alloc = g.n_alloc; f.T = g.Tx; f.Rx = Rx;
+        f.plane0 = p0; f.plane_begin = p0; f.plane_end = p0 + cnt;
+        f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
+        dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
+        if (out_f64) k_finalize<double2><<<grid, 256, 0, st>>>(f, tx);
+        else k_finalize<float2><<<grid, 256, 0, st>>>(f, tx);
+        GPA_CHECK_CUDA(cudaGetLastError());
+    }
+    return GPA_OK;
+}
+
+extern "C" int gpa_wfr_sweep(const float* img, int N, int M, const double* wx_rows, int n_rows,
+                             const double* wy_planes, int n_planes, int cand_mode, const float* taps_x, int Rx,
+                             const float* taps_y, int Ry, double kref_x, double kref_y, int grad_mode,
+                             int out_f64, unsigned long long* key, void* lockin, void* grad, void* w, int* kidx,
+                             void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(key != nullptr && N > 0 && M > 0, "key is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GPA_CHECK_CUDA(cudaMemsetAsync(key, 0, (size_t)N * M * sizeof(unsigned long long), st));
+    int rc = gpa_sweep_argmax(img, N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, 0, n_planes, taps_x,
+                              Rx, taps_y, Ry, key, ws, ws_bytes, st);
+    if (rc) return rc;
+    return gpa_sweep_finalize(img, N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, 0, n_planes, 1, taps_x,
+                              Rx, taps_y, Ry, key, kref_x, kref_y, grad_mode, out_f64, lockin, grad, w, kidx, ws,
+                              ws_bytes, st);
+}

@@ -1,0 +1,201 @@
+"""Device-side driver of the lock-in / sweep kernels (K1).
+
+PyTorch is used for device buffers, streams and pinned host memory only; every kernel
+that runs is one of libgpa_b200.so's.  Functions here take and return torch CUDA tensors;
+the NumPy-in / NumPy-out mirrors of the reference API live in cuGPA.py and
+geometric_phase_analysis.py.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._taps import DEFAULT_TRUNC, axis_taps
+
+GRAD_CENTRAL, GRAD_FORWARD, GRAD_NONE = 0, 1, 2
+CAND_GRID, CAND_LIST = 0, 1
+
+_workspaces = {}
+launch_count = 0     # kernels of ours enqueued so far (bench.py reports the delta)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.GpaError("pygpa_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _lib.load()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device (the C ABI never allocates)."""
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[device] = None
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def release_workspaces():
+    _workspaces.clear()
+
+
+def image_to_device(image, device=None):
+    """Host image (any real dtype) -> contiguous float32 CUDA tensor, cast on the device."""
+    device = device or require_cuda()
+    if isinstance(image, torch.Tensor):
+        t = image.to(device)
+        return t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
+    arr = np.ascontiguousarray(image)
+    if arr.ndim != 2:
+        raise ValueError("image must be 2-D")
+    if np.iscomplexobj(arr):
+        raise TypeError("image must be real")
+    if arr.dtype == np.float32:
+        return torch.from_numpy(arr).to(device, non_blocking=True)
+    if arr.dtype != np.float64:
+        arr = arr.astype(np.float64)
+    staged = torch.from_numpy(arr).to(device, non_blocking=True)
+    out = torch.empty(arr.shape, dtype=torch.float32, device=device)
+    lib = _lib.load()
+    _lib.check(lib.gpa_cast_f64_to_f32(_ptr(staged), _ptr(out), arr.size, _stream()))
+    _count(1)
+    return out
+
+
+def _count(n):
+    global launch_count
+    launch_count += n
+
+
+def _plan_planes(n, m, n_rows, n_planes, rx, ry, device, planes_in_flight):
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+
+    def need(p):
+        _lib.check(lib.gpa_lockin_workspace_bytes(n, m, n_rows, n_planes, rx, ry, p, ctypes.byref(nbytes)))
+        return nbytes.value
+    if planes_in_flight is None:
+        free, _total = torch.cuda.mem_get_info(device)
+        cached = _workspaces.get(device)
+        budget = int(0.6 * free) + (cached.numel() if cached is not None else 0)
+        base, full = need(1), need(n_planes)
+        if full <= budget or n_planes == 1:
+            planes_in_flight = n_planes
+        else:
+            per = (full - base) // (n_planes - 1)
+            planes_in_flight = int(max(1, min(n_planes, (budget - base) // per + 1)))
+    return planes_in_flight, need(planes_in_flight)
+
+
+def lockin_fixed(img_dev, kvec, sigma, trunc=DEFAULT_TRUNC, out_f64=False):
+    """Fixed-reference lock-in of a float32 CUDA image; returns a complex CUDA tensor (N, M)."""
+    device = img_dev.device
+    lib = _lib.load()
+    n, m = img_dev.shape
+    tx, rx = axis_taps(n, sigma, trunc)
+    ty, ry = axis_taps(m, sigma, trunc)
+    _p, nbytes = _plan_planes(n, m, 1, 1, rx, ry, device, 1)
+    ws = workspace(nbytes, device)
+    out = torch.empty((n, m), dtype=torch.complex128 if out_f64 else torch.complex64, device=device)
+    _lib.check(lib.gpa_lockin_fixed(_ptr(img_dev), n, m, float(kvec[0]), float(kvec[1]),
+                                    _lib.as_pf(tx), rx, _lib.as_pf(ty), ry, int(out_f64), _ptr(out),
+                                    _ptr(ws), ws.numel(), _stream()))
+    _count(4)
+    return out
+
+
+class SweepPlan:
+    """Geometry + scratch of one sweep call (candidate axes, taps, workspace)."""
+
+    def __init__(self, shape, wx_rows, wy_planes, sigma, cand_mode=CAND_GRID, trunc=DEFAULT_TRUNC,
+                 planes_in_flight=None, device=None):
+        self.device = device or require_cuda()
+        self.n, self.m = int(shape[0]), int(shape[1])
+        self.wx = np.ascontiguousarray(wx_rows, dtype=np.float64)
+        self.wy = np.ascontiguousarray(wy_planes, dtype=np.float64)
+        if self.wx.ndim != 1 or self.wy.ndim != 1 or self.wx.size == 0 or self.wy.size == 0:
+            raise ValueError("candidate axes must be non-empty 1-D arrays")
+        self.cand_mode = cand_mode
+        self.tx, self.rx = axis_taps(self.n, sigma, trunc)
+        self.ty, self.ry = axis_taps(self.m, sigma, trunc)
+        self.in_flight, self.ws_bytes = _plan_planes(self.n, self.m, self.wx.size, self.wy.size,
+                                                     self.rx, self.ry, self.device, planes_in_flight)
+        self.n_cand = self.wx.size * self.wy.size if cand_mode == CAND_GRID else self.wy.size
+
+    def _geom(self):
+        return (self.n, self.m, _lib.as_pd(self.wx), self.wx.size, _lib.as_pd(self.wy), self.wy.size, self.cand_mode)
+
+    def _taps(self):
+        return (_lib.as_pf(self.tx), self.rx, _lib.as_pf(self.ty), self.ry)
+
+    def argmax(self, img_dev, key, plane_begin=0, plane_end=None):
+        """key (N, M) int64 CUDA tensor, updated in place with this plane range's candidates."""
+        lib = _lib.load()
+        plane_end = self.wy.size if plane_end is None else plane_end
+        ws = workspace(self.ws_bytes, self.device)
+        _lib.check(lib.gpa_sweep_argmax(_ptr(img_dev), *self._geom(), plane_begin, plane_end, *self._taps(),
+                                        _ptr(key), _ptr(ws), ws.numel(), _stream()))
+        chunks = -(-(plane_end - plane_begin) // self.in_flight) if plane_end > plane_begin else 0
+        _count(2 + 2 * chunks)
+
+    def finalize(self, img_dev, key, kref, grad_mode=GRAD_CENTRAL, out_f64=False, want_w=False, want_kidx=True,
+                 plane_begin=0, plane_end=None, planes_valid=False, out=None):
+        lib = _lib.load()
+        plane_end = self.wy.size if plane_end is None else plane_end
+        n, m, dev = self.n, self.m, self.device
+        real = torch.float64 if out_f64 else torch.float32
+        cplx = torch.complex128 if out_f64 else torch.complex64
+        if out is None:
+            out = {}
+            full = plane_begin == 0 and plane_end == self.wy.size
+            make = torch.empty if full else torch.zeros
+            out["lockin"] = make((n, m), dtype=cplx, device=dev)
+            out["grad"] = make((n, m, 2), dtype=real, device=dev) if grad_mode != GRAD_NONE else None
+            out["w"] = make((2, n, m), dtype=real, device=dev) if want_w else None
+            out["kidx"] = make((n, m), dtype=torch.int32, device=dev) if want_kidx else None
+        ws = workspace(self.ws_bytes, self.device)
+        _lib.check(lib.gpa_sweep_finalize(_ptr(img_dev), *self._geom(), plane_begin, plane_end, int(planes_valid),
+                                          *self._taps(), _ptr(key), float(kref[0]), float(kref[1]), grad_mode,
+                                          int(out_f64), _ptr(out["lockin"]), _ptr(out.get("grad")),
+                                          _ptr(out.get("w")), _ptr(out.get("kidx")), _ptr(ws), ws.numel(), _stream()))
+        chunks = -(-(plane_end - plane_begin) // self.in_flight) if plane_end > plane_begin else 0
+        reuse = planes_valid and chunks == 1
+        _count(chunks if reuse else 2 + 2 * chunks)
+        return out
+
+    def run(self, img_dev, kref, grad_mode=GRAD_CENTRAL, out_f64=False, want_w=False, want_kidx=True):
+        """Whole sweep on this GPU: zero key, arg-max over all planes, finalize."""
+        lib = _lib.load()
+        n, m, dev = self.n, self.m, self.device
+        real = torch.float64 if out_f64 else torch.float32
+        out = {"key": torch.empty((n, m), dtype=torch.int64, device=dev),
+               "lockin": torch.empty((n, m), dtype=torch.complex128 if out_f64 else torch.complex64, device=dev),
+               "grad": torch.empty((n, m, 2), dtype=real, device=dev) if grad_mode != GRAD_NONE else None,
+               "w": torch.empty((2, n, m), dtype=real, device=dev) if want_w else None,
+               "kidx": torch.empty((n, m), dtype=torch.int32, device=dev) if want_kidx else None}
+        ws = workspace(self.ws_bytes, dev)
+        _lib.check(lib.gpa_wfr_sweep(_ptr(img_dev), *self._geom(), *self._taps(), float(kref[0]), float(kref[1]),
+                                     grad_mode, int(out_f64), _ptr(out["key"]), _ptr(out["lockin"]),
+                                     _ptr(out["grad"]), _ptr(out["w"]), _ptr(out["kidx"]), _ptr(ws), ws.numel(),
+                                     _stream()))
+        chunks = -(-self.wy.size // self.in_flight)
+        _count(2 + 2 * chunks + (1 if chunks == 1 else 2 + 2 * chunks))
+        return out
+
+
+def grid_axes(kx, ky, kw, kstep):
+    """The reference's candidate axes, verbatim NumPy expression because the lengths are
+    rounding dependent (geometric_phase_analysis.py:803-804)."""
+    return np.arange(kx - kw, kx + kw, kstep), np.arange(ky - kw, ky + kw, kstep)
