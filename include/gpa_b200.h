@@ -53,6 +53,13 @@ const char* gpa_last_error(void);
 int gpa_version(void);          /* 10000*major + 100*minor + patch */
 int gpa_device_sm_count(void);  /* of the current device; <0 on error */
 
+/* Per-kernel timing for benchmarks: when enabled every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  gpa_profile_read sums the recorded durations of
+ * the kernel called `kernel` ("k_pass1", "k_pass2_argmax", "k_finalize", ...), synchronising
+ * on them, and optionally clears the record. */
+int gpa_profile_enable(int on);
+int gpa_profile_read(const char* kernel, double* total_ms, int* launches, int reset);
+
 /* Staging helper for the host binding: the reference takes float64 images
  * (cp.asarray(image), cuGPA.py:52); the kernels read float32. */
 int gpa_cast_f64_to_f32(const double* in, float* out, size_t n, void* stream);

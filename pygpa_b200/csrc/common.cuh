@@ -30,6 +30,17 @@ void set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
+// Optional per-kernel timing (CUDA events on the launch stream), off by default.
+// bench.py turns it on to report the dominant kernel's live duration.
+struct KernelTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    bool on;
+    KernelTimer(const char* name, cudaStream_t stream);
+    ~KernelTimer();
+    const char* name;
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -495,6 +495,7 @@ static int launch_pass1(const Geometry& g, const float* img, const TapTable& ty,
         attr_set = true;
     }
     dim3 grid(ceil_div(p.n_rows_filled, 32), ceil_div(g.pitch, kTile), count);
+    KernelTimer timer("k_pass1", st);
     k_pass1<<<grid, kWarps * 32, smem, st>>>(p, ty);
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
@@ -518,6 +519,7 @@ static int launch_pass2(const Geometry& g, const TapTable& tx, int plane0, int c
         attr_set = true;
     }
     dim3 grid(g.pitch / kLanes, ceil_div(g.N, kTile), count);
+    KernelTimer timer(MODE == kArgmax ? "k_pass2_argmax" : "k_pass2_store", st);
     k_pass2<MODE><<<grid, kWarps * 32, smem, st>>>(p, tx);
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
@@ -632,6 +634,7 @@ extern "C" int gpa_sweep_finalize(const float* img, int N, int M, const double* 
         f.plane0 = p0; f.plane_begin = p0; f.plane_end = p0 + cnt;
         f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
         dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
+        KernelTimer timer("k_finalize", st);
         if (out_f64) k_finalize<double2><<<grid, 256, 0, st>>>(f, tx);
         else k_finalize<float2><<<grid, 256, 0, st>>>(f, tx);
         GPA_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,71 @@
+"""Host-side logic that needs no GPU: taps, candidate axes, argument handling, hygiene."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+import torch
+
+import oracle
+from conftest import ROOT
+from pygpa_b200 import _lib, _taps, cuGPA, engine, synth
+
+
+@pytest.mark.parametrize("n,m,sigma", [(64, 48, 4.0), (200, 256, 10), (33, 40, 2.5)])
+def test_taps_reproduce_scipy_fourier_gaussian(n, m, sigma):
+    tx, rx = _taps.axis_taps(n, sigma)
+    ty, ry = _taps.axis_taps(m, sigma)
+    kernel = np.fft.ifft2(ndi.fourier_gaussian(np.ones((n, m)), sigma)).real
+    sub = kernel[np.ix_(np.arange(-rx, rx + 1) % n, np.arange(-ry, ry + 1) % m)]
+    assert np.abs(np.outer(tx, ty) - sub).max() < 1e-7 * kernel.max() + 1e-9
+    assert rx == min(int(np.ceil(4.5 * sigma)), (n - 1) // 2)
+
+
+def test_taps_clamped_to_frame_and_limited():
+    t, r = _taps.axis_taps(21, 10)
+    assert r == 10 and len(t) == 21 and abs(t.sum() - 1) < 1e-6      # whole circle: exact filter
+    with pytest.raises(ValueError):
+        _taps.axis_taps(4096, 60)
+
+
+def test_candidate_axes_match_oracle_expression():
+    ks = synth.primary_ks(0.1, 7.0, 3)
+    kw = np.linalg.norm(ks, axis=1).mean() / 2.5
+    for k in ks:
+        for kstep in (kw / 3, 2 * kw / 21, 2 * kw / 20.5):
+            a = engine.grid_axes(k[0], k[1], kw, kstep)
+            b = oracle.candidate_axes(k[0], k[1], kw, kstep)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for n in (7, 21, 41):
+        kw, kstep = synth.sweep_params(ks, n)
+        wx, wy = engine.grid_axes(ks[0][0], ks[0][1], kw, kstep)
+        assert len(wx) == n and len(wy) == n
+
+
+def test_grad_argument_handling():
+    assert cuGPA._grad_mode(None) == engine.GRAD_CENTRAL
+    assert cuGPA._grad_mode('diff') == engine.GRAD_FORWARD
+    with pytest.raises(NotImplementedError):
+        cuGPA._grad_mode(lambda p: np.gradient(p))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(_lib.GpaError):
+        cuGPA.wfr2_grad_opt(np.zeros((32, 32)), 3, 0.1, 0.0, 0.02, 0.01)
+
+
+def test_synth_is_deterministic():
+    a = synth.make_config('C2', size=64, n_grid=5)
+    b = synth.make_config('C2', size=64, n_grid=5)
+    assert np.array_equal(a['image'], b['image']) and abs(a['image'].mean()) < 1e-12
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|/root/reference|_refimport", re.M)
+    for dirpath, _dirs, files in os.walk(os.path.join(ROOT, "pygpa_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(text), f"{f} references the oracle / reference"

@@ -1,0 +1,232 @@
+"""Parity of the CUDA lock-in / adaptive sweep (K1) with the oracle and the reference-made
+golden fixtures.  Needs a B200; everything goes through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+from parity import NEAR_TIE, check_sweep, wrap
+from pygpa_b200 import cuGPA, engine, synth
+from pygpa_b200 import geometric_phase_analysis as GPA
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def noisy_case():
+    shape = (160, 128)
+    ks = synth.primary_ks(0.1, 7.0, 3)
+    u = synth.smooth_random_field(shape, 0.1, 5)
+    img = synth.lattice_image(shape, ks, u, noise=0.3, seed=6)
+    img -= img.mean()
+    kw, kstep = synth.sweep_params(ks, 7)
+    return dict(img=img, ks=ks, sigma=5, kw=kw, kstep=kstep)
+
+
+def test_golden_fixture_all_peaks():
+    g = load_golden("sweep_64x48.npz")
+    img, ks = g["in_image"], g["in_ks"]
+    sigma, kw, kstep = int(g["in_sigma"]), float(g["in_kw"]), float(g["in_kstep"])
+    for i, k in enumerate(ks):
+        diag = oracle.wfr_sweep(img, sigma, k[0], k[1], kw, kstep, return_diag=True)
+        ref = dict(lockin=g["out_lockin"][i], w=g["out_w"][i], grad=g["out_grad"][i],
+                   amp1=diag["amp1"], amp2=diag["amp2"])
+        got = cuGPA.wfr2_grad_opt(img, sigma, k[0], k[1], kw, kstep)
+        assert got["lockin"].dtype == np.complex128 and got["lockin"].shape == img.shape
+        assert got["w"].shape == (2,) + img.shape and got["grad"].shape == img.shape + (2,)
+        check_sweep(got, ref)
+    got = GPA.optwfr2(img, sigma, ks[0][0], ks[0][1], kw, kstep)
+    ref = dict(lockin=g["out_optwfr2_lockin"], w=g["out_optwfr2_w"], amp1=diag["amp1"] * 0 + 1, amp2=diag["amp2"] * 0)
+    assert set(got) == {"lockin", "w"}
+    diag0 = oracle.wfr_sweep(img, sigma, ks[0][0], ks[0][1], kw, kstep, return_diag=True, want_grad=False)
+    ref["amp1"], ref["amp2"] = diag0["amp1"], diag0["amp2"]
+    check_sweep(got, ref, check_grad=False)
+
+
+@pytest.mark.parametrize("peak", [0, 1, 2])
+def test_oracle_parity_nonsquare(noisy_case, peak):
+    c = noisy_case
+    k = c["ks"][peak]
+    ref = oracle.wfr_sweep(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"], return_diag=True)
+    got = cuGPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    stats = check_sweep(got, ref)
+    assert stats["frac_mismatch"] < 1e-3
+
+
+def test_forward_difference_gradient_mode(noisy_case):
+    c = noisy_case
+    k = c["ks"][0]
+    ref = oracle.wfr_sweep(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"], grad_mode='diff', return_diag=True)
+    got = cuGPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"], grad='diff')
+    assert np.isnan(got["grad"][-1, :, 0]).all() and np.isnan(got["grad"][:, -1, 1]).all()
+    check_sweep(got, ref)
+    only = cuGPA.wfr2_only_grad(c["img"], c["sigma"], tuple(k), c["kw"], c["kstep"], grad='diff')
+    assert np.array_equal(np.isnan(only), np.isnan(got["grad"]))
+    with pytest.raises(NotImplementedError):
+        cuGPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"], grad=np.gradient)
+
+
+def test_config2_quarter_size_near_tie_accounting():
+    """C2 lattice at 256^2 with the full 21x21 grid: every k mismatch must sit on a near-tie."""
+    cfg = synth.make_config('C2', size=256)
+    k = cfg["ks"][0]
+    ref = oracle.wfr_sweep(cfg["image"], cfg["sigma"], k[0], k[1], cfg["kw"], cfg["kstep"], return_diag=True)
+    assert len(ref["wxs"]) == 21 and len(ref["wys"]) == 21
+    got = cuGPA.wfr2_grad_opt(cfg["image"], cfg["sigma"], k[0], k[1], cfg["kw"], cfg["kstep"])
+    stats = check_sweep(got, ref)
+    assert stats["frac_mismatch"] < 1e-3 and stats["phase_err"] < 1e-3
+    near = ((ref["amp1"] - ref["amp2"]) / ref["amp1"] < NEAR_TIE).mean()
+    assert stats["frac_mismatch"] <= near
+
+
+def test_variants_and_single(noisy_case):
+    c = noisy_case
+    k = c["ks"][1]
+    full = cuGPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    single = cuGPA.wfr2_grad_single(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    assert set(single) == {"lockin", "grad"}
+    assert np.array_equal(single["lockin"], full["lockin"]) and np.array_equal(single["grad"], full["grad"])
+    assert np.array_equal(cuGPA.wfr2_only_lockin(c["img"], c["sigma"], tuple(k), c["kw"], c["kstep"]), full["lockin"])
+    assert np.array_equal(GPA.wfr2_only_lockin(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"]), full["lockin"])
+    r = GPA.wfr(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    assert np.array_equal(r["wx"], full["w"][0]) and np.allclose(r["r"], np.abs(full["lockin"]))
+
+
+def test_fixed_reference_lockin(noisy_case):
+    c = noisy_case
+    for k in c["ks"]:
+        ref = oracle.lockin_fixed(c["img"], k, 6)
+        for got in (GPA.optGPA(c["img"], k, 6), GPA.GPA(c["img"], k[0], k[1], 6), np.asarray(cuGPA.cuGPA(c["img"], k, 6))):
+            assert got.dtype == np.complex128
+            assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
+    stack = GPA.vecGPA(c["img"], c["ks"], 6)
+    assert stack.shape == (3,) + c["img"].shape
+    g = load_golden("fixed_64x64.npz")
+    got = np.stack([GPA.optGPA(g["in_image"], k, int(g["in_sigma"])) for k in g["in_ks"]])
+    assert np.abs(got - g["out_lockin"]).max() < 1e-4 * np.abs(g["out_lockin"]).max()
+    strong = np.abs(g["out_lockin"]) > 0.05 * np.abs(g["out_lockin"]).max()
+    assert np.abs(np.angle(got * np.conj(g["out_lockin"])))[strong].max() < 1e-3
+
+
+def test_wfr3_candidate_list():
+    g = load_golden("wfr3_64x48.npz")
+    got = GPA.wfr3(g["in_image"], int(g["in_sigma"]), g["in_klist"], g["in_kref"])
+    diag = oracle.wfr_sweep_klist(g["in_image"], int(g["in_sigma"]), g["in_klist"], g["in_kref"],
+                                  want_grad=False, return_diag=True)
+    ref = dict(lockin=g["out_lockin"], w=g["out_w"], amp1=diag["amp1"], amp2=diag["amp2"])
+    check_sweep(got, ref, check_grad=False)
+
+
+def _run_device(img, plan, kref, **kw):
+    return plan.run(img, kref, **kw)
+
+
+def test_plane_chunking_and_range_merge_are_bit_exact(noisy_case):
+    """Resident-plane chunking and splitting the plane range over several calls (the multi-GPU
+    k-grid sharding) must not change a single bit."""
+    c = noisy_case
+    dev = engine.require_cuda()
+    img = engine.image_to_device(c["img"], dev)
+    k = c["ks"][2]
+    wxs, wys = engine.grid_axes(k[0], k[1], c["kw"], c["kstep"])
+    full = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev).run(img, k, want_w=True)
+    chunked = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], planes_in_flight=3, device=dev).run(img, k, want_w=True)
+    for key in ("key", "lockin", "grad", "w", "kidx"):
+        assert torch.equal(torch.view_as_real(full[key]) if full[key].is_complex() else full[key],
+                           torch.view_as_real(chunked[key]) if chunked[key].is_complex() else chunked[key]), key
+    # two "ranks": planes [0,3) and [3,ny)
+    plan = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev)
+    keys = []
+    for lo, hi in ((0, 3), (3, len(wys))):
+        kk = torch.zeros(img.shape, dtype=torch.int64, device=dev)
+        plan.argmax(img, kk, lo, hi)
+        keys.append(kk)
+    # keys are unsigned 64-bit with the top bit clear (|sf|^2 >= 0), so a signed max is the same
+    merged = torch.maximum(keys[0], keys[1])
+    assert torch.equal(merged, full["key"])
+    parts = [plan.finalize(img, merged, k, plane_begin=lo, plane_end=hi, want_w=True) for lo, hi in ((0, 3), (3, len(wys)))]
+    assert torch.equal(torch.view_as_real(parts[0]["lockin"] + parts[1]["lockin"]), torch.view_as_real(full["lockin"]))
+    assert torch.equal(parts[0]["grad"] + parts[1]["grad"], full["grad"])
+
+
+def test_zero_image_keeps_zeros():
+    """|sf| never exceeds |0|: the reference leaves lockin = 0, w = 0, grad = 0."""
+    img = np.zeros((40, 36))
+    got = cuGPA.wfr2_grad_opt(img, 3, 0.1, 0.02, 0.04, 0.013)
+    assert not got["lockin"].any() and not got["w"].any() and not got["grad"].any()
+    dev = engine.require_cuda()
+    wxs, wys = engine.grid_axes(0.1, 0.02, 0.04, 0.013)
+    res = engine.SweepPlan(img.shape, wxs, wys, 3, device=dev).run(engine.image_to_device(img, dev), (0.1, 0.02))
+    assert (res["kidx"] == -1).all()
+
+
+def test_small_frame_filter_covers_whole_circle():
+    """Frames narrower than the 4.5 sigma window: the filter radius is clamped to (n-1)//2.
+    Odd axes then carry the reference's whole circular kernel (exact); on even axes the single
+    antipodal tap (d = n/2) is dropped, a documented deviation of order g(n/2)/g(0)."""
+    rng = np.random.default_rng(3)
+    img = rng.normal(size=(25, 31))
+    ref = oracle.wfr_sweep(img, 4, 0.2, 0.1, 0.05, 0.02, return_diag=True)
+    got = cuGPA.wfr2_grad_opt(img, 4, 0.2, 0.1, 0.05, 0.02)
+    check_sweep(got, ref)
+    img = rng.normal(size=(24, 31))
+    ref = oracle.wfr_sweep(img, 4, 0.2, 0.1, 0.05, 0.02, return_diag=True)
+    got = cuGPA.wfr2_grad_opt(img, 4, 0.2, 0.1, 0.05, 0.02)
+    same = np.all(got["w"] == ref["w"], axis=0)
+    assert same.mean() > 0.97
+    assert np.abs(got["lockin"] - ref["lockin"])[same].max() < 3e-2 * np.abs(ref["lockin"]).max()
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 size (2048^2, 41x41 candidates), one peak: size-independent properties.
+    (a) exact linearity: scaling the image by 2 leaves every k-index unchanged and doubles the
+        lock-in bit-exactly (power-of-two scaling is exact in fp32);
+    (b) the winner really is the arg-max: an independent float64 evaluation of the Gabor sum at
+        sampled pixels reproduces the phase and is not beaten by the four neighbouring candidates;
+    (c) circular-shift covariance of the selected k-vector."""
+    cfg = synth.make_config('C3')
+    dev = engine.require_cuda()
+    img64 = cfg["image"]
+    img = engine.image_to_device(img64, dev)
+    k = cfg["ks"][0]
+    sigma = cfg["sigma"]
+    wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+    assert len(wxs) == 41 and len(wys) == 41
+    plan = engine.SweepPlan(img.shape, wxs, wys, sigma, device=dev)
+    a = plan.run(img, k)
+    b = plan.run(img * 2, k)
+    assert torch.equal(a["kidx"], b["kidx"])
+    assert torch.equal(torch.view_as_real(a["lockin"]) * 2, torch.view_as_real(b["lockin"]))
+    assert torch.equal(a["grad"], b["grad"])
+
+    kidx = a["kidx"].cpu().numpy()
+    lock = a["lockin"].cpu().numpy()
+    assert kidx.min() >= 0 and kidx.max() < 41 * 41
+    rng = np.random.default_rng(0)
+    n = img64.shape[0]
+    r = 6 * sigma
+    d = np.arange(-r, r + 1)
+    gw = np.exp(-d ** 2 / (2.0 * sigma ** 2)) / (sigma * np.sqrt(2 * np.pi))
+
+    def gabor(x, y, wx, wy):
+        xs, ys = (x + d) % n, (y + d) % n
+        patch = img64[np.ix_(xs, ys)]
+        return (gw[:, None] * gw[None, :] * patch * np.exp(2j * np.pi * (wx * xs[:, None] + wy * ys[None, :]))).sum()
+
+    for _ in range(24):
+        x, y = rng.integers(0, n, size=2)
+        ix, iy = divmod(int(kidx[x, y]), 41)
+        s = gabor(x, y, wxs[ix], wys[iy])
+        rot = np.exp(-2j * np.pi * ((wxs[ix] - k[0]) * x + (wys[iy] - k[1]) * y))
+        assert abs(np.angle(lock[x, y] * np.conj(s * rot))) < 1e-3
+        assert abs(abs(lock[x, y]) - abs(s)) < 1e-4 * abs(s) + 1e-6
+        for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            jx, jy = ix + dx, iy + dy
+            if 0 <= jx < 41 and 0 <= jy < 41:
+                assert abs(gabor(x, y, wxs[jx], wys[jy])) <= abs(s) * (1 + NEAR_TIE)
+
+    shift = (37, 1001)
+    c = plan.run(engine.image_to_device(np.roll(img64, shift, axis=(0, 1)), dev), k)
+    rolled = np.roll(kidx, shift, axis=(0, 1))
+    assert (c["kidx"].cpu().numpy() == rolled).mean() > 0.999
