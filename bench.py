@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the adaptive-GPA hot path (BASELINE.json metric: Mpixel*kvec/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE config 3 — synthetic twisted-bilayer moire 2048x2048,
+3 primary k-vectors, adaptive sweep 41x41 candidates per peak, sigma = 10 px.  One "step" is
+the full sweep of one frame (all peaks): arg-max over the candidate grid + winner lock-in,
+k-index and phase gradient.  N > 1 shards the k-grid over the GPUs (strong scaling) with one
+NCCL MAX all-reduce of the packed keys and one SUM all-reduce of the payload.
+
+  value  device-resident throughput, CUDA events around exactly K steps, max over ranks
+  e2e    same sweep through the reference-facing API (pygpa_b200.cuGPA.wfr2_grad_opt per
+         peak): NumPy image in pinned host memory in, float64/complex128 NumPy arrays out,
+         H2D and D2H inside the timed region
+  roofline       dominant kernel k_pass2 (arg-max sweep), FP32 FMA pipe
+  cpu_baseline   the oracle port of the reference CPU path on a bounded sample (rank 0, N=1)
+
+--impl reference times the reference CPU algorithm (oracle port, all host cores) instead.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3: synthetic TBG moire 2048x2048, 3 peaks x 41x41 k-vectors, sigma=10"
+SIZE, NGRID, SIGMA = 2048, 41, 10
+METRIC, UNIT = "adaptive_gpa_sweep_throughput", "Mpixel*kvec/s"
+
+
+def units_per_step(size=SIZE, ngrid=NGRID, peaks=3):
+    return size * size * peaks * ngrid * ngrid
+
+
+def f_alg(taps, nx):
+    """Algorithmic flops per pixel*kvec: separable, demodulate then real taps."""
+    return 4 * taps * (1 + 1.0 / nx) + 8 + 2.0 / nx
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(image, sigma):
+    import oracle
+    _W["oracle"], _W["image"], _W["sigma"] = oracle, image, sigma
+
+
+def _worker_run(args):
+    klist, kref = args
+    out = _W["oracle"].wfr_sweep_klist(_W["image"], _W["sigma"], klist, kref)
+    return float(np.abs(out["lockin"]).sum())
+
+
+def cpu_sample(image, cfg, n_cand, procs, pool=None):
+    """Time the oracle's sweep loop on `n_cand` candidates of peak 0 split over `procs` processes.
+    Returns Mpixel*kvec/s."""
+    import oracle
+    k = cfg["ks"][0]
+    wxs, wys = oracle.candidate_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+    klist = np.stack(np.meshgrid(wxs, wys, indexing="ij"), axis=-1).reshape(-1, 2)[:n_cand]
+    t0 = time.perf_counter()
+    if procs == 1:
+        oracle.wfr_sweep_klist(image, cfg["sigma"], klist, k)
+    else:
+        pool.map(_worker_run, [(part, k) for part in np.array_split(klist, procs)])
+    dt = time.perf_counter() - t0
+    return image.size * len(klist) / dt / 1e6, dt
+
+
+def run_reference(args, cfg):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    per_step = procs            # one candidate per core per step
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs, initializer=_worker_init, initargs=(cfg["image"], cfg["sigma"])) as pool:
+        for _ in range(args.warmup):
+            cpu_sample(cfg["image"], cfg, per_step, procs, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_sample(cfg["image"], cfg, per_step, procs, pool)
+        dt = time.perf_counter() - t0
+    value = cfg["image"].size * per_step * args.steps / dt / 1e6
+    sample = f"{per_step} candidates of peak 0 per step ({procs} processes x 1), full 2048x2048 frame, float64 FFT path"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from pygpa_b200 import _lib, cuGPA, engine
+    from pygpa_b200 import dist as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = engine.require_cuda()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    ks = cfg["ks"]
+    img_host = torch.from_numpy(cfg["image"]).pin_memory()            # float64, pinned
+    img = engine.image_to_device(img_host.numpy(), dev)
+    plans = []
+    for k in ks:
+        wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+        assert len(wxs) == NGRID and len(wys) == NGRID
+        plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev))
+    taps = 2 * plans[0].rx + 1
+
+    def step():
+        return gdist.sharded_sweep(img, plans, ks)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.gpa_profile_enable(1)
+    launches0 = engine.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    lib.gpa_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    gpu_launches = engine.launch_count - launches0
+    tot, n = ctypes.c_double(0), ctypes.c_int(0)
+    kernels = {}
+    for name in ("k_pass1", "k_pass2_argmax", "k_finalize"):
+        _lib.check(lib.gpa_profile_read(name.encode(), ctypes.byref(tot), ctypes.byref(n), 0))
+        kernels[name] = (tot.value, n.value)
+    _lib.check(lib.gpa_profile_read(b"k_pass1", ctypes.byref(tot), ctypes.byref(n), 1))
+
+    units = units_per_step()
+    value = units * args.steps / (ms_total / 1e3) / 1e6
+
+    # ---- end to end through the public API (rank 0 drives; N>1 shares the work the same way) ----
+    e2e = None
+    if world == 1:
+        def e2e_step():
+            outs = [cuGPA.wfr2_grad_opt(img_host.numpy(), cfg["sigma"], k[0], k[1], cfg["kw"], cfg["kstep"]) for k in ks]
+            return outs
+        for _ in range(2):
+            outs = e2e_step()
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            outs = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        d2h = sum(v.nbytes for o in outs for v in o.values())
+        e2e = {"value": units / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(img_host.numel() * 8 * len(ks)), "d2h_bytes_per_step": int(d2h),
+               "api": "pygpa_b200.cuGPA.wfr2_grad_opt x3 (NumPy float64 in pinned memory -> NumPy c128/f64 out)"}
+    else:
+        def e2e_step():
+            if rank == 0:
+                staged = torch.from_numpy(img_host.numpy()).to(dev, non_blocking=True)
+            else:
+                staged = torch.empty(img_host.shape, dtype=torch.float64, device=dev)
+            dist.broadcast(staged, 0)
+            im = torch.empty(staged.shape, dtype=torch.float32, device=dev)
+            _lib.check(lib.gpa_cast_f64_to_f32(ctypes.c_void_p(staged.data_ptr()), ctypes.c_void_p(im.data_ptr()),
+                                               staged.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            outs = gdist.sharded_sweep(im, plans, ks)
+            if rank == 0:
+                host = [(cuGPA._to_host(o["lockin"]), cuGPA._to_host(o["grad"]), cuGPA._to_host(o["kidx"])) for o in outs]
+                torch.cuda.current_stream().synchronize()
+                return host
+            return None
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            host = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        if rank == 0:
+            d2h = sum(t.numel() * t.element_size() for h in host for t in h)
+            e2e = {"value": units / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": int(img_host.numel() * 8), "d2h_bytes_per_step": int(d2h),
+                   "api": "pinned float64 frame on rank 0 -> NCCL broadcast -> pygpa_b200.dist.sharded_sweep -> c64/f32/i32 to rank-0 host"}
+
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12          # TFLOP/s, FFMA at the max SM clock
+        p2_ms, p2_n = kernels["k_pass2_argmax"]
+        # k_pass2 alone: 2 FMA per real-tap x complex-sample MAC + 8 for the demodulation (no pass-1 share)
+        p2_flops_per_launch = (4 * taps + 8) * units * args.steps / world / max(p2_n, 1)
+        p2_avg_s = p2_ms / max(p2_n, 1) / 1e3
+        achieved = p2_flops_per_launch / p2_avg_s / 1e12 if p2_n else None
+        roofline = {
+            "bound": "fp32", "kernel": "k_pass2<argmax>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+            "peak_source": f"148 SM x 128 FFMA lanes x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; that file has no fp32 figure)",
+            "avg_launch_ms": p2_avg_s * 1e3, "launches": p2_n,
+            "share_of_step": p2_ms / ms_total,
+            "step_frac": f_alg(taps, NGRID) * units * args.steps / (ms_total / 1e3) / 1e12 / fp32_peak / world,
+            "hbm_gbs_algorithmic": 28.0 * SIZE * SIZE * 3 * args.steps / (ms_total / 1e3) / 1e9,
+            "other_kernels_ms": {k: v[0] for k, v in kernels.items()},
+        }
+        prof = os.path.join(ROOT, "profiles", "r01_pass2_ncu.json")
+        if os.path.exists(prof):
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_cand = 8
+            v, dt_cpu = cpu_sample(cfg["image"], cfg, n_cand, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {n_cand} candidates of peak 0 on the full 2048x2048 frame ({dt_cpu:.1f} s), "
+                             "oracle.wfr_sweep_klist = the reference's single-threaded float64 FFT loop"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "working set per step (3 x 1.44 GB of first-pass planes) exceeds L2; no flush needed",
+                       "parallelism": f"k-grid sharded over {world} GPU(s)", "filter": f"{taps} taps (4.5 sigma)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
+            "ms_per_2048_frame": ms_total / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
+    from pygpa_b200 import synth
+    cfg = synth.make_config("C3")
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@ import functools
 import numpy as np
 
 DEFAULT_TRUNC = 4.5   # phase error 3.2e-4 rad, k flips only at top-2 gaps < 3.3e-6
-MAX_TAPS = 448        # kMaxTaps in csrc/lockin.cu
+MAX_TAPS = 446        # kMaxTaps in csrc/lockin.cu
 
 
 @functools.lru_cache(maxsize=64)

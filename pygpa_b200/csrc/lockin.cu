@@ -20,14 +20,14 @@
 
 namespace gpa {
 
-constexpr int kMaxTaps = 448;      // 2R+1 <= kMaxTaps  (sigma <= 49 at 4.5 sigma); param space budget
+constexpr int kMaxTaps = 446;      // 2R+1 <= kMaxTaps  (sigma <= 49 at 4.5 sigma); param space budget
 constexpr int kP = 16;             // outputs per thread along the filter axis
 constexpr int kWarps = 8;          // warps per CTA
 constexpr int kTile = kP * kWarps; // outputs per CTA along the filter axis (128)
 constexpr int kLanes = 32;         // outputs per CTA across the filter axis
 
 struct TapTable {
-    float2 g[kMaxTaps];            // (tap, tap): packed operand of FFMA2
+    float2 g[kMaxTaps + 2];        // (tap, tap): packed operand of FFMA2; zero-filled past 2R+1
 };
 
 struct WList {
@@ -55,36 +55,50 @@ __global__ void k_build_phasors(float2* __restrict__ table, double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // register-blocked FIR core
 // ---------------------------------------------------------------------------------------------
-// acc[p] = sum_{d<T} g[d] * sample(p + d),  p < P.   `load(j)` returns sample j; it is called
-// for j up to T + P - 1 (one past the last sample that is used), so that index must be readable.
+// acc[p] = sum_{d<T} g[d] * sample(p + d),  p < P.   `load(j)` returns sample j.  Taps and samples
+// are fetched kAhead steps before they are consumed (software pipeline in registers), so load(j)
+// is called for j up to T + P - 1 + kAhead and taps.g is read up to index T - 1 + kAhead: both
+// must be readable (the callers pad their tiles / the tap table is zero-filled).
+constexpr int kAhead = 2;
+
 template <int P, typename Load>
 __device__ __forceinline__ void fir_block(float2 (&acc)[P], const TapTable& taps, int T, Load load) {
-    float2 win[P];
+    static_assert(P % kAhead == 0, "P must be a multiple of the prefetch depth");
+    float2 win[P], gq[kAhead], sq[kAhead];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         win[p] = load(p);
         acc[p] = make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int a = 0; a < kAhead; ++a) {
+        gq[a] = taps.g[a];
+        sq[a] = load(P + a);
+    }
     int d0 = 0;
     for (; d0 + P <= T; d0 += P) {
 #pragma unroll
         for (int u = 0; u < P; ++u) {
-            const float2 g = taps.g[d0 + u];
-            const float2 nxt = load(d0 + u + P);
+            const float2 g = gq[u % kAhead];
+            const float2 s = sq[u % kAhead];
+            gq[u % kAhead] = taps.g[d0 + u + kAhead];
+            sq[u % kAhead] = load(d0 + u + P + kAhead);
 #pragma unroll
             for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
-            win[u] = nxt;
+            win[u] = s;
         }
     }
     const int rem = T - d0;
 #pragma unroll
     for (int u = 0; u < P - 1; ++u) {
         if (u < rem) {  // warp-uniform
-            const float2 g = taps.g[d0 + u];
-            const float2 nxt = load(d0 + u + P);
+            const float2 g = gq[u % kAhead];
+            const float2 s = sq[u % kAhead];
+            gq[u % kAhead] = taps.g[d0 + u + kAhead];
+            sq[u % kAhead] = load(d0 + u + P + kAhead);
 #pragma unroll
             for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
-            win[u] = nxt;
+            win[u] = s;
         }
     }
 }
@@ -112,7 +126,7 @@ k_pass1(const Pass1Params prm, const __grid_constant__ TapTable taps) {
     const int y0 = blockIdx.y * kTile;         // first output column
     const int pl = blockIdx.z;                 // plane within the chunk
     const int T = prm.T, M = prm.M, N = prm.N;
-    const int n_samp = kTile + T;              // T-1 halo + 1 spare
+    const int n_samp = kTile + T + kAhead; // T-1 halo + prefetch slack
     const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
 
     int cbase = (y0 - prm.Ry) % M;
@@ -181,7 +195,7 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
     const int pl = blockIdx.z;
     const int plane = prm.plane0 + pl;
     const int T = prm.T;
-    const int n_samp = kTile + T;
+    const int n_samp = kTile + T + kAhead;
 
     {   // tile fill: rows are 256 B, fully coalesced; pitch/n_alloc padding keeps it in bounds
         const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride +
@@ -192,12 +206,11 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
 
     const float2* col = smem + (warp * kP) * kLanes + lane;
     float best[kP];
-    int bidx[kP];
+    unsigned bidx[kP / 2];   // winning candidate per output, two 16-bit fields per register
 #pragma unroll
-    for (int p = 0; p < kP; ++p) {
-        best[p] = 0.f;
-        bidx[p] = 0;
-    }
+    for (int p = 0; p < kP; ++p) best[p] = 0.f;
+#pragma unroll
+    for (int p = 0; p < kP / 2; ++p) bidx[p] = 0u;
 
     for (int c = 0; c < prm.n_cand; ++c) {
         const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc +
@@ -205,12 +218,14 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
         float2 acc[kP];
         fir_block<kP>(acc, taps, T, [&](int j) { return cmul(col[j * kLanes], __ldg(ph + j)); });
         if (MODE == kArgmax) {
+            const unsigned c2 = (unsigned)c * 0x10001u;
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
                 if (a2 > best[p]) {   // strict: the earlier candidate keeps exact ties
                     best[p] = a2;
-                    bidx[p] = c;
+                    const unsigned keep = (p & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+                    bidx[p / 2] = (bidx[p / 2] & keep) | (c2 & ~keep);
                 }
             }
         } else {
@@ -233,7 +248,8 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
             for (int p = 0; p < kP; ++p) {
                 const int x = x0 + warp * kP + p;
                 if (x < prm.N && best[p] > 0.f) {
-                    const unsigned idx = (unsigned)(bidx[p] * prm.idx_c + plane * prm.idx_p);
+                    const unsigned cwin = (bidx[p / 2] >> ((p & 1) * 16)) & 0xFFFFu;
+                    const unsigned idx = cwin * (unsigned)prm.idx_c + (unsigned)(plane * prm.idx_p);
                     const unsigned long long k =
                         ((unsigned long long)__float_as_uint(best[p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
                     atomicMax(prm.key + (size_t)x * prm.M + y, k);
@@ -429,7 +445,7 @@ static int plan(Geometry& g, int N, int M, int n_rows, int n_planes, int Rx, int
     g.N = N; g.M = M; g.n_rows = n_rows; g.n_planes = n_planes;
     g.Rx = Rx; g.Ry = Ry; g.Tx = 2 * Rx + 1; g.Ty = 2 * Ry + 1;
     g.pitch = (int)align_up((size_t)M, 32);
-    g.n_alloc = ceil_div(N, kTile) * kTile + g.Tx;   // every pass-2 tile reads kTile + Tx rows
+    g.n_alloc = ceil_div(N, kTile) * kTile + g.Tx + kAhead;   // every pass-2 tile reads this many rows past x0
     g.plane_stride = (size_t)g.n_alloc * g.pitch;
     return GPA_OK;
 }
@@ -488,7 +504,7 @@ static int launch_pass1(const Geometry& g, const float* img, const TapTable& ty,
     p.img = img; p.phy = g.phy; p.planes = g.planes; p.plane_stride = g.plane_stride;
     p.N = g.N; p.M = g.M; p.pitch = g.pitch; p.n_rows_filled = g.N + 2 * g.Rx;
     p.Rx = g.Rx; p.Ry = g.Ry; p.T = g.Ty; p.plane0 = plane0;
-    const size_t smem = (size_t)(kTile + g.Ty) * 33 * sizeof(float2);
+    const size_t smem = (size_t)(kTile + g.Ty + kAhead) * 33 * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
         GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -512,7 +528,7 @@ static int launch_pass2(const Geometry& g, const TapTable& tx, int plane0, int c
     } else {
         p.n_cand = 1; p.row_c = 0; p.row_p = 1; p.idx_c = 0; p.idx_p = 1;
     }
-    const size_t smem = (size_t)(kTile + g.Tx) * kLanes * sizeof(float2);
+    const size_t smem = (size_t)(kTile + g.Tx + kAhead) * kLanes * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
         GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -533,6 +549,7 @@ static int check_common(const float* img, const double* wx_rows, const double* w
     GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes,
                 "bad plane range [%d, %d) of %d", plane_begin, plane_end, n_planes);
     GPA_REQUIRE(cand_mode == GPA_CAND_LIST || (long long)n_rows * n_planes < 0x7fffffffLL, "too many candidates");
+    GPA_REQUIRE(cand_mode == GPA_CAND_LIST || n_rows <= 65535, "grid mode supports at most 65535 rows (got %d)", n_rows);
     return GPA_OK;
 }
 

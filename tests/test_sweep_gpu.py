@@ -184,7 +184,7 @@ def test_full_size_properties_config3():
         lock-in bit-exactly (power-of-two scaling is exact in fp32);
     (b) the winner really is the arg-max: an independent float64 evaluation of the Gabor sum at
         sampled pixels reproduces the phase and is not beaten by the four neighbouring candidates;
-    (c) circular-shift covariance of the selected k-vector."""
+    (c) circular-shift covariance of the selected k-vector (away from the frame seam)."""
     cfg = synth.make_config('C3')
     dev = engine.require_cuda()
     img64 = cfg["image"]
@@ -226,7 +226,14 @@ def test_full_size_properties_config3():
             if 0 <= jx < 41 and 0 <= jy < 41:
                 assert abs(gabor(x, y, wxs[jx], wys[jy])) <= abs(s) * (1 + NEAR_TIE)
 
+    # the carrier is evaluated at the true pixel index, so it is NOT periodic with the frame: the
+    # covariance holds away (> R) from the frame seam and from where the shift moves that seam
     shift = (37, 1001)
     c = plan.run(engine.image_to_device(np.roll(img64, shift, axis=(0, 1)), dev), k)
     rolled = np.roll(kidx, shift, axis=(0, 1))
-    assert (c["kidx"].cpu().numpy() == rolled).mean() > 0.999
+    idx = np.arange(n)
+    far = [np.minimum.reduce([np.minimum((idx - s0) % n, (s0 - idx) % n) for s0 in (0, sh)]) > plan.rx + 1
+           for sh in shift]
+    m = far[0][:, None] & far[1][None, :]
+    assert m.mean() > 0.6
+    assert (c["kidx"].cpu().numpy() == rolled)[m].mean() > 0.999
