@@ -64,6 +64,12 @@ int gpa_profile_read(const char* kernel, double* total_ms, int* launches, int re
  * (cp.asarray(image), cuGPA.py:52); the kernels read float32. */
 int gpa_cast_f64_to_f32(const double* in, float* out, size_t n, void* stream);
 
+/* Glue of extract_displacement_field (geometric_phase_analysis.py:922-926) kept on the device:
+ * phases = angle(lockin), weights = |lockin| * (mask + eps) with mask = 1 on the interior
+ * [border, N-border) x [border, M-border).  lockin is float2 (is_f64 = 0) or double2. */
+int gpa_phase_weight(const void* lockin, int is_f64, int N, int M, int border, double eps,
+                     double* phases, double* weights, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1 — spatial lock-in and the adaptive (windowed-Fourier-ridge) sweep.
  *
@@ -138,6 +144,53 @@ int gpa_wfr_sweep(const float* img, int N, int M,
                   double kref_x, double kref_y, int grad_mode, int out_f64,
                   unsigned long long* key, void* lockin, void* grad, void* w, int* kidx,
                   void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 — per-pixel phase -> displacement least squares (float64 in, float64 out).
+ *
+ * Replaces: myweighed_lstsq (geometric_phase_analysis.py:97-113, numba + LAPACK gelsd per
+ * pixel), the three branches of reconstruct_u_inv (:157-193) and the wrapped-difference /
+ * least-squares stage of reconstruct_u_inv_from_phases (:228-237).
+ * ------------------------------------------------------------------------------------------ */
+
+/* where the right-hand side b (d planes) comes from */
+#define GPA_LSQ_SRC_PLAIN 0     /* b = src (d,N,M)                                   solve grid (N, M)   */
+#define GPA_LSQ_SRC_DIFF1 1     /* b = wrapToPi(diff(src, axis=2)), src (d,N,M)  :234 solve grid (N, M-1) */
+#define GPA_LSQ_SRC_DIFF0 2     /* b = wrapToPi(diff(src, axis=1))               :235 solve grid (N-1, M) */
+#define GPA_LSQ_SRC_PREDIFF0 3  /* b = wrapToPi(src[...,0])[:, :, :-1], src (d,N,M,2) :229,231  (N, M-1)  */
+#define GPA_LSQ_SRC_PREDIFF1 4  /* b = wrapToPi(src[...,1])[:, :-1]              :230,232        (N-1, M)  */
+
+#define GPA_LSQ_WEIGHTED 0      /* per pixel argmin |w (K x - b)|, K = 2 pi kvecs, minimum norm when rank deficient */
+#define GPA_LSQ_MATRIX 1        /* x = matrix (2,d) . b : the unweighted pinv(K) (:185) and the two-k inverse (:191) */
+
+int gpa_lstsq_workspace_bytes(int d, size_t* bytes);
+
+/* out (2, n, m) on the solve grid of src_kind.  w is (d, wn, wm) with wn >= n, wm >= m and is
+ * indexed with the solve-grid indices, exactly like the reference indexes `w[:, i, j]`.
+ * subtract_mean: subtract each plane's mean first (reconstruct_u_inv, :182); needs ws. */
+int gpa_lstsq_u(const double* src, int src_kind, const double* w, int wn, int wm,
+                const double* kvecs /*host (d,2)*/, int d, int N, int M,
+                int solver, const double* matrix /*host (2,d) or NULL*/, int subtract_mean,
+                double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* out[i] = sqrt(sum_k w[k*n + i]^2): np.linalg.norm(weights, axis=0) (:240). */
+int gpa_norm_axis0(const double* w, int d, size_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — weighted least-squares phase unwrapping (Ghiglia-Romero PCG, DCT Poisson preconditioner),
+ * float64 throughout.
+ *
+ * Replaces: phase_unwrap (phase_unwrap.py:141-208) when `psi` is given, phase_unwrap_prediff
+ * (:282-350) when (`dx`, `dy`) are given: dx (N, M-1) = differences along axis 1, dy (N-1, M)
+ * along axis 0; both are wrapped to [-pi, pi) first, like the reference does.  weight (N, M) or
+ * NULL (unweighted).  Stops after kmax iterations or when |r| < 1e-9 |r0| (at least one
+ * iteration, as the reference).  *iterations (host, optional) receives the iteration count and
+ * forces a stream synchronisation.
+ * ------------------------------------------------------------------------------------------ */
+int gpa_unwrap_workspace_bytes(int N, int M, size_t* bytes);
+int gpa_unwrap_pcg(const double* psi, const double* dx, const double* dy, const double* weight,
+                   int N, int M, int kmax, double* phi, int* iterations /*host or NULL*/,
+                   void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

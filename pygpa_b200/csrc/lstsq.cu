@@ -1,0 +1,251 @@
+// K3 — per-pixel phase -> displacement least squares (float64), sm_100a.
+//
+// Reference semantics: myweighed_lstsq (pyGPA/geometric_phase_analysis.py:97-113), the three
+// branches of reconstruct_u_inv (157-193) and the gradient assembly of
+// reconstruct_u_inv_from_phases (196-237).  One thread per pixel; the d x 2 system
+// (w_i K_i) x = w_i b_i is solved by a column-pivoted Gram-Schmidt QR in registers (error ~
+// cond * eps, like LAPACK's SVD path, not cond^2 * eps like the normal equations) with
+// gelsd's rank rule: singular values <= eps * s_max are dropped and the minimum-norm solution
+// returned (all-zero weights -> 0).  HBM-bound: (2d + 2) doubles per pixel.
+#include "common.cuh"
+
+namespace gpa {
+
+constexpr int kMaxD = 8;
+
+struct LsqParams {
+    const double* src;    // phases / gradients / unwrapped phases
+    const double* w;      // weights (d, wn, wm) or null
+    const double* means;  // per-plane mean to subtract (d) or null
+    double* out;          // (2, n, m)
+    long long base, ps, rs, cs, doff;   // b_i(r, c) = src[base + i*ps + r*rs + c*cs (+ doff)] ...
+    int do_wrap, d, n, m, wn, wm;
+    double K[kMaxD][2];   // 2 pi k
+    double P[2][kMaxD];   // unweighted / two-k branch: x = P b
+    int use_matrix;
+};
+
+__device__ __forceinline__ double wrap_pi(double v) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const double pi = 3.141592653589793238462643383279;
+    double t = (v + pi) / two_pi;
+    t -= floor(t);
+    return t * two_pi - pi;
+}
+
+__global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= p.n || c >= p.m) return;
+    double b[kMaxD];
+    const long long o = p.base + (long long)r * p.rs + (long long)c * p.cs;
+#pragma unroll
+    for (int i = 0; i < kMaxD; ++i) {
+        if (i < p.d) {
+            double v = p.src[o + i * p.ps];
+            if (p.doff) v = p.src[o + i * p.ps + p.doff] - v;
+            if (p.do_wrap) v = wrap_pi(v);
+            if (p.means) v -= p.means[i];
+            b[i] = v;
+        }
+    }
+    double x0 = 0.0, x1 = 0.0;
+    if (p.use_matrix) {
+#pragma unroll
+        for (int i = 0; i < kMaxD; ++i) {
+            if (i < p.d) {
+                x0 = fma(p.P[0][i], b[i], x0);
+                x1 = fma(p.P[1][i], b[i], x1);
+            }
+        }
+    } else {
+        double a0[kMaxD], a1[kMaxD], y[kMaxD];
+        double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < kMaxD; ++i) {
+            if (i < p.d) {
+                const double w = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
+                a0[i] = w * p.K[i][0];
+                a1[i] = w * p.K[i][1];
+                y[i] = w * b[i];
+                n0 = fma(a0[i], a0[i], n0);
+                n1 = fma(a1[i], a1[i], n1);
+            }
+        }
+        const bool swap = n1 > n0;   // column pivoting: the larger column first
+        const double f2 = swap ? n1 : n0;
+        if (f2 > 0.0) {
+            const double f = sqrt(f2);
+            double g = 0.0, z1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i) {
+                if (i < p.d) {
+                    const double q = (swap ? a1[i] : a0[i]) / f;
+                    g = fma(q, swap ? a0[i] : a1[i], g);
+                    z1 = fma(q, y[i], z1);
+                }
+            }
+            double h2 = 0.0, z2h = 0.0;   // second column orthogonalised against the first
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i) {
+                if (i < p.d) {
+                    const double q = (swap ? a1[i] : a0[i]) / f;
+                    const double e = (swap ? a0[i] : a1[i]) - g * q;
+                    h2 = fma(e, e, h2);
+                    z2h = fma(e, y[i], z2h);     // = h * z2
+                }
+            }
+            const double h = sqrt(h2);
+            // singular values of [[f, g], [0, h]]
+            const double t = f * f + g * g + h * h;
+            const double det = f * h;
+            const double disc = sqrt(fmax(t * t - 4.0 * det * det, 0.0));
+            const double s1 = sqrt(0.5 * (t + disc));
+            const double s2 = det / s1;
+            double u0, u1;
+            if (s2 > 2.220446049250313e-16 * s1) {
+                u1 = z2h / h2;                 // z2 / h
+                u0 = (z1 - g * u1) / f;
+            } else {                            // rank 1: minimum-norm solution of [f g] u = z1
+                const double nn = f * f + g * g;
+                u0 = f * z1 / nn;
+                u1 = g * z1 / nn;
+            }
+            x0 = swap ? u1 : u0;
+            x1 = swap ? u0 : u1;
+        }
+    }
+    const size_t np = (size_t)p.n * p.m;
+    p.out[(size_t)r * p.m + c] = x0;
+    p.out[np + (size_t)r * p.m + c] = x1;
+}
+
+// per-plane mean of a (d, n) array, deterministic two-stage reduction
+__global__ void __launch_bounds__(256) k_plane_partial(const double* __restrict__ src, double* __restrict__ part, size_t n) {
+    __shared__ double sh[256];
+    const int plane = blockIdx.y;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s += src[(size_t)plane * n + i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[(size_t)plane * gridDim.x + blockIdx.x] = sh[0];
+}
+
+__global__ void k_plane_mean_final(const double* __restrict__ part, double* __restrict__ means, int nblk, double inv_n) {
+    __shared__ double sh[256];
+    const int plane = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 256) s += part[(size_t)plane * nblk + i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) means[plane] = sh[0] * inv_n;
+}
+
+// out[r, c] = sqrt(sum_i w[i, r, c]^2)   (np.linalg.norm(weights, axis=0), geometric_phase_analysis.py:240)
+__global__ void __launch_bounds__(256) k_norm_axis0(const double* __restrict__ w, double* __restrict__ out, int d, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double v = w[(size_t)k * n + i];
+            s = fma(v, v, s);
+        }
+        out[i] = sqrt(s);
+    }
+}
+
+}  // namespace gpa
+
+using namespace gpa;
+
+extern "C" int gpa_lstsq_workspace_bytes(int d, size_t* bytes) {
+    GPA_REQUIRE(bytes && d >= 1 && d <= kMaxD, "d must be in [1, %d]", kMaxD);
+    *bytes = (size_t)(d * 1024 + kMaxD) * sizeof(double) + 512;
+    return GPA_OK;
+}
+
+extern "C" int gpa_lstsq_u(const double* src, int src_kind, const double* w, int wn, int wm,
+                           const double* kvecs /*host (d,2), cycles/pixel*/, int d, int N, int M,
+                           int solver, const double* matrix /*host (2,d) or null*/, int subtract_mean,
+                           double* out, void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(src && kvecs && out, "null pointer argument");
+    GPA_REQUIRE(d >= 1 && d <= kMaxD, "d must be in [1, %d] (got %d)", kMaxD, d);
+    GPA_REQUIRE(N >= 1 && M >= 1, "bad shape");
+    GPA_REQUIRE(src_kind >= GPA_LSQ_SRC_PLAIN && src_kind <= GPA_LSQ_SRC_PREDIFF1, "bad src_kind %d", src_kind);
+    GPA_REQUIRE(solver == GPA_LSQ_WEIGHTED || solver == GPA_LSQ_MATRIX, "bad solver %d", solver);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LsqParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.src = src; p.w = w; p.out = out; p.d = d;
+    const long long NM = (long long)N * M;
+    switch (src_kind) {
+        case GPA_LSQ_SRC_PLAIN: p.ps = NM; p.rs = M; p.cs = 1; p.n = N; p.m = M; break;
+        case GPA_LSQ_SRC_DIFF1: p.ps = NM; p.rs = M; p.cs = 1; p.doff = 1; p.do_wrap = 1; p.n = N; p.m = M - 1; break;
+        case GPA_LSQ_SRC_DIFF0: p.ps = NM; p.rs = M; p.cs = 1; p.doff = M; p.do_wrap = 1; p.n = N - 1; p.m = M; break;
+        case GPA_LSQ_SRC_PREDIFF0: p.ps = 2 * NM; p.rs = 2LL * M; p.cs = 2; p.base = 0; p.do_wrap = 1; p.n = N; p.m = M - 1; break;
+        case GPA_LSQ_SRC_PREDIFF1: p.ps = 2 * NM; p.rs = 2LL * M; p.cs = 2; p.base = 1; p.do_wrap = 1; p.n = N - 1; p.m = M; break;
+    }
+    GPA_REQUIRE(p.n >= 1 && p.m >= 1, "frame too small for a difference");
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < d; ++i) {
+        p.K[i][0] = two_pi * kvecs[2 * i];
+        p.K[i][1] = two_pi * kvecs[2 * i + 1];
+    }
+    if (solver == GPA_LSQ_MATRIX) {
+        GPA_REQUIRE(matrix != nullptr, "matrix is null");
+        p.use_matrix = 1;
+        for (int i = 0; i < d; ++i) {
+            p.P[0][i] = matrix[i];
+            p.P[1][i] = matrix[d + i];
+        }
+    } else {
+        GPA_REQUIRE(w != nullptr, "weights are null");
+        GPA_REQUIRE(wn >= p.n && wm >= p.m, "weights (%d x %d) smaller than the solve grid (%d x %d)", wn, wm, p.n, p.m);
+        p.wn = wn; p.wm = wm;
+    }
+    if (subtract_mean) {
+        GPA_REQUIRE(src_kind == GPA_LSQ_SRC_PLAIN, "mean subtraction applies to plain sources only");
+        size_t need = 0;
+        gpa_lstsq_workspace_bytes(d, &need);
+        if (!ws || ws_bytes < need) {
+            set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+            return GPA_ERR_WORKSPACE;
+        }
+        Arena a(ws, ws_bytes);
+        double* part = a.take<double>((size_t)d * 1024);
+        double* means = a.take<double>(kMaxD);
+        const int nblk = (int)((NM + 256 * 8 - 1) / (256 * 8) < 1024 ? (NM + 256 * 8 - 1) / (256 * 8) : 1024);
+        {
+            KernelTimer t("k_plane_mean", st);
+            k_plane_partial<<<dim3(nblk, d), 256, 0, st>>>(src, part, (size_t)NM);
+            k_plane_mean_final<<<d, 256, 0, st>>>(part, means, nblk, 1.0 / (double)NM);
+        }
+        p.means = means;
+    }
+    {
+        KernelTimer t("k_lstsq", st);
+        dim3 grid(ceil_div(p.m, 64), ceil_div(p.n, 4));
+        k_lstsq<<<grid, 256, 0, st>>>(p);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_norm_axis0(const double* w, int d, size_t n, double* out, void* stream) {
+    GPA_REQUIRE(w && out && d >= 1, "bad argument");
+    if (n == 0) return GPA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    KernelTimer t("k_norm_axis0", st);
+    k_norm_axis0<<<(unsigned)blocks, 256, 0, st>>>(w, out, d, n);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}

@@ -1,0 +1,565 @@
+// K2 — weighted least-squares phase unwrapping: PCG with a DCT Poisson preconditioner (float64).
+//
+// Reference semantics: phase_unwrap / phase_unwrap_prediff (pyGPA/phase_unwrap.py:141-208,
+// 282-350), solvePoisson_precomped (:95-103), precomp_Poissonscaling (:106-115, including the
+// swapped N/M in the cosine arguments), applyQ (:118-132).  Ghiglia & Romero, JOSA A 11 (1994).
+//
+// Everything stays on the device: the PCG scalars (alpha, beta, the norms and the stop flag) live
+// in device memory, every kernel returns immediately once the stop flag is set, and the host only
+// enqueues (it polls the flag every few iterations to stop enqueueing early).
+//
+// DCT-II / DCT-III (scipy.fft.dctn / idctn, unnormalised): one row per CTA in shared memory.
+// Power-of-two lengths use Makhoul's N-point complex FFT (radix-2 Stockham in place, twiddles
+// from a table); other lengths use the O(n^2) cosine-table sum (any n, slower).  The 2-D
+// transform is row pass -> transpose -> row pass; the 1/scale of the Poisson solve is fused into
+// the second forward pass and <r, z> into the last inverse pass.
+#include "common.cuh"
+
+namespace gpa {
+
+constexpr double kPi = 3.141592653589793238462643383279;
+constexpr int kMaxFftLen = 8192;   // 16 B * 8192 = 128 KB of shared memory per row
+
+struct UwScalars {
+    double rz, rz_prev, pqp, r0sq, rsq, alpha, beta;
+    int done, k, kmax, pad;
+};
+
+__device__ __forceinline__ double wrap_pi_d(double v) {
+    const double two_pi = 2.0 * kPi;
+    double t = (v + kPi) / two_pi;
+    t -= floor(t);
+    return t * two_pi - kPi;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (int k = blockDim.x >> 1; k > 0; k >>= 1) {
+        if (t < k) sh[t] += sh[t + k];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------
+// tw[t] = exp(-2 pi i t / n), t < n/2 ;  mk[k] = exp(-i pi k / (2n)), k < n ; ct[j] = cos(pi j / (2n)), j < 4n
+__global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pow2) {
+        if (i < n / 2) {
+            double s, c;
+            sincospi(-2.0 * (double)i / (double)n, &s, &c);
+            tw[i] = make_double2(c, s);
+        }
+        if (i < n) {
+            double s, c;
+            sincospi(-(double)i / (2.0 * (double)n), &s, &c);
+            mk[i] = make_double2(c, s);
+        }
+    } else if (i < 4 * n) {
+        ct[i] = cospi((double)i / (2.0 * (double)n));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// in-place radix-2 Stockham FFT of buf[0..n) (forward, e^{-2 pi i jk/n}); all threads of the CTA
+// ------------------------------------------------------------------------------------------
+template <int MAXB>
+__device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __restrict__ tw) {
+    const int half = n >> 1;
+    const int nthr = blockDim.x;
+    for (int ns = 1; ns < n; ns <<= 1) {
+        double2 a[MAXB], b[MAXB];
+        const int tstep = half / ns;   // twiddle index stride: exp(-2 pi i k/(2 ns)) = tw[k * n/(2 ns)]
+#pragma unroll
+        for (int q = 0; q < MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                const int k = j & (ns - 1);
+                const double2 w = __ldg(tw + k * tstep);
+                const double2 x = buf[j + half];
+                a[q] = buf[j];
+                b[q] = make_double2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                const int k = j & (ns - 1);
+                const int j0 = ((j - k) << 1) + k;
+                buf[j0] = make_double2(a[q].x + b[q].x, a[q].y + b[q].y);
+                buf[j0 + ns] = make_double2(a[q].x - b[q].x, a[q].y - b[q].y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct DctArgs {
+    const double* in;
+    double* out;
+    int rows, n;               // rows of length n, contiguous
+    const double2 *tw, *mk;    // pow2 tables
+    const double* ct;          // direct table
+    // fused Poisson scaling (second forward pass; data is in the transposed layout: row = axis-1
+    // frequency J, column = axis-0 frequency I): out /= 2 (cos(pi I / dimM) + cos(pi J / dimN) - 2)
+    int fuse_scale, dimN, dimM;
+    // fused <r, z> (last inverse pass): partial[row] = sum_c out[row][c] * dot_with[row][c]
+    const double* dot_with;
+    double* partial;
+    const UwScalars* sc;
+};
+
+__device__ __forceinline__ double poisson_scale(int I, int J, int dimN, int dimM) {
+    // phase_unwrap.py:109: 2 (cos(pi I / M) + cos(pi J / N) - 2), [0,0] := 1
+    if (I == 0 && J == 0) return 1.0;
+    return 2.0 * (cospi((double)I / (double)dimM) + cospi((double)J / (double)dimN) - 2.0);
+}
+
+// forward DCT-II of every row:  y[k] = 2 sum_m x[m] cos(pi k (2m+1) / (2n))
+template <int MAXB>
+__global__ void k_dct2_rows_pow2(const DctArgs a) {
+    if (a.sc->done) return;
+    extern __shared__ double2 cbuf[];
+    const int n = a.n, row = blockIdx.x;
+    const double* __restrict__ x = a.in + (size_t)row * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double v = x[j];
+        const int dst = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
+        cbuf[dst] = make_double2(v, 0.0);
+    }
+    __syncthreads();
+    fft_pow2<MAXB>(cbuf, n, a.tw);
+    double* __restrict__ y = a.out + (size_t)row * n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double2 w = __ldg(a.mk + k), v = cbuf[k];
+        double r = 2.0 * (v.x * w.x - v.y * w.y);      // Re(e^{-i pi k/2n} V[k])
+        if (a.fuse_scale) r /= poisson_scale(k, row, a.dimN, a.dimM);
+        y[k] = r;
+    }
+}
+
+// inverse (scipy idct type 2, norm=None): x = dct2^{-1}(y)
+template <int MAXB>
+__global__ void k_idct2_rows_pow2(const DctArgs a) {
+    if (a.sc->done) return;
+    extern __shared__ double2 cbuf[];
+    __shared__ double red[1024];
+    const int n = a.n, row = blockIdx.x;
+    const double* __restrict__ y = a.in + (size_t)row * n;
+    // V[k] = e^{+i pi k/2n} (y[k] - i y[n-k]) / 2 ; load conj(V) so the forward FFT yields conj(n v) (v is real)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double yk = y[k], ynk = k ? y[n - k] : 0.0;
+        const double2 w = __ldg(a.mk + k);             // e^{-i pi k/2n} = (c, -s)
+        // e^{+i t}(yk - i ynk) = (c yk + s ynk) + i (s yk - c ynk), with c = w.x, s = -w.y
+        const double re = 0.5 * (w.x * yk - w.y * ynk);
+        const double im = 0.5 * (-w.y * yk - w.x * ynk);
+        cbuf[k] = make_double2(re, -im);
+    }
+    __syncthreads();
+    fft_pow2<MAXB>(cbuf, n, a.tw);
+    double* __restrict__ x = a.out + (size_t)row * n;
+    const double inv = 1.0 / (double)n;
+    double dot = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int src = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
+        const double v = cbuf[src].x * inv;
+        x[j] = v;
+        if (a.dot_with) dot = fma(v, a.dot_with[(size_t)row * n + j], dot);
+    }
+    if (a.dot_with) {
+        const double s = block_sum(dot, red);
+        if (threadIdx.x == 0) a.partial[row] = s;
+    }
+}
+
+// any length: direct cosine sums from the table ct[j] = cos(pi j / 2n), j < 4n
+template <int INVERSE>
+__global__ void k_dct2_rows_direct(const DctArgs a) {
+    if (a.sc->done) return;
+    extern __shared__ double rbuf[];
+    __shared__ double red[1024];
+    const int n = a.n, row = blockIdx.x, n4 = 4 * n;
+    const double* __restrict__ in = a.in + (size_t)row * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) rbuf[j] = in[j];
+    __syncthreads();
+    double* __restrict__ out = a.out + (size_t)row * n;
+    double dot = 0.0;
+    for (int o = threadIdx.x; o < n; o += blockDim.x) {
+        double acc = 0.0;
+        if (!INVERSE) {
+            int idx = o % n4;                      // k (2m+1) mod 4n, m = 0
+            const int step = (2 * o) % n4;
+            for (int m = 0; m < n; ++m) {
+                acc = fma(rbuf[m], __ldg(a.ct + idx), acc);
+                idx += step;
+                if (idx >= n4) idx -= n4;
+            }
+            acc *= 2.0;
+            if (a.fuse_scale) acc /= poisson_scale(o, row, a.dimN, a.dimM);
+        } else {
+            const int step = (2 * o + 1) % n4;     // k (2m+1) mod 4n, k = 1, 2, ...
+            int idx = step;
+            for (int k = 1; k < n; ++k) {
+                acc = fma(rbuf[k], __ldg(a.ct + idx), acc);
+                idx += step;
+                if (idx >= n4) idx -= n4;
+            }
+            acc = (rbuf[0] + 2.0 * acc) / (2.0 * (double)n);
+            if (a.dot_with) dot = fma(acc, a.dot_with[(size_t)row * n + o], dot);
+        }
+        out[o] = acc;
+    }
+    if (INVERSE && a.dot_with) {
+        const double s = block_sum(dot, red);
+        if (threadIdx.x == 0) a.partial[row] = s;
+    }
+}
+
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
+                            const UwScalars* sc) {
+    if (sc->done) return;
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PCG pieces
+// ------------------------------------------------------------------------------------------
+struct SetupArgs {
+    const double *psi, *dx, *dy, *weight;   // psi (N,M) or dx (N,M-1) & dy (N-1,M); weight (N,M) or null
+    double *wwx, *wwy, *r, *phi, *partial;
+    int N, M;
+};
+
+__device__ __forceinline__ double edge_w(const double* w, size_t i, size_t j) {
+    if (!w) return 1.0;
+    const double a = w[i] * w[i], b = w[j] * w[j];
+    return fmin(a, b);    // phase_unwrap.py:166-167
+}
+
+// weighted right-hand side r = A^T W^T W b, edge weights, phi = 0        (phase_unwrap.py:154-176)
+__global__ void __launch_bounds__(256) k_uw_setup(const SetupArgs a) {
+    __shared__ double red[256];
+    const int N = a.N, M = a.M;
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    double rsq = 0.0;
+    if (r < N && c < M) {
+        const size_t i = (size_t)r * M + c;
+        auto bx = [&](int rr, int cc) -> double {      // wrapped difference along axis 1 at (rr, cc), cc < M-1
+            const double d = a.psi ? a.psi[(size_t)rr * M + cc + 1] - a.psi[(size_t)rr * M + cc]
+                                   : a.dx[(size_t)rr * (M - 1) + cc];
+            return wrap_pi_d(d);
+        };
+        auto by = [&](int rr, int cc) -> double {      // along axis 0 at (rr, cc), rr < N-1
+            const double d = a.psi ? a.psi[(size_t)(rr + 1) * M + cc] - a.psi[(size_t)rr * M + cc]
+                                   : a.dy[(size_t)rr * M + cc];
+            return wrap_pi_d(d);
+        };
+        double v = 0.0;
+        if (c < M - 1) {
+            const double w = edge_w(a.weight, i, i + 1);
+            a.wwx[(size_t)r * (M - 1) + c] = w;
+            v += w * bx(r, c);
+        }
+        if (c > 0) v -= edge_w(a.weight, i - 1, i) * bx(r, c - 1);
+        if (r < N - 1) {
+            const double w = edge_w(a.weight, i, i + M);
+            a.wwy[i] = w;
+            v += w * by(r, c);
+        }
+        if (r > 0) v -= edge_w(a.weight, i - M, i) * by(r - 1, c);
+        a.r[i] = v;
+        a.phi[i] = 0.0;
+        rsq = v * v;
+    }
+    const double s = block_sum(rsq, red);
+    if (threadIdx.x == 0) a.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+// single-CTA scalar updates ------------------------------------------------------------------
+__device__ __forceinline__ double sum_partials(const double* part, int n, double* sh) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    return block_sum(s, sh);
+}
+
+__global__ void k_sc_init(UwScalars* sc, const double* part, int n, int kmax) {
+    __shared__ double sh[256];
+    const double s = sum_partials(part, n, sh);
+    if (threadIdx.x == 0) {
+        sc->r0sq = s;
+        sc->rsq = s;
+        sc->rz = sc->rz_prev = sc->pqp = sc->alpha = sc->beta = 0.0;
+        sc->k = 0;
+        sc->kmax = kmax;
+        sc->done = (s == 0.0);        // `while not all(rk == 0)`: nothing to do
+    }
+}
+
+__global__ void k_sc_beta(UwScalars* sc, const double* part, int n) {
+    __shared__ double sh[256];
+    if (sc->done) return;
+    const double s = sum_partials(part, n, sh);
+    if (threadIdx.x == 0) {
+        sc->k += 1;
+        sc->rz = s;
+        sc->beta = (sc->k == 1) ? 0.0 : s / sc->rz_prev;      // phase_unwrap.py:189-193
+        sc->rz_prev = s;
+    }
+}
+
+__global__ void k_sc_alpha(UwScalars* sc, const double* part, int n) {
+    __shared__ double sh[256];
+    if (sc->done) return;
+    const double s = sum_partials(part, n, sh);
+    if (threadIdx.x == 0) {
+        sc->pqp = s;
+        sc->alpha = sc->rz / s;                                 // :201
+    }
+}
+
+__global__ void k_sc_stop(UwScalars* sc, const double* part, int n) {
+    __shared__ double sh[256];
+    if (sc->done) return;
+    const double s = sum_partials(part, n, sh);
+    if (threadIdx.x == 0) {
+        sc->rsq = s;
+        // :206  k >= kmax or |r| < 1e-9 |r0| ; and the loop condition `not all(r == 0)`
+        if (sc->k >= sc->kmax || sqrt(s) < 1e-9 * sqrt(sc->r0sq) || s == 0.0) sc->done = 1;
+    }
+}
+
+// p = z + beta p  (first iteration: p = z)
+__global__ void __launch_bounds__(256) k_uw_update_p(const double* __restrict__ z, double* __restrict__ p, size_t n,
+                                                     const UwScalars* sc) {
+    if (sc->done) return;
+    const double beta = sc->beta;
+    const bool first = sc->k == 1;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+
+// q = Q p = A^T W^T W A p (phase_unwrap.py:118-132) and partial sums of <p, q>
+__global__ void __launch_bounds__(256) k_uw_apply_q(const double* __restrict__ p, const double* __restrict__ wwx,
+                                                    const double* __restrict__ wwy, double* __restrict__ q,
+                                                    double* __restrict__ partial, int N, int M, const UwScalars* sc) {
+    if (sc->done) return;
+    __shared__ double red[256];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    double pq = 0.0;
+    if (r < N && c < M) {
+        const size_t i = (size_t)r * M + c;
+        const double pc = p[i];
+        double v = 0.0;
+        if (c < M - 1) v += wwx[(size_t)r * (M - 1) + c] * (p[i + 1] - pc);
+        if (c > 0) v -= wwx[(size_t)r * (M - 1) + c - 1] * (pc - p[i - 1]);
+        if (r < N - 1) v += wwy[i] * (p[i + M] - pc);
+        if (r > 0) v -= wwy[i - M] * (pc - p[i - M]);
+        q[i] = v;
+        pq = pc * v;
+    }
+    const double s = block_sum(pq, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+// phi += alpha p ; r -= alpha q ; partial sums of r^2
+__global__ void __launch_bounds__(256) k_uw_update_xr(double* __restrict__ phi, double* __restrict__ r,
+                                                      const double* __restrict__ p, const double* __restrict__ q,
+                                                      double* __restrict__ partial, size_t n, const UwScalars* sc) {
+    if (sc->done) return;
+    __shared__ double red[256];
+    const double alpha = sc->alpha;
+    double rs = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        phi[i] = fma(alpha, p[i], phi[i]);
+        const double v = fma(-alpha, q[i], r[i]);
+        r[i] = v;
+        rs = fma(v, v, rs);
+    }
+    const double s = block_sum(rs, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static bool is_pow2(int n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+struct AxisTables {
+    double2 *tw, *mk;
+    double* ct;
+    int n, pow2;
+};
+
+struct UwPlan {
+    int N, M;
+    double *r, *z, *t, *p, *q, *wwx, *wwy, *partial;
+    AxisTables axN, axM;
+    UwScalars* sc;
+    int npart;
+};
+
+static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
+    Arena a(ws, ws_bytes);
+    const size_t nm = (size_t)N * M;
+    u.N = N; u.M = M;
+    u.r = a.take<double>(nm); u.z = a.take<double>(nm); u.t = a.take<double>(nm);
+    u.p = a.take<double>(nm); u.q = a.take<double>(nm);
+    u.wwx = a.take<double>(nm); u.wwy = a.take<double>(nm);
+    u.npart = 16384;
+    u.partial = a.take<double>(u.npart);
+    for (AxisTables* ax : {&u.axN, &u.axM}) {
+        const int n = ax == &u.axN ? N : M;
+        ax->n = n; ax->pow2 = is_pow2(n) && n <= kMaxFftLen;
+        ax->tw = a.take<double2>(n / 2 + 1);
+        ax->mk = a.take<double2>(n);
+        ax->ct = a.take<double>(ax->pow2 ? 1 : 4 * (size_t)n);
+    }
+    u.sc = a.take<UwScalars>(1);
+    return a.off;
+}
+
+template <int INVERSE>
+static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
+    a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n;
+    if (ax.pow2) {
+        const int half = ax.n / 2;
+        int threads = half < 32 ? 32 : (half > 512 ? 512 : half);
+        const int per = (half + threads - 1) / threads;     // butterflies per thread
+        const size_t smem = (size_t)ax.n * sizeof(double2);
+        auto go = [&](auto kern) -> int {
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+            kern<<<a.rows, threads, smem, st>>>(a);
+            return GPA_OK;
+        };
+        if (per <= 1) return INVERSE ? go(k_idct2_rows_pow2<1>) : go(k_dct2_rows_pow2<1>);
+        if (per <= 2) return INVERSE ? go(k_idct2_rows_pow2<2>) : go(k_dct2_rows_pow2<2>);
+        if (per <= 4) return INVERSE ? go(k_idct2_rows_pow2<4>) : go(k_dct2_rows_pow2<4>);
+        return INVERSE ? go(k_idct2_rows_pow2<8>) : go(k_dct2_rows_pow2<8>);
+    }
+    GPA_REQUIRE((size_t)ax.n * sizeof(double) <= 200 * 1024, "axis of length %d is too long for the direct DCT", ax.n);
+    const size_t smem = (size_t)ax.n * sizeof(double);
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(k_dct2_rows_direct<INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_dct2_rows_direct<INVERSE><<<a.rows, 256, smem, st>>>(a);
+    return GPA_OK;
+}
+
+static void transpose(const double* in, double* out, int rows, int cols, const UwScalars* sc, cudaStream_t st) {
+    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+    k_transpose<<<grid, dim3(32, 8), 0, st>>>(in, out, rows, cols, sc);
+}
+
+// z = idctn(dctn(r) / scale); partial[0..N) = row sums of r * z           (phase_unwrap.py:95-103)
+static int poisson_solve(const UwPlan& u, cudaStream_t st) {
+    const int N = u.N, M = u.M;
+    int rc;
+    DctArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = u.sc; a.dimN = N; a.dimM = M;
+    KernelTimer timer("uw_poisson_solve", st);
+    a.in = u.r; a.out = u.z; a.rows = N;                                   // rows along axis 1
+    if ((rc = launch_rows<0>(u.axM, a, st))) return rc;
+    transpose(u.z, u.t, N, M, u.sc, st);                                   // t: (M, N)
+    a.in = u.t; a.out = u.z; a.rows = M; a.fuse_scale = 1;                 // rows along axis 0, then / scale
+    if ((rc = launch_rows<0>(u.axN, a, st))) return rc;
+    a.fuse_scale = 0;
+    a.in = u.z; a.out = u.t; a.rows = M;                                   // inverse along axis 0
+    if ((rc = launch_rows<1>(u.axN, a, st))) return rc;
+    transpose(u.t, u.z, M, N, u.sc, st);                                   // z: (N, M)
+    a.in = u.z; a.out = u.t; a.rows = N; a.dot_with = u.r; a.partial = u.partial;
+    if ((rc = launch_rows<1>(u.axM, a, st))) return rc;                    // t = z_k, partial = <r, z> rows
+    return GPA_OK;
+}
+
+}  // namespace gpa
+
+using namespace gpa;
+
+extern "C" int gpa_unwrap_workspace_bytes(int N, int M, size_t* bytes) {
+    GPA_REQUIRE(bytes && N >= 2 && M >= 2, "frame must be at least 2x2");
+    UwPlan u;
+    *bytes = carve_unwrap(u, nullptr, 0, N, M) + 512;
+    return GPA_OK;
+}
+
+extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double* dy, const double* weight,
+                              int N, int M, int kmax, double* phi, int* iterations /*host, may be null*/,
+                              void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(phi && ws, "null pointer argument");
+    GPA_REQUIRE((psi != nullptr) != (dx != nullptr || dy != nullptr), "pass either psi or (dx, dy)");
+    GPA_REQUIRE(psi || (dx && dy), "both dx and dy are needed");
+    GPA_REQUIRE(N >= 2 && M >= 2, "frame must be at least 2x2 (got %dx%d)", N, M);
+    UwPlan u;
+    const size_t need = carve_unwrap(u, ws, ws_bytes, N, M);
+    if (need > ws_bytes) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nm = (size_t)N * M;
+    for (const AxisTables* ax : {&u.axN, &u.axM}) {
+        const int cnt = ax->pow2 ? ax->n : 4 * ax->n;
+        k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, ax->pow2);
+    }
+    dim3 g2(ceil_div(M, 64), ceil_div(N, 4));
+    const int n2 = g2.x * g2.y;
+    GPA_REQUIRE(n2 <= u.npart && N <= u.npart, "frame too large for the reduction scratch");
+    const int g1 = (int)((nm + 2047) / 2048 < 4096 ? (nm + 2047) / 2048 : 4096);
+    {
+        SetupArgs s;
+        s.psi = psi; s.dx = dx; s.dy = dy; s.weight = weight;
+        s.wwx = u.wwx; s.wwy = u.wwy; s.r = u.r; s.phi = phi; s.partial = u.partial; s.N = N; s.M = M;
+        KernelTimer timer("uw_setup", st);
+        k_uw_setup<<<g2, 256, 0, st>>>(s);
+        k_sc_init<<<1, 256, 0, st>>>(u.sc, u.partial, n2, kmax);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    // The reference always runs at least one iteration (k is tested after the update), so kmax <= 1
+    // behaves like kmax = 1.
+    const int iters = kmax < 1 ? 1 : kmax;
+    int done_host = 0;
+    for (int k = 0; k < iters; ++k) {
+        int rc = poisson_solve(u, st);                       // t = z
+        if (rc) return rc;
+        k_sc_beta<<<1, 256, 0, st>>>(u.sc, u.partial, N);
+        {
+            KernelTimer timer("uw_vector_ops", st);
+            k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
+            k_uw_apply_q<<<g2, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
+            k_sc_alpha<<<1, 256, 0, st>>>(u.sc, u.partial, n2);
+            k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
+            k_sc_stop<<<1, 256, 0, st>>>(u.sc, u.partial, g1);
+        }
+        GPA_CHECK_CUDA(cudaGetLastError());
+        if ((k & 7) == 7 && k + 1 < iters) {                 // stop enqueueing once converged
+            GPA_CHECK_CUDA(cudaMemcpyAsync(&done_host, &u.sc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GPA_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (done_host) break;
+        }
+    }
+    if (iterations) {
+        GPA_CHECK_CUDA(cudaMemcpyAsync(iterations, &u.sc->k, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GPA_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+    return GPA_OK;
+}

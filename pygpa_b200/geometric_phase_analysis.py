@@ -10,12 +10,14 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import engine
+from . import cuGPA as _cu
+from . import engine, solvers
 from .cuGPA import _sweep, _to_host
 from .mathtools import wrapToPi  # noqa: F401  (re-exported like the reference does)
 
 __all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_grad_opt",
-           "wfr2_grad", "wfr3"]
+           "wfr2_grad", "wfr3", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
+           "extract_displacement_field"]
 
 
 def optGPA(image, kvec, sigma=22):
@@ -87,3 +89,107 @@ def wfr3(image, sigma, klist, kref):
     host = {k: _to_host(res[k]) for k in ("lockin", "w")}
     torch.cuda.current_stream().synchronize()
     return {k: v.numpy() for k, v in host.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# phase -> displacement (K3 + K2)
+# ----------------------------------------------------------------------------------------------
+def _host(t):
+    h = _to_host(t)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def myweighed_lstsq(b, K, w):
+    """Per-pixel weighted least squares, minimise |w (K x - b)| (geometric_phase_analysis.py:97-113).
+    b (d, n, m), K (d, 2), w (d, >=n, >=m) -> (2, n, m).  Note K is taken as given (the reference's
+    callers pass 2 pi kvecs)."""
+    dev = engine.require_cuda()
+    K = np.asarray(K, dtype=np.float64)
+    return _host(solvers.lstsq(solvers.to_device_f64(b, dev), solvers.SRC_PLAIN, K / (2 * np.pi),
+                               solvers.to_device_f64(w, dev)))
+
+
+def reconstruct_u_inv(kvecs, b, weights=None, use_only_ks=None):
+    """Reconstruct the displacement field from unwrapped GPA phases
+    (geometric_phase_analysis.py:157-193): mean-subtracted phases, then (i) the global
+    pseudo-inverse of 2 pi kvecs, (ii) with weights the per-pixel weighted least squares, or
+    (iii) with use_only_ks the exact inverse for two chosen k-vectors."""
+    dev = engine.require_cuda()
+    kvecs = np.asarray(kvecs, dtype=np.float64)
+    bd = solvers.to_device_f64(b, dev)
+    d = kvecs.shape[0]
+    K = 2 * np.pi * kvecs
+    if use_only_ks is not None:
+        assert len(use_only_ks) == 2
+        sel = list(use_only_ks)
+        mat = np.zeros((2, d))
+        mat[:, sel] = np.linalg.inv(K[sel])
+        return _host(solvers.lstsq(bd, solvers.SRC_PLAIN, kvecs, matrix=mat, subtract_mean=True))
+    if weights is None:
+        if d != 3:   # the reference reshapes to (3, -1) (geometric_phase_analysis.py:185)
+            raise ValueError("cannot reshape: the unweighted branch of reconstruct_u_inv needs exactly 3 k-vectors")
+        return _host(solvers.lstsq(bd, solvers.SRC_PLAIN, kvecs, matrix=np.linalg.pinv(K), subtract_mean=True))
+    return _host(solvers.lstsq(bd, solvers.SRC_PLAIN, kvecs, solvers.to_device_f64(weights, dev), subtract_mean=True))
+
+
+def reconstruct_u_inv_from_phases(kvecs, phases, weights, weighted_unwrap=True, pre_diff=False):
+    """Displacement field from wrapped phases: project the wrapped phase differences onto
+    Cartesian displacement gradients per pixel, then integrate by weighted least squares
+    (geometric_phase_analysis.py:196-245)."""
+    dev = engine.require_cuda()
+    u = solvers.displacement_from_phases(np.asarray(kvecs, dtype=np.float64), solvers.to_device_f64(phases, dev),
+                                         solvers.to_device_f64(weights, dev), weighted_unwrap, pre_diff)
+    return _host(u)
+
+
+_DEVICE_SWEEPS = {}
+
+
+def extract_displacement_field(image, kvecs, sigma=None, kwscale=2.5, ksteps=3, return_gs=False,
+                               wfr_func=optwfr2, deconvolve=False):
+    """Top-level convenience function (geometric_phase_analysis.py:907-932).
+
+    With one of this package's sweeps as ``wfr_func`` (the default) the whole chain — sweep per
+    k-vector, phases and masked weights, per-pixel least squares, PCG integration — stays on the
+    GPU and only u comes back.  Any other callable is invoked exactly like the reference does and
+    its NumPy results are uploaded for the tail.  deconvolve=True needs scikit-image's Wiener
+    filter, which is outside this package: NotImplementedError."""
+    if deconvolve:
+        raise NotImplementedError("deconvolve=True (skimage Wiener deconvolution) is not part of the B200 hot path")
+    dev = engine.require_cuda()
+    image = np.asarray(image, dtype=np.float64)
+    kvecs = np.asarray(kvecs, dtype=np.float64)
+    norms = np.linalg.norm(kvecs, axis=1)
+    kw = norms.mean() / kwscale
+    if sigma is None:
+        sigma = int(np.ceil(1 / norms.min()))
+    kstep = kw / ksteps
+    dr = int(2 * sigma)
+    centred = image - image.mean()
+    mode = _DEVICE_SWEEPS.get(wfr_func)
+    if mode is not None and not return_gs:
+        img = engine.image_to_device(centred, dev)
+        phs, wts = [], []
+        for pk in kvecs:
+            wxs, wys = engine.grid_axes(pk[0], pk[1], kw, kstep)
+            plan = engine.SweepPlan(img.shape, wxs, wys, sigma, device=dev)
+            res = plan.run(img, pk, engine.GRAD_NONE, want_kidx=False)
+            ph, wt = solvers.phase_weight(res["lockin"], dr)
+            phs.append(ph)
+            wts.append(wt)
+        u = solvers.displacement_from_phases(kvecs, torch.stack(phs), torch.stack(wts))
+        return _host(u)
+    gs = [wfr_func(centred, sigma, pk[0], pk[1], kw=kw, kstep=kstep) for pk in kvecs]
+    phases = np.stack([np.angle(g['lockin']) for g in gs])
+    mask = np.zeros_like(image, dtype=bool)
+    mask[dr:-dr, dr:-dr] = 1.
+    weights = np.stack([np.abs(g['lockin']) for g in gs]) * (mask + 1e-6)
+    u = reconstruct_u_inv_from_phases(kvecs, phases, weights)
+    if return_gs:
+        return u, gs
+    return u
+
+
+for _f in (optwfr2, wfr2_grad_opt, wfr2_grad, _cu.wfr2_grad_opt, _cu.wfr2_grad_single):
+    _DEVICE_SWEEPS[_f] = True

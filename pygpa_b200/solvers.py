@@ -1,0 +1,112 @@
+"""Device-side drivers of K2 (PCG phase unwrap) and K3 (per-pixel least squares).
+torch tensors in, torch tensors out; all float64 like the reference."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import _count, _ptr, _stream, require_cuda, workspace
+
+SRC_PLAIN, SRC_DIFF1, SRC_DIFF0, SRC_PREDIFF0, SRC_PREDIFF1 = range(5)
+LSQ_WEIGHTED, LSQ_MATRIX = 0, 1
+MAX_D = 8
+
+
+def to_device_f64(a, device=None):
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device, non_blocking=True)
+
+
+def unwrap(psi=None, dx=None, dy=None, weight=None, kmax=100, return_iters=False):
+    """PCG unwrap on the device.  Give psi (N, M) or the gradients dx (N, M-1), dy (N-1, M)."""
+    lib = _lib.load()
+    if psi is not None:
+        n, m = psi.shape
+        dev = psi.device
+    else:
+        n, m = dx.shape[0], dy.shape[1]
+        if dx.shape != (n, m - 1) or dy.shape != (n - 1, m):
+            raise ValueError(f"dx {tuple(dx.shape)} / dy {tuple(dy.shape)} do not describe one (N, M) grid")
+        dev = dx.device
+    if weight is not None and tuple(weight.shape) != (n, m):
+        raise ValueError("weight must have the shape of the unwrapped phase")
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.gpa_unwrap_workspace_bytes(n, m, ctypes.byref(nbytes)))
+    ws = workspace(nbytes.value, dev)
+    phi = torch.empty((n, m), dtype=torch.float64, device=dev)
+    iters = ctypes.c_int(0)
+    _lib.check(lib.gpa_unwrap_pcg(_ptr(psi), _ptr(dx), _ptr(dy), _ptr(weight), n, m, int(kmax), _ptr(phi),
+                                  ctypes.byref(iters) if return_iters else None, _ptr(ws), ws.numel(), _stream()))
+    _count(4 + 12 * max(1, int(kmax)))
+    return (phi, iters.value) if return_iters else phi
+
+
+def lstsq(src, kind, kvecs, weights=None, matrix=None, subtract_mean=False):
+    """Per-pixel least squares on the device, (2, n, m) float64 (see include/gpa_b200.h, K3)."""
+    lib = _lib.load()
+    kv = np.ascontiguousarray(kvecs, dtype=np.float64).reshape(-1, 2)
+    d = kv.shape[0]
+    if d > MAX_D:
+        raise ValueError(f"at most {MAX_D} k-vectors are supported")
+    if src.shape[0] != d:
+        raise ValueError("first axis of the phases must match the number of k-vectors")
+    n, m = int(src.shape[1]), int(src.shape[2])
+    on, om = {SRC_PLAIN: (n, m), SRC_DIFF1: (n, m - 1), SRC_DIFF0: (n - 1, m),
+              SRC_PREDIFF0: (n, m - 1), SRC_PREDIFF1: (n - 1, m)}[kind]
+    out = torch.empty((2, on, om), dtype=torch.float64, device=src.device)
+    ws_t, ws_n = None, 0
+    if subtract_mean:
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.gpa_lstsq_workspace_bytes(d, ctypes.byref(nbytes)))
+        ws_t = workspace(nbytes.value, src.device)
+        ws_n = ws_t.numel()
+    mat = None
+    if matrix is not None:
+        mat = np.ascontiguousarray(matrix, dtype=np.float64)
+        assert mat.shape == (2, d)
+    wn, wm = (int(weights.shape[1]), int(weights.shape[2])) if weights is not None else (0, 0)
+    _lib.check(lib.gpa_lstsq_u(_ptr(src), kind, _ptr(weights), wn, wm, _lib.as_pd(kv), d, n, m,
+                               LSQ_MATRIX if matrix is not None else LSQ_WEIGHTED,
+                               _lib.as_pd(mat) if mat is not None else None, int(subtract_mean),
+                               _ptr(out), _ptr(ws_t), ws_n, _stream()))
+    _count(3 if subtract_mean else 1)
+    return out
+
+
+def norm_axis0(w):
+    lib = _lib.load()
+    out = torch.empty(w.shape[1:], dtype=torch.float64, device=w.device)
+    _lib.check(lib.gpa_norm_axis0(_ptr(w), int(w.shape[0]), out.numel(), _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
+def phase_weight(lockin, border, eps=1e-6):
+    """(phases, weights) float64 from a complex lock-in tensor (extract_displacement_field glue)."""
+    lib = _lib.load()
+    n, m = lockin.shape
+    ph = torch.empty((n, m), dtype=torch.float64, device=lockin.device)
+    w = torch.empty((n, m), dtype=torch.float64, device=lockin.device)
+    _lib.check(lib.gpa_phase_weight(_ptr(lockin), int(lockin.dtype == torch.complex128), n, m, int(border),
+                                    float(eps), _ptr(ph), _ptr(w), _stream()))
+    _count(1)
+    return ph, w
+
+
+def displacement_from_phases(kvecs, phases, weights, weighted_unwrap=True, pre_diff=False):
+    """reconstruct_u_inv_from_phases (geometric_phase_analysis.py:196-245) on device tensors:
+    wrapped differences -> two per-pixel least-squares solves -> two PCG integrations (kmax=10)."""
+    k0, k1 = (SRC_PREDIFF0, SRC_PREDIFF1) if pre_diff else (SRC_DIFF1, SRC_DIFF0)
+    dudx = lstsq(phases, k0, kvecs, weights)
+    dudy = lstsq(phases, k1, kvecs, weights)
+    if weighted_unwrap:
+        wn = norm_axis0(weights)
+        us = [unwrap(dx=dudx[i], dy=dudy[i], weight=wn, kmax=10) for i in range(2)]
+    else:
+        us = [unwrap(dx=dudx[i], dy=dudy[i]) for i in range(2)]
+    return torch.stack(us)
