@@ -192,6 +192,31 @@ int gpa_unwrap_pcg(const double* psi, const double* dx, const double* dy, const 
                    int N, int M, int kmax, double* phi, int* iterations /*host or NULL*/,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K4 — Lawler-Fujita: invert the displacement field and resample (float64).
+ *
+ * Replaces: invert_u_overlap (geometric_phase_analysis.py:262-300; invert_u :248-259 is the
+ * edge = 0 case up to its `- edge` typo) and undistort_image (:935-974), i.e. 73 calls of
+ * scipy.ndimage.map_coordinates(order=3) — mode='nearest' for the fixed-point inversion,
+ * mode='constant', cval=0 for the final resample.  The cubic-spline prefilter of u runs once
+ * instead of 72 times and the fixed-point loop of a pixel runs in registers.
+ * ------------------------------------------------------------------------------------------ */
+int gpa_lawler_workspace_bytes(int N, int M, int edge, size_t* bytes);
+
+/* out (2, N+2 edge, M+2 edge): u_it <- (scale u)(r), then `iters` times u_it <- (scale u)(r + u_it),
+ * r on the grid [-edge, N+edge) x [-edge, M+edge), scipy mode='nearest'.  u is (2, N, M). */
+int gpa_invert_u(const double* u, int N, int M, double scale, int iters, int edge, double* out,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* out (N, M) = cubic-spline resampling of img at (r + u_inv[0], c + u_inv[1]), 0 outside the frame
+ * (scipy mode='constant', cval=0). */
+int gpa_resample_image(const double* img, int N, int M, const double* u_inv, double* out,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* undistort_image(deformed, u): gpa_invert_u(u, scale=-1, iters, edge=0) then gpa_resample_image. */
+int gpa_undistort_image(const double* img, const double* u, int N, int M, int iters, double* out,
+                        void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,312 @@
+// K4 — Lawler-Fujita: fixed-point inversion of the displacement field and cubic-spline
+// resampling (float64), sm_100a.
+//
+// Reference semantics: invert_u_overlap (pyGPA/geometric_phase_analysis.py:262-300) and
+// undistort_image (:935-974), i.e. scipy.ndimage.map_coordinates(order=3) in mode='nearest'
+// (inversion) and mode='constant', cval=0 (final resample).  SciPy's rules are restated in
+// oracle/spline_restatement.py; in short: cubic B-spline, pole sqrt(3)-2, gain 6 per axis;
+// 'nearest' = 12-sample edge padding + reflect initial conditions + tap indices clamped;
+// 'constant' = mirror initial conditions + mirrored taps + 0 outside [0, n-1].
+//
+// What is different from the reference: it re-runs the spline prefilter of the unchanged u in
+// each of its 72 map_coordinates calls; here the prefilter runs once, both components are
+// interleaved so one 16-byte load fetches both coefficients of a tap, and the whole fixed-point
+// loop of a pixel runs in registers inside ONE kernel (no intermediate u_it ever touches HBM).
+#include "common.cuh"
+
+namespace gpa {
+
+constexpr int kPad = 12;                 // scipy's _prepad_for_spline_filter
+constexpr int kInitTerms = 96;           // |pole|^96 ~ 1e-55: the initial-condition sums are exact in double
+__device__ __constant__ const double kPole = -0.26794919243112270647255365849413;   // sqrt(3) - 2
+
+enum { kNearest = 0, kConstant = 1 };
+
+// Prefilter along axis 0 of a (n x cols) array: one thread per column, coalesced across the warp.
+// Source mapping (first pass only): s[i][c] = scale * src[clamp(i - pad)][clamp(c - pad)];
+// later passes run in place (src == dst, pad == 0, src dims == dst dims).
+struct PrefilterArgs {
+    const double* src;
+    double* dst;
+    int n, cols;            // destination extent along the filter axis / across it
+    int src_n, src_cols;    // source extent
+    int pad;
+    double scale;
+    int boundary;           // kNearest -> reflect init, kConstant -> mirror init
+    int dst_stride;         // elements between consecutive i (>= cols); lets pass 1 write every 2nd slot
+    int dst_elem;           // element stride within a row (1, or 2 for the interleaved layout)
+};
+
+__global__ void __launch_bounds__(128) k_prefilter_axis0(const PrefilterArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.cols) return;
+    const double z = kPole;
+    const int n = a.n;
+    int cs = c - a.pad;
+    cs = cs < 0 ? 0 : (cs >= a.src_cols ? a.src_cols - 1 : cs);
+    auto s = [&](int i) -> double {
+        int r = i - a.pad;
+        r = r < 0 ? 0 : (r >= a.src_n ? a.src_n - 1 : r);
+        return 6.0 * a.scale * a.src[(size_t)r * a.src_cols + cs];
+    };
+    double* out = a.dst + (size_t)c * a.dst_elem;    // may alias a.src (in-place second pass)
+    const size_t st = (size_t)a.dst_stride;
+    if (n == 1) {
+        out[0] = a.scale * a.src[cs];
+        return;
+    }
+    // ---- causal initial condition
+    double c0;
+    const int terms = n < kInitTerms ? n : kInitTerms;
+    if (a.boundary == kNearest) {          // reflect (half-sample symmetric)
+        const double zn = pow(z, (double)n);
+        double acc = 0.0, zi = 1.0;
+        for (int i = 0; i < terms; ++i) {
+            acc += zi * (s(i) + zn * s(n - 1 - i));
+            zi *= z;
+        }
+        c0 = acc * z / (1.0 - zn * zn) + s(0);
+    } else {                               // mirror (whole-sample symmetric)
+        const double zn1 = pow(z, (double)(n - 1));
+        double acc = s(0) + zn1 * s(n - 1), zi = z;
+        const int last = (n - 1) < kInitTerms ? (n - 1) : kInitTerms;
+        for (int i = 1; i < last; ++i) {
+            acc += zi * (s(i) + zn1 * s(n - 1 - i));
+            zi *= z;
+        }
+        c0 = acc / (1.0 - zn1 * zn1);
+    }
+    // ---- causal sweep
+    double prev = c0;
+    out[0] = prev;
+    for (int i = 1; i < n; ++i) {
+        prev = fma(z, prev, s(i));
+        out[i * st] = prev;
+    }
+    // ---- anti-causal initial condition and sweep
+    double nxt;
+    if (a.boundary == kNearest) nxt = prev * (z / (z - 1.0));
+    else nxt = (z * out[(size_t)(n - 2) * st] + prev) * z / (z * z - 1.0);
+    out[(size_t)(n - 1) * st] = nxt;
+    for (int i = n - 2; i >= 0; --i) {
+        nxt = z * (nxt - out[i * st]);
+        out[i * st] = nxt;
+    }
+}
+
+__global__ void k_transpose_plain(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
+                                  int out_elem, int out_off) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[((size_t)c * rows + r) * out_elem + out_off] = tile[threadIdx.x][i];
+    }
+}
+
+// cubic B-spline weights for the fractional offset t in [0, 1)
+__device__ __forceinline__ void bspline_weights(double t, double (&w)[4]) {
+    const double t2 = t * t, t3 = t2 * t, u = 1.0 - t;
+    w[0] = u * u * u * (1.0 / 6.0);
+    w[1] = (3.0 * t3 - 6.0 * t2 + 4.0) * (1.0 / 6.0);
+    w[2] = (-3.0 * t3 + 3.0 * t2 + 3.0 * t + 1.0) * (1.0 / 6.0);
+    w[3] = t3 * (1.0 / 6.0);
+}
+
+template <int MODE>
+__device__ __forceinline__ int tap_index(int i, int n) {
+    if (MODE == kNearest) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    if (n == 1) return 0;
+    const int s2 = 2 * n - 2;
+    i = (i < 0 ? -i : i) % s2;
+    return i >= n ? s2 - i : i;
+}
+
+// coefficient arrays: (Np, Mp) of T (double or double2), evaluated at (cx, cy) in array coordinates
+template <int MODE, typename T>
+__device__ __forceinline__ T spline_eval(const T* __restrict__ coef, int Np, int Mp, double cx, double cy) {
+    // beyond one sample outside every tap is clamped anyway; this also keeps the int conversion safe
+    if (MODE == kNearest) {
+        cx = fmin(fmax(cx, -4.0), (double)Np + 3.0);
+        cy = fmin(fmax(cy, -4.0), (double)Mp + 3.0);
+    }
+    const double fx = floor(cx), fy = floor(cy);
+    double wx[4], wy[4];
+    bspline_weights(cx - fx, wx);
+    bspline_weights(cy - fy, wy);
+    const int ix = (int)fx - 1, iy = (int)fy - 1;
+    int ty[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ty[j] = tap_index<MODE>(iy + j, Mp);
+    T acc;
+    if constexpr (sizeof(T) == sizeof(double2)) acc = make_double2(0.0, 0.0);
+    else acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T* __restrict__ row = coef + (size_t)tap_index<MODE>(ix + i, Np) * Mp;
+        T r;
+        if constexpr (sizeof(T) == sizeof(double2)) {
+            r = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = __ldg(row + ty[j]);
+                r.x = fma(wy[j], v.x, r.x);
+                r.y = fma(wy[j], v.y, r.y);
+            }
+            acc.x = fma(wx[i], r.x, acc.x);
+            acc.y = fma(wx[i], r.y, acc.y);
+        } else {
+            r = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r = fma(wy[j], __ldg(row + ty[j]), r);
+            acc = fma(wx[i], r, acc);
+        }
+    }
+    return acc;
+}
+
+// whole fixed-point inversion of one output pixel in registers:
+//   u_it <- u(r);  repeat iters times: u_it <- u(r + u_it)         (geometric_phase_analysis.py:291-299)
+__global__ void __launch_bounds__(256) k_invert_u(const double2* __restrict__ coef, int Np, int Mp, int N, int M,
+                                                  int edge, int iters, double* __restrict__ out) {
+    const int on = N + 2 * edge, om = M + 2 * edge;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (r >= on || c >= om) return;
+    const double x = (double)(r - edge) + kPad, y = (double)(c - edge) + kPad;   // padded-array coordinates
+    double2 u = spline_eval<kNearest>(coef, Np, Mp, x, y);
+    for (int it = 0; it < iters; ++it) u = spline_eval<kNearest>(coef, Np, Mp, x + u.x, y + u.y);
+    out[(size_t)r * om + c] = u.x;
+    out[(size_t)on * om + (size_t)r * om + c] = u.y;
+}
+
+// out(r, c) = spline(img)(r + u0(r,c), c + u1(r,c)), 0 outside [0, N-1] x [0, M-1]     (:973)
+__global__ void __launch_bounds__(256) k_resample(const double* __restrict__ coef, int N, int M,
+                                                  const double* __restrict__ u, double* __restrict__ out) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (r >= N || c >= M) return;
+    const size_t i = (size_t)r * M + c;
+    const double cx = (double)r + u[i], cy = (double)c + u[(size_t)N * M + i];
+    double v = 0.0;
+    // comparisons written so that NaN coordinates fall outside
+    if (cx >= 0.0 && cx <= (double)(N - 1) && cy >= 0.0 && cy <= (double)(M - 1))
+        v = spline_eval<kConstant>(coef, N, M, cx, cy);
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+// Prefilter `src` (N, M) [times scale] into dst with element stride dst_elem / offset dst_off;
+// dst extent is (N + 2 pad, M + 2 pad).  tmp: two scratch arrays of that extent.
+static int prefilter_2d(const double* src, int N, int M, double scale, int boundary, double* dst, int dst_elem,
+                        int dst_off, double* tmp0, double* tmp1, cudaStream_t st) {
+    const int pad = boundary == kNearest ? kPad : 0;
+    const int Np = N + 2 * pad, Mp = M + 2 * pad;
+    PrefilterArgs a;
+    a.src = src; a.dst = tmp0; a.n = Np; a.cols = Mp; a.src_n = N; a.src_cols = M; a.pad = pad; a.scale = scale;
+    a.boundary = boundary; a.dst_stride = Mp; a.dst_elem = 1;
+    k_prefilter_axis0<<<ceil_div(Mp, 128), 128, 0, st>>>(a);                       // along axis 0 (+ padding)
+    dim3 g1(ceil_div(Mp, 32), ceil_div(Np, 32));
+    k_transpose_plain<<<g1, dim3(32, 8), 0, st>>>(tmp0, tmp1, Np, Mp, 1, 0);        // tmp1: (Mp, Np)
+    a.src = tmp1; a.dst = tmp1; a.n = Mp; a.cols = Np; a.src_n = Mp; a.src_cols = Np; a.pad = 0; a.scale = 1.0;
+    a.dst_stride = Np;
+    k_prefilter_axis0<<<ceil_div(Np, 128), 128, 0, st>>>(a);                       // along axis 1
+    dim3 g2(ceil_div(Np, 32), ceil_div(Mp, 32));
+    k_transpose_plain<<<g2, dim3(32, 8), 0, st>>>(tmp1, dst, Mp, Np, dst_elem, dst_off);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+}  // namespace gpa
+
+using namespace gpa;
+
+extern "C" int gpa_lawler_workspace_bytes(int N, int M, int edge, size_t* bytes) {
+    GPA_REQUIRE(bytes && N >= 1 && M >= 1 && edge >= 0, "bad argument");
+    const size_t np = (size_t)(N + 2 * kPad) * (M + 2 * kPad);
+    const size_t out = (size_t)(N + 2 * edge) * (M + 2 * edge);
+    // interleaved coefficients (2 np) + 2 scratch (np each) + image coefficients (N M) + u_inv (2 out)
+    *bytes = (4 * np + (size_t)N * M + 2 * out) * sizeof(double) + 8 * 256;
+    return GPA_OK;
+}
+
+extern "C" int gpa_invert_u(const double* u, int N, int M, double scale, int iters, int edge, double* out,
+                            void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(u && out && ws, "null pointer argument");
+    GPA_REQUIRE(N >= 1 && M >= 1 && iters >= 0 && edge >= 0, "bad argument");
+    const int Np = N + 2 * kPad, Mp = M + 2 * kPad;
+    const size_t np = (size_t)Np * Mp;
+    Arena a(ws, ws_bytes);
+    double* coef = a.take<double>(2 * np);
+    double* t0 = a.take<double>(np);
+    double* t1 = a.take<double>(np);
+    if (!a.ok()) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, a.off);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    {
+        KernelTimer t("lf_prefilter", st);
+        for (int comp = 0; comp < 2; ++comp)
+            if ((rc = prefilter_2d(u + (size_t)comp * N * M, N, M, scale, kNearest, coef, 2, comp, t0, t1, st))) return rc;
+    }
+    {
+        KernelTimer t("k_invert_u", st);
+        dim3 grid(ceil_div(M + 2 * edge, 32), ceil_div(N + 2 * edge, 8));
+        k_invert_u<<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(coef), Np, Mp, N, M, edge, iters, out);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_resample_image(const double* img, int N, int M, const double* u_inv, double* out,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(img && u_inv && out && ws, "null pointer argument");
+    GPA_REQUIRE(N >= 1 && M >= 1, "bad shape");
+    const size_t nm = (size_t)N * M;
+    Arena a(ws, ws_bytes);
+    double* coef = a.take<double>(nm);
+    double* t0 = a.take<double>(nm);
+    double* t1 = a.take<double>(nm);
+    if (!a.ok()) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, a.off);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    {
+        KernelTimer t("lf_prefilter", st);
+        if ((rc = prefilter_2d(img, N, M, 1.0, kConstant, coef, 1, 0, t0, t1, st))) return rc;
+    }
+    {
+        KernelTimer t("k_resample", st);
+        dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
+        k_resample<<<grid, 256, 0, st>>>(coef, N, M, u_inv, out);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_undistort_image(const double* img, const double* u, int N, int M, int iters, double* out,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(ws != nullptr && N >= 1 && M >= 1, "bad argument");
+    Arena a(ws, ws_bytes);
+    double* u_inv = a.take<double>(2 * (size_t)N * M);
+    const size_t used = align_up(a.off, 256);
+    if (used >= ws_bytes) {
+        set_error("workspace too small (%zu)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    char* rest = static_cast<char*>(ws) + used;
+    int rc = gpa_invert_u(u, N, M, -1.0, iters, 0, u_inv, rest, ws_bytes - used, stream);    // invert_u_overlap(-u), :971
+    if (rc) return rc;
+    return gpa_resample_image(img, N, M, u_inv, out, rest, ws_bytes - used, stream);
+}

@@ -17,7 +17,7 @@ from .mathtools import wrapToPi  # noqa: F401  (re-exported like the reference d
 
 __all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_grad_opt",
            "wfr2_grad", "wfr3", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
-           "extract_displacement_field"]
+           "extract_displacement_field", "invert_u", "invert_u_overlap", "undistort_image"]
 
 
 def optGPA(image, kvec, sigma=22):
@@ -141,6 +141,38 @@ def reconstruct_u_inv_from_phases(kvecs, phases, weights, weighted_unwrap=True, 
     u = solvers.displacement_from_phases(np.asarray(kvecs, dtype=np.float64), solvers.to_device_f64(phases, dev),
                                          solvers.to_device_f64(weights, dev), weighted_unwrap, pre_diff)
     return _host(u)
+
+
+def invert_u_overlap(us, iters=35, edge=0, mode='nearest'):
+    """Find the inverse of the displacement us, u_it(r + us(r)) = r, by fixed-point iteration of
+    cubic-spline resampling on a grid grown by `edge` (geometric_phase_analysis.py:262-300)."""
+    if mode != 'nearest':
+        raise NotImplementedError("the B200 Lawler-Fujita kernel implements scipy mode='nearest' (the reference default)")
+    dev = engine.require_cuda()
+    us = np.asarray(us, dtype=np.float64)
+    if us.ndim != 3 or us.shape[0] != 2:
+        raise ValueError("us must have shape (2, N, M)")
+    return _host(solvers.invert_u(solvers.to_device_f64(us, dev), iters=iters, edge=edge))
+
+
+def invert_u(us, iters=35, edge=0, mode='nearest'):
+    """geometric_phase_analysis.py:248-259.  For edge = 0 (the only value for which the reference's
+    coordinate arithmetic is consistent) this equals invert_u_overlap: one initial evaluation and
+    `iters` fixed-point rounds."""
+    if edge != 0:
+        raise NotImplementedError("invert_u with edge != 0 is not supported; use invert_u_overlap")
+    return invert_u_overlap(us, iters=iters, edge=0, mode=mode)
+
+
+def undistort_image(deformed, u):
+    """Reconstruct an undistorted image from a deformed image and the displacement field u
+    (Lawler-Fujita; geometric_phase_analysis.py:935-974)."""
+    dev = engine.require_cuda()
+    deformed = np.asarray(deformed, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    if u.shape != (2,) + deformed.shape:
+        raise ValueError("u must have shape (2,) + deformed.shape")
+    return _host(solvers.undistort(solvers.to_device_f64(deformed, dev), solvers.to_device_f64(u, dev)))
 
 
 _DEVICE_SWEEPS = {}

@@ -110,3 +110,32 @@ def displacement_from_phases(kvecs, phases, weights, weighted_unwrap=True, pre_d
     else:
         us = [unwrap(dx=dudx[i], dy=dudy[i]) for i in range(2)]
     return torch.stack(us)
+
+
+def _lawler_ws(n, m, edge, device):
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.gpa_lawler_workspace_bytes(n, m, edge, ctypes.byref(nbytes)))
+    return workspace(nbytes.value, device)
+
+
+def invert_u(u, iters=35, edge=0, scale=1.0):
+    """Fixed-point inverse of the displacement field (2, N, M) -> (2, N+2e, M+2e), on the device."""
+    lib = _lib.load()
+    n, m = int(u.shape[1]), int(u.shape[2])
+    ws = _lawler_ws(n, m, edge, u.device)
+    out = torch.empty((2, n + 2 * edge, m + 2 * edge), dtype=torch.float64, device=u.device)
+    _lib.check(lib.gpa_invert_u(_ptr(u), n, m, float(scale), int(iters), int(edge), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    _count(9)
+    return out
+
+
+def undistort(img, u, iters=35):
+    """undistort_image on the device: invert -u, then resample img (N, M) with zeros outside."""
+    lib = _lib.load()
+    n, m = int(img.shape[0]), int(img.shape[1])
+    ws = _lawler_ws(n, m, 0, img.device)
+    out = torch.empty((n, m), dtype=torch.float64, device=img.device)
+    _lib.check(lib.gpa_undistort_image(_ptr(img), _ptr(u), n, m, int(iters), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    _count(14)
+    return out
