@@ -116,6 +116,24 @@ int gpa_sweep_argmax(const float* img, int N, int M,
                      const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
                      unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
 
+/* Multirate form of gpa_sweep_argmax (same key, same merge rules).  The Gaussian is factorised,
+ * G_sigma = G_a * G_b (sigma_a^2 + sigma_b^2 = sigma^2): G_a is applied with decimation by
+ * `stride` (2, 4 or 8) per axis and G_b as a `stride`-fold interpolator, which cuts the taps per
+ * candidate about five-fold; the aliasing this introduces is below 1e-7 of the signal for the
+ * strides the host chooses (pygpa_b200/_taps.py), far inside the near-tie budget.  Only the
+ * arg-max decision uses these amplitudes: gpa_sweep_finalize recomputes the winner in the direct
+ * form.  taps_a*: decimation filter (2 Ra + 1 taps per axis); taps_b*: interpolation filter
+ * (2 Rb + 1 taps, not yet multiplied by the stride).  N and M must be multiples of stride. */
+int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int stride,
+                                 int Rax, int Ray, int Rb, int planes_in_flight, size_t* bytes);
+int gpa_sweep_argmax_mr(const float* img, int N, int M,
+                        const double* wx_rows /*host*/, int n_rows,
+                        const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                        int plane_begin, int plane_end, int stride,
+                        const float* taps_ax /*host*/, int Rax, const float* taps_ay /*host*/, int Ray,
+                        const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
+                        unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
+
 /* For every pixel whose winning candidate (decoded from key) lies in planes
  * [plane_begin, plane_end): recompute that candidate's lock-in at the pixel and its four
  * neighbours and write

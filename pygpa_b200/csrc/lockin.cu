@@ -61,46 +61,51 @@ __global__ void k_build_phasors(float2* __restrict__ table, double* __restrict__
 // must be readable (the callers pad their tiles / the tap table is zero-filled).
 constexpr int kAhead = 2;
 
+// acc[p] += sum_{d<cnt} taps.g[off + d] * sample(p + d)
 template <int P, typename Load>
-__device__ __forceinline__ void fir_block(float2 (&acc)[P], const TapTable& taps, int T, Load load) {
+__device__ __forceinline__ void fir_phase(float2 (&acc)[P], const TapTable& taps, int off, int cnt, Load load) {
     static_assert(P % kAhead == 0, "P must be a multiple of the prefetch depth");
     float2 win[P], gq[kAhead], sq[kAhead];
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        win[p] = load(p);
-        acc[p] = make_float2(0.f, 0.f);
-    }
+    for (int p = 0; p < P; ++p) win[p] = load(p);
 #pragma unroll
     for (int a = 0; a < kAhead; ++a) {
-        gq[a] = taps.g[a];
+        gq[a] = taps.g[off + a];
         sq[a] = load(P + a);
     }
     int d0 = 0;
-    for (; d0 + P <= T; d0 += P) {
+    for (; d0 + P <= cnt; d0 += P) {
 #pragma unroll
         for (int u = 0; u < P; ++u) {
             const float2 g = gq[u % kAhead];
             const float2 s = sq[u % kAhead];
-            gq[u % kAhead] = taps.g[d0 + u + kAhead];
+            gq[u % kAhead] = taps.g[off + d0 + u + kAhead];
             sq[u % kAhead] = load(d0 + u + P + kAhead);
 #pragma unroll
             for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
             win[u] = s;
         }
     }
-    const int rem = T - d0;
+    const int rem = cnt - d0;
 #pragma unroll
     for (int u = 0; u < P - 1; ++u) {
         if (u < rem) {  // warp-uniform
             const float2 g = gq[u % kAhead];
             const float2 s = sq[u % kAhead];
-            gq[u % kAhead] = taps.g[d0 + u + kAhead];
+            gq[u % kAhead] = taps.g[off + d0 + u + kAhead];
             sq[u % kAhead] = load(d0 + u + P + kAhead);
 #pragma unroll
             for (int p = 0; p < P; ++p) acc[p] = __ffma2_rn(g, win[(u + p) % P], acc[p]);
             win[u] = s;
         }
     }
+}
+
+template <int P, typename Load>
+__device__ __forceinline__ void fir_block(float2 (&acc)[P], const TapTable& taps, int T, Load load) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[p] = make_float2(0.f, 0.f);
+    fir_phase<P>(acc, taps, 0, T, load);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,6 +259,245 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
                         ((unsigned long long)__float_as_uint(best[p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
                     atomicMax(prm.key + (size_t)x * prm.M + y, k);
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// multirate arg-max sweep
+// ---------------------------------------------------------------------------------------------
+// The Gaussian factorises, G_sigma = G_a * G_b with sigma_a^2 + sigma_b^2 = sigma^2, and after G_a
+// the signal is band-limited, so it can be decimated by S per axis and G_b applied as an S-fold
+// interpolator (aliasing ~ exp(-2 pi^2 sigma_a^2 sigma_b^2 / (sigma^2 S^2)) < 1e-7 for the strides the
+// host picks).  Per candidate the cost falls from T = 2R+1 full-rate taps to ~T_a/S^2 + W/S + W with
+// W = 11 coarse taps:
+//   k_mr_pass1  P1[wy](x', my)    = sum_y' G_a(S my - y') img(x', y') e^{2 pi i wy y'}       (per plane)
+//   k_mr_pass2  P2[wx,wy](mx, my) = sum_x' G_a(S mx - x') e^{2 pi i wx x'} P1[wy](x', my)    (per candidate)
+//   k_mr_interp sf(x, y) = sum_my S G_b(y - S my) sum_mx S G_b(x - S mx) P2(mx, my), |sf|^2, arg-max
+// Only the arg-max DECISION uses these amplitudes; k_finalize recomputes the winner with the direct
+// form, so lock-in, gradient and w keep the direct path's accuracy.
+constexpr int kMrW = 12;      // coarse taps per output (11 used, padded to 12)
+constexpr int kMrHL = 5;      // coarse samples to the left of an output's own cell
+constexpr int kMrTX = 64;     // k_mr_interp tile: rows
+constexpr int kMrTY = 128;    //                   columns
+
+struct MrPass1Params {
+    const float* img;
+    const float2* phy;
+    float2* p1;            // [chunk][n_alloc][pitch_d]
+    size_t plane_stride;
+    int N, M, Md, pitch_d, n_rows_filled, Rax, Ray, J /* taps per phase */, plane0;
+};
+
+// decimating version of k_pass1: lane = padded row, warp w owns decimated outputs [w*P, w*P+P)
+template <int S>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    constexpr int SP = 33;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32;
+    const int m0 = blockIdx.y * kTile;          // first decimated output column
+    const int pl = blockIdx.z;
+    const int M = prm.M, N = prm.N, J = prm.J;
+    const int n_samp = S * (kTile + J + kAhead + 1);
+    const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
+    int cbase = (S * m0 - prm.Ray) % M;
+    if (cbase < 0) cbase += M;
+    for (int rr = warp; rr < 32; rr += kWarps) {
+        int xs = (r0 + rr - prm.Rax) % N;
+        if (xs < 0) xs += N;
+        const float* __restrict__ row = prm.img + (size_t)xs * M;
+        for (int j = lane; j < n_samp; j += 32) {
+            int c = cbase + j;
+            if (c >= M) c %= M;
+            const float v = __ldg(row + c);
+            const float2 ph = __ldg(phy + c);
+            smem[j * SP + rr] = make_float2(v * ph.x, v * ph.y);
+        }
+    }
+    __syncthreads();
+    const float2* col = smem + (S * warp * kP) * SP + lane;
+    float2 acc[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+    for (int q = 0; q < S; ++q)
+        fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return col[(S * j + q) * SP]; });
+    const int r = r0 + lane;
+    const int m = m0 + warp * kP;
+    if (r < prm.n_rows_filled) {
+        float2* out = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)r * prm.pitch_d + m;
+#pragma unroll
+        for (int p = 0; p < kP; p += 2) {
+            if (m + p + 1 < prm.pitch_d) *reinterpret_cast<float4*>(out + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
+            else if (m + p < prm.pitch_d) out[p] = acc[p];
+        }
+    }
+}
+
+struct MrPass2Params {
+    const float2* p1;      // [chunk][n_alloc][pitch_d]
+    size_t plane_stride;
+    const float2* phx;     // [n_rows][n_alloc], padded-row carrier
+    float2* p2;            // [chunk][n_cand][Nd][Md]
+    int Nd, Md, pitch_d, n_alloc, J, plane0, n_cand, row_c, row_p;
+};
+
+// decimating version of k_pass2: lane = decimated column, warp w owns decimated rows [w*P, w*P+P);
+// the result of every candidate goes to HBM (coarse grid: 1/S^2 of a frame per candidate)
+template <int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int my0 = blockIdx.x * kLanes;
+    const int mx0 = blockIdx.y * (WARPS * kP);
+    const int pl = blockIdx.z;
+    const int plane = prm.plane0 + pl;
+    const int J = prm.J;
+    const int n_samp = S * (WARPS * kP + J + kAhead + 1);
+    {
+        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
+        for (int j = warp; j < n_samp; j += WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
+    }
+    __syncthreads();
+    const float2* col = smem + (S * warp * kP) * kLanes + lane;
+    const int my = my0 + lane;
+    for (int c = 0; c < prm.n_cand; ++c) {
+        const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * (mx0 + warp * kP);
+        float2 acc[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+        for (int q = 0; q < S; ++q)
+            fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(col[(S * j + q) * kLanes], __ldg(ph + S * j + q)); });
+        float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * prm.Nd * prm.Md;
+        if (my < prm.Md) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int mx = mx0 + warp * kP + p;
+                if (mx < prm.Nd) out[(size_t)mx * prm.Md + my] = acc[p];
+            }
+        }
+    }
+}
+
+// 16 consecutive fine outputs from kP/S + kMrW - 1 coarse samples; tb[phi * kMrW + w] are the
+// interpolation taps (S G_b(phi + S (HL - w)), zero outside the truncation radius)
+template <int S>
+__device__ __forceinline__ void interp16(float2 (&acc)[kP], const float2 (&smp)[kP / S + kMrW - 1],
+                                         const TapTable& taps, int tb) {
+#pragma unroll
+    for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kMrW; ++w) {
+#pragma unroll
+        for (int p = 0; p < kP; ++p) acc[p] = __ffma2_rn(taps.g[tb + (p % S) * kMrW + w], smp[p / S + w], acc[p]);
+    }
+}
+
+struct MrInterpParams {
+    const float2* p2;      // [chunk][n_cand][Nd][Md]
+    unsigned long long* key;
+    int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p;
+};
+
+// CTA = kMrTX x kMrTY fine pixels of one plane; all candidate rows of the plane stream through:
+//   coarse tile -> smem, interpolate along x into smem (transposed), interpolate along y in
+//   registers, |sf|^2, running arg-max (2 x 16 outputs per thread), one atomicMax per pixel.
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
+    constexpr int CX = kMrTX / S + kMrW - 1;        // coarse rows / columns held per candidate
+    constexpr int CY = kMrTY / S + kMrW - 1;
+    constexpr int NS = kP / S + kMrW - 1;           // coarse samples per 16 outputs
+    constexpr int P3P = kMrTX + 1;                  // pitch of the x-interpolated tile [cy][x]
+    constexpr int PER = (CX * CY + 255) / 256;
+    extern __shared__ float2 smem[];
+    float2* const p2c = smem;                 // [CX][CY]
+    float2* const p3t = smem + CX * CY;       // [CY][P3P]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
+    const int pl = blockIdx.z, plane = prm.plane0 + pl;
+    const int Nd = prm.Nd, Md = prm.Md;
+    // this thread's share of the coarse tile: fixed (row, col) offsets, wrapped once
+    int off[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int t = threadIdx.x + e * 256;
+        int i = x0 / S - kMrHL + t / CY, j = y0 / S - kMrHL + t % CY;
+        i %= Nd; if (i < 0) i += Nd;
+        j %= Md; if (j < 0) j += Md;
+        off[e] = t < CX * CY ? i * Md + j : -1;
+    }
+    float best[2][kP];
+    unsigned bidx[2][kP / 2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int p = 0; p < kP; ++p) best[h][p] = 0.f;
+#pragma unroll
+        for (int p = 0; p < kP / 2; ++p) bidx[h][p] = 0u;
+    }
+    const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
+    float2 stage[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) stage[e] = off[e] >= 0 ? __ldg(src + off[e]) : make_float2(0.f, 0.f);
+
+    for (int c = 0; c < prm.n_cand; ++c) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int t = threadIdx.x + e * 256;
+            if (t < CX * CY) p2c[t] = stage[e];
+        }
+        __syncthreads();                       // coarse tile of candidate c visible; p3t free again
+        // ---- along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy]
+        for (int t = threadIdx.x; t < CY * (kMrTX / kP); t += 256) {
+            const int cy = t % CY, xb = t / CY;
+            float2 smp[NS], acc[kP];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) smp[i] = p2c[(xb * (kP / S) + i) * CY + cy];
+            interp16<S>(acc, smp, taps, 0);
+#pragma unroll
+            for (int p = 0; p < kP; ++p) p3t[cy * P3P + xb * kP + p] = acc[p];
+        }
+        __syncthreads();
+        if (c + 1 < prm.n_cand) {              // prefetch the next candidate's coarse tile
+            const float2* __restrict__ nsrc = src + (size_t)(c + 1) * Nd * Md;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) stage[e] = off[e] >= 0 ? __ldg(nsrc + off[e]) : make_float2(0.f, 0.f);
+        }
+        // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
+        const unsigned c2 = (unsigned)c * 0x10001u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 smp[NS], acc[kP];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) smp[i] = p3t[(warp * (kP / S) + i) * P3P + lane + 32 * h];
+            interp16<S>(acc, smp, taps, S * kMrW);
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
+                if (a2 > best[h][p]) {
+                    best[h][p] = a2;
+                    const unsigned keep = (p & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+                    bidx[h][p / 2] = (bidx[h][p / 2] & keep) | (c2 & ~keep);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int x = x0 + lane + 32 * h;
+#pragma unroll
+        for (int p = 0; p < kP; ++p) {
+            const int y = y0 + warp * kP + p;
+            if (x < prm.N && y < prm.M && best[h][p] > 0.f) {
+                const unsigned cwin = (bidx[h][p / 2] >> ((p & 1) * 16)) & 0xFFFFu;
+                const unsigned idx = cwin * (unsigned)prm.idx_c + (unsigned)(plane * prm.idx_p);
+                const unsigned long long k =
+                    ((unsigned long long)__float_as_uint(best[h][p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+                atomicMax(prm.key + (size_t)x * prm.M + y, k);
             }
         }
     }
@@ -553,9 +797,188 @@ static int check_common(const float* img, const double* wx_rows, const double* w
     return GPA_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// multirate host side
+// ---------------------------------------------------------------------------------------------
+struct MrGeometry {
+    int N, M, S, Nd, Md, pitch_d, n_rows, n_planes, Rax, Ray, Rb, Jx, Jy, txd, warps2, n_alloc, n_rows_filled, n_cand;
+    size_t plane_stride, p2_stride;   // elements per plane
+    double *wx_d, *wy_d;
+    float2 *phx, *phy, *p1, *p2;
+    int chunk;
+};
+
+static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax, int Ray, int Rb) {
+    GPA_REQUIRE(S == 2 || S == 4 || S == 8, "multirate stride must be 2, 4 or 8 (got %d)", S);
+    GPA_REQUIRE(N % S == 0 && M % S == 0, "frame (%d x %d) is not divisible by the stride %d", N, M, S);
+    GPA_REQUIRE(n_rows >= 1 && n_planes >= 1, "empty candidate set");
+    GPA_REQUIRE(2 * Rax + 1 <= N && 2 * Ray + 1 <= M, "decimation filter must fit the frame");
+    GPA_REQUIRE(Rb >= 1 && Rb / S <= kMrHL && (Rb + S - 1) / S <= kMrW - 1 - kMrHL,
+                "interpolation radius %d does not fit the %d-tap window at stride %d", Rb, kMrW, S);
+    GPA_REQUIRE(N / S >= kMrW && M / S >= kMrW, "frame too small for the multirate sweep");
+    g.N = N; g.M = M; g.S = S; g.Nd = N / S; g.Md = M / S; g.n_rows = n_rows; g.n_planes = n_planes;
+    g.Rax = Rax; g.Ray = Ray; g.Rb = Rb;
+    g.Jx = ceil_div(2 * Rax + 1, S); g.Jy = ceil_div(2 * Ray + 1, S);
+    GPA_REQUIRE(S * g.Jx + kAhead <= kMaxTaps && S * g.Jy + kAhead <= kMaxTaps, "decimation filter too long");
+    g.warps2 = S == 8 ? 4 : 8;
+    g.txd = g.warps2 * kP;
+    g.pitch_d = (int)align_up((size_t)g.Md, 32);
+    g.n_alloc = S * (ceil_div(g.Nd, g.txd) * g.txd + g.Jx + kAhead + 1);
+    g.n_rows_filled = N + S * g.Jx;
+    g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
+    g.n_cand = cand_mode == GPA_CAND_GRID ? n_rows : 1;
+    g.p2_stride = (size_t)g.n_cand * g.Nd * g.Md;
+    return GPA_OK;
+}
+
+static size_t carve_mr(MrGeometry& g, void* ws, size_t ws_bytes, int chunk) {
+    Arena a(ws, ws_bytes);
+    g.wx_d = a.take<double>(g.n_rows);
+    g.wy_d = a.take<double>(g.n_planes);
+    g.phx = a.take<float2>((size_t)g.n_rows * g.n_alloc);
+    g.phy = a.take<float2>((size_t)g.n_planes * g.M);
+    g.p1 = a.take<float2>((size_t)chunk * g.plane_stride);
+    g.p2 = a.take<float2>((size_t)chunk * g.p2_stride);
+    g.chunk = chunk;
+    return a.off;
+}
+
+static int fit_chunk_mr(MrGeometry& g, void* ws, size_t ws_bytes, int want) {
+    const size_t fixed = carve_mr(g, nullptr, 0, 0);
+    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + 512;
+    if (ws_bytes < fixed + per_plane + 512) return 0;
+    size_t c = (ws_bytes - fixed - 512) / per_plane;
+    const int chunk = (int)(c < (size_t)want ? c : (size_t)want);
+    carve_mr(g, ws, ws_bytes, chunk);
+    return chunk;
+}
+
+// polyphase table of a decimating filter: g[q * J + j] = taps[q + S j]
+static int fill_polyphase(TapTable& t, const float* taps, int R, int S, int J) {
+    GPA_REQUIRE(taps != nullptr, "taps pointer is null");
+    std::memset(&t, 0, sizeof(t));
+    const int T = 2 * R + 1;
+    for (int q = 0; q < S; ++q)
+        for (int j = 0; j < J; ++j) {
+            const int i = q + S * j;
+            const float v = i < T ? taps[i] : 0.f;
+            t.g[q * J + j] = make_float2(v, v);
+        }
+    return GPA_OK;
+}
+
+// interpolation tables: [phi * W + w] = S * gb[phi + S (HL - w) + Rb] (x table, then y table)
+static int fill_interp(TapTable& t, const float* bx, const float* by, int Rb, int S) {
+    GPA_REQUIRE(bx && by, "taps pointer is null");
+    std::memset(&t, 0, sizeof(t));
+    for (int ax = 0; ax < 2; ++ax) {
+        const float* b = ax ? by : bx;
+        for (int phi = 0; phi < S; ++phi)
+            for (int w = 0; w < kMrW; ++w) {
+                const int d = phi + S * (kMrHL - w);
+                const float v = (d >= -Rb && d <= Rb) ? (float)S * b[d + Rb] : 0.f;
+                t.g[ax * S * kMrW + phi * kMrW + w] = make_float2(v, v);
+            }
+    }
+    return GPA_OK;
+}
+
+template <int S>
+static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, const TapTable& tx, const TapTable& tb,
+                     int plane0, int count, int cand_mode, unsigned long long* key, cudaStream_t st) {
+    {   // stage 1
+        MrPass1Params p;
+        p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
+        p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
+        p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0;
+        const size_t smem = (size_t)S * (kTile + g.Jy + kAhead + 1) * 33 * sizeof(float2);
+        GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, kTile), count);
+        KernelTimer timer("k_mr_pass1", st);
+        k_mr_pass1<S><<<grid, kWarps * 32, smem, st>>>(p, ty);
+    }
+    {   // stage 2
+        MrPass2Params p;
+        p.p1 = g.p1; p.plane_stride = g.plane_stride; p.phx = g.phx; p.p2 = g.p2;
+        p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = g.Jx; p.plane0 = plane0;
+        p.n_cand = g.n_cand;
+        if (cand_mode == GPA_CAND_GRID) { p.row_c = 1; p.row_p = 0; } else { p.row_c = 0; p.row_p = 1; }
+        constexpr int W2 = S == 8 ? 4 : 8;
+        const size_t smem = (size_t)S * (W2 * kP + g.Jx + kAhead + 1) * kLanes * sizeof(float2);
+        GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2<S, W2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, W2 * kP), count);
+        KernelTimer timer("k_mr_pass2", st);
+        k_mr_pass2<S, W2><<<grid, W2 * 32, smem, st>>>(p, tx);
+    }
+    {   // stages 3 + 4 + arg-max
+        MrInterpParams p;
+        p.p2 = g.p2; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
+        if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
+        constexpr int CX = kMrTX / S + kMrW - 1, CY = kMrTY / S + kMrW - 1;
+        const size_t smem = (size_t)(CX * CY + CY * (kMrTX + 1)) * sizeof(float2);
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        dim3 grid(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX), count);
+        KernelTimer timer("k_mr_interp", st);
+        k_mr_interp<S><<<grid, 256, smem, st>>>(p, tb);
+    }
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
 }  // namespace gpa
 
 using namespace gpa;
+
+extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax,
+                                            int Ray, int Rb, int planes_in_flight, size_t* bytes) {
+    MrGeometry g;
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    if (rc) return rc;
+    GPA_REQUIRE(bytes != nullptr, "bytes is null");
+    GPA_REQUIRE(planes_in_flight >= 1 && planes_in_flight <= n_planes, "planes_in_flight out of range");
+    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 512 + 1024;
+    return GPA_OK;
+}
+
+extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double* wx_rows, int n_rows,
+                                   const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
+                                   int plane_end, int S, const float* taps_ax, int Rax, const float* taps_ay, int Ray,
+                                   const float* taps_bx, const float* taps_by, int Rb, unsigned long long* key,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    MrGeometry g;
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    if (rc) return rc;
+    if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
+    GPA_REQUIRE(key != nullptr, "key is null");
+    if (plane_begin == plane_end) return GPA_OK;
+    const int chunk = fit_chunk_mr(g, ws, ws_bytes, plane_end - plane_begin);
+    if (chunk < 1) {
+        set_error("workspace too small (%zu bytes)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    TapTable tx, ty, tb;
+    if ((rc = fill_polyphase(tx, taps_ax, Rax, S, g.Jx)) || (rc = fill_polyphase(ty, taps_ay, Ray, S, g.Jy)) ||
+        (rc = fill_interp(tb, taps_bx, taps_by, Rb, S)))
+        return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {   // carrier tables: same kernel as the direct path, padded-row layout of the decimating stage
+        Geometry t;
+        t.N = N; t.M = M; t.n_rows = n_rows; t.n_planes = n_planes; t.Rx = Rax; t.n_alloc = g.n_alloc;
+        t.wx_d = g.wx_d; t.wy_d = g.wy_d; t.phx = g.phx; t.phy = g.phy;
+        if ((rc = build_tables(t, wx_rows, wy_planes, st))) return rc;
+    }
+    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
+        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
+        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
+        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
+        else rc = launch_mr<8>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
+        if (rc) return rc;
+    }
+    return GPA_OK;
+}
 
 extern "C" int gpa_lockin_workspace_bytes(int N, int M, int n_rows, int n_planes, int Rx, int Ry,
                                           int planes_in_flight, size_t* bytes) {

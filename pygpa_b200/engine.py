@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._taps import DEFAULT_TRUNC, axis_taps
+from ._taps import DEFAULT_TRUNC, axis_taps, multirate_taps
 
 GRAD_CENTRAL, GRAD_FORWARD, GRAD_NONE = 0, 1, 2
 CAND_GRID, CAND_LIST = 0, 1
@@ -120,7 +120,7 @@ class SweepPlan:
     """Geometry + scratch of one sweep call (candidate axes, taps, workspace)."""
 
     def __init__(self, shape, wx_rows, wy_planes, sigma, cand_mode=CAND_GRID, trunc=DEFAULT_TRUNC,
-                 planes_in_flight=None, device=None):
+                 planes_in_flight=None, device=None, method="auto"):
         self.device = device or require_cuda()
         self.n, self.m = int(shape[0]), int(shape[1])
         self.wx = np.ascontiguousarray(wx_rows, dtype=np.float64)
@@ -133,6 +133,41 @@ class SweepPlan:
         self.in_flight, self.ws_bytes = _plan_planes(self.n, self.m, self.wx.size, self.wy.size,
                                                      self.rx, self.ry, self.device, planes_in_flight)
         self.n_cand = self.wx.size * self.wy.size if cand_mode == CAND_GRID else self.wy.size
+        # arg-max method: the multirate form when the frame and sigma allow it (and the candidate
+        # grid is large enough to amortise its extra passes), else the direct form
+        if method not in ("auto", "direct", "multirate"):
+            raise ValueError("method must be 'auto', 'direct' or 'multirate'")
+        self.mr = None
+        if method != "direct" and trunc == DEFAULT_TRUNC and self.wx.size <= 65535:
+            self.mr = multirate_taps(self.n, self.m, float(sigma), trunc)
+            if self.mr is not None and method == "auto" and cand_mode == CAND_LIST:
+                self.mr = None
+        if method == "multirate" and self.mr is None:
+            raise ValueError("the multirate sweep does not apply to this frame size / sigma")
+        if self.mr is not None:
+            self.mr_in_flight, self.mr_ws_bytes = self._plan_mr(planes_in_flight)
+            self.ws_bytes = max(self.ws_bytes, self.mr_ws_bytes)
+
+    def _plan_mr(self, planes_in_flight):
+        lib = _lib.load()
+        mr, nbytes = self.mr, ctypes.c_size_t(0)
+
+        def need(p):
+            _lib.check(lib.gpa_sweep_mr_workspace_bytes(self.n, self.m, self.wx.size, self.wy.size, self.cand_mode,
+                                                        mr["S"], mr["Ra_x"], mr["Ra_y"], mr["Rb"], p, ctypes.byref(nbytes)))
+            return nbytes.value
+        p = planes_in_flight
+        if p is None:
+            free, _total = torch.cuda.mem_get_info(self.device)
+            cached = _workspaces.get(self.device)
+            budget = int(0.6 * free) + (cached.numel() if cached is not None else 0)
+            base, full = need(1), need(self.wy.size)
+            if full <= budget or self.wy.size == 1:
+                p = self.wy.size
+            else:
+                per = (full - base) // (self.wy.size - 1)
+                p = int(max(1, min(self.wy.size, (budget - base) // per + 1)))
+        return p, need(p)
 
     def _geom(self):
         return (self.n, self.m, _lib.as_pd(self.wx), self.wx.size, _lib.as_pd(self.wy), self.wy.size, self.cand_mode)
@@ -145,6 +180,15 @@ class SweepPlan:
         lib = _lib.load()
         plane_end = self.wy.size if plane_end is None else plane_end
         ws = workspace(self.ws_bytes, self.device)
+        if self.mr is not None:
+            mr = self.mr
+            _lib.check(lib.gpa_sweep_argmax_mr(_ptr(img_dev), *self._geom(), plane_begin, plane_end, mr["S"],
+                                               _lib.as_pf(mr["taps_ax"]), mr["Ra_x"], _lib.as_pf(mr["taps_ay"]), mr["Ra_y"],
+                                               _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
+                                               _ptr(key), _ptr(ws), ws.numel(), _stream()))
+            chunks = -(-(plane_end - plane_begin) // self.mr_in_flight) if plane_end > plane_begin else 0
+            _count(2 + 3 * chunks)
+            return
         _lib.check(lib.gpa_sweep_argmax(_ptr(img_dev), *self._geom(), plane_begin, plane_end, *self._taps(),
                                         _ptr(key), _ptr(ws), ws.numel(), _stream()))
         chunks = -(-(plane_end - plane_begin) // self.in_flight) if plane_end > plane_begin else 0
@@ -177,6 +221,12 @@ class SweepPlan:
 
     def run(self, img_dev, kref, grad_mode=GRAD_CENTRAL, out_f64=False, want_w=False, want_kidx=True):
         """Whole sweep on this GPU: zero key, arg-max over all planes, finalize."""
+        if self.mr is not None:
+            key = torch.zeros((self.n, self.m), dtype=torch.int64, device=self.device)
+            self.argmax(img_dev, key)
+            out = self.finalize(img_dev, key, kref, grad_mode, out_f64, want_w, want_kidx)
+            out["key"] = key
+            return out
         lib = _lib.load()
         n, m, dev = self.n, self.m, self.device
         real = torch.float64 if out_f64 else torch.float32
