@@ -61,7 +61,7 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
         sigma_a = float(np.sqrt(sigma ** 2 - sigma_b ** 2))
         rb = int(np.ceil(trunc * sigma_b))
         ra = int(np.ceil(trunc * sigma_a))
-        if rb // s > MR_HL or (rb + s - 1) // s > MR_WINDOW - 1 - MR_HL:
+        if rb > MR_HL * s:
             continue
         if 2 * ra + 1 > min(n, m) or s * (-(-(2 * ra + 1) // s)) + 2 > MAX_TAPS:
             continue

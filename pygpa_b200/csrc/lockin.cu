@@ -291,21 +291,21 @@ struct MrPass1Params {
 };
 
 // decimating version of k_pass1: lane = padded row, warp w owns decimated outputs [w*P, w*P+P)
-template <int S>
-__global__ void __launch_bounds__(kWarps * 32, 1)
+template <int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
     extern __shared__ float2 smem[];
     constexpr int SP = 33;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = blockIdx.x * 32;
-    const int m0 = blockIdx.y * kTile;          // first decimated output column
+    const int m0 = blockIdx.y * (WARPS * kP);          // first decimated output column
     const int pl = blockIdx.z;
     const int M = prm.M, N = prm.N, J = prm.J;
-    const int n_samp = S * (kTile + J + kAhead + 1);
+    const int n_samp = S * (WARPS * kP + J + kAhead + 1);
     const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
     int cbase = (S * m0 - prm.Ray) % M;
     if (cbase < 0) cbase += M;
-    for (int rr = warp; rr < 32; rr += kWarps) {
+    for (int rr = warp; rr < 32; rr += WARPS) {
         int xs = (r0 + rr - prm.Rax) % N;
         if (xs < 0) xs += N;
         const float* __restrict__ row = prm.img + (size_t)xs * M;
@@ -385,12 +385,16 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
 // 16 consecutive fine outputs from kP/S + kMrW - 1 coarse samples; tb[phi * kMrW + w] are the
 // interpolation taps (S G_b(phi + S (HL - w)), zero outside the truncation radius)
 template <int S>
-__device__ __forceinline__ void interp16(float2 (&acc)[kP], const float2 (&smp)[kP / S + kMrW - 1],
+__device__ __forceinline__ void interp16(float2 (&acc)[kP], const float2 (&smp)[kP / S + kMrW - 2],
                                          const TapTable& taps, int tb) {
+    // With Rb <= 5 S (enforced by plan_mr) the distance phi + S (HL - w) exceeds Rb for w = 11 (every
+    // phase) and for w = 0 unless phi = 0: those taps are identically zero and are not issued.
 #pragma unroll
     for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < kMrW; ++w) {
+    for (int p = 0; p < kP; p += S) acc[p] = __ffma2_rn(taps.g[tb], smp[p / S], acc[p]);
+#pragma unroll
+    for (int w = 1; w < kMrW - 1; ++w) {
 #pragma unroll
         for (int p = 0; p < kP; ++p) acc[p] = __ffma2_rn(taps.g[tb + (p % S) * kMrW + w], smp[p / S + w], acc[p]);
     }
@@ -402,20 +406,29 @@ struct MrInterpParams {
     int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p;
 };
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // CTA = kMrTX x kMrTY fine pixels of one plane; all candidate rows of the plane stream through:
-//   coarse tile -> smem, interpolate along x into smem (transposed), interpolate along y in
-//   registers, |sf|^2, running arg-max (2 x 16 outputs per thread), one atomicMax per pixel.
-template <int S>
-__global__ void __launch_bounds__(256, 1)
+//   coarse tile -> smem (cp.async, double buffered), interpolate along x into smem (transposed),
+//   interpolate along y in registers, |sf|^2, running arg-max (2 x 16 outputs per thread), one
+//   atomicMax per pixel.  IB = bits per packed winner index (8 when n_cand <= 256, else 16).
+template <int S, int IB>
+__global__ void __launch_bounds__(256, 2)
 k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
-    constexpr int CX = kMrTX / S + kMrW - 1;        // coarse rows / columns held per candidate
-    constexpr int CY = kMrTY / S + kMrW - 1;
-    constexpr int NS = kP / S + kMrW - 1;           // coarse samples per 16 outputs
+    constexpr int CX = kMrTX / S + kMrW - 2;        // coarse rows / columns held per candidate
+    constexpr int CY = kMrTY / S + kMrW - 2;
+    constexpr int NS = kP / S + kMrW - 2;           // coarse samples per 16 outputs
     constexpr int P3P = kMrTX + 1;                  // pitch of the x-interpolated tile [cy][x]
     constexpr int PER = (CX * CY + 255) / 256;
+    constexpr int IPR = 32 / IB;                    // indices per register
+    constexpr unsigned IMASK = (1u << IB) - 1u;
     extern __shared__ float2 smem[];
-    float2* const p2c = smem;                 // [CX][CY]
-    float2* const p3t = smem + CX * CY;       // [CY][P3P]
+    float2* const p3t = smem + 2 * CX * CY;         // [CY][P3P]; smem[0 .. 2 CX CY) = two coarse tiles [CX][CY]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
     const int pl = blockIdx.z, plane = prm.plane0 + pl;
@@ -431,26 +444,29 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         off[e] = t < CX * CY ? i * Md + j : -1;
     }
     float best[2][kP];
-    unsigned bidx[2][kP / 2];
+    unsigned bidx[2][kP / IPR];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int p = 0; p < kP; ++p) best[h][p] = 0.f;
 #pragma unroll
-        for (int p = 0; p < kP / 2; ++p) bidx[h][p] = 0u;
+        for (int p = 0; p < kP / IPR; ++p) bidx[h][p] = 0u;
     }
     const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
-    float2 stage[PER];
+    auto fetch = [&](int c) {
+        const float2* __restrict__ g = src + (size_t)c * Nd * Md;
+        float2* dst = smem + (c & 1) * CX * CY;
 #pragma unroll
-    for (int e = 0; e < PER; ++e) stage[e] = off[e] >= 0 ? __ldg(src + off[e]) : make_float2(0.f, 0.f);
-
+        for (int e = 0; e < PER; ++e)
+            if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
+        cp_async_commit();
+    };
+    fetch(0);
     for (int c = 0; c < prm.n_cand; ++c) {
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int t = threadIdx.x + e * 256;
-            if (t < CX * CY) p2c[t] = stage[e];
-        }
-        __syncthreads();                       // coarse tile of candidate c visible; p3t free again
+        cp_async_wait_all();
+        __syncthreads();                       // coarse tile c landed; p3t and the other buffer are free
+        if (c + 1 < prm.n_cand) fetch(c + 1);
+        const float2* p2c = smem + (c & 1) * CX * CY;
         // ---- along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy]
         for (int t = threadIdx.x; t < CY * (kMrTX / kP); t += 256) {
             const int cy = t % CY, xb = t / CY;
@@ -462,13 +478,8 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             for (int p = 0; p < kP; ++p) p3t[cy * P3P + xb * kP + p] = acc[p];
         }
         __syncthreads();
-        if (c + 1 < prm.n_cand) {              // prefetch the next candidate's coarse tile
-            const float2* __restrict__ nsrc = src + (size_t)(c + 1) * Nd * Md;
-#pragma unroll
-            for (int e = 0; e < PER; ++e) stage[e] = off[e] >= 0 ? __ldg(nsrc + off[e]) : make_float2(0.f, 0.f);
-        }
         // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
-        const unsigned c2 = (unsigned)c * 0x10001u;
+        const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float2 smp[NS], acc[kP];
@@ -480,8 +491,8 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
                 const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
                 if (a2 > best[h][p]) {
                     best[h][p] = a2;
-                    const unsigned keep = (p & 1) ? 0x0000FFFFu : 0xFFFF0000u;
-                    bidx[h][p / 2] = (bidx[h][p / 2] & keep) | (c2 & ~keep);
+                    const unsigned field = IMASK << ((p % IPR) * IB);
+                    bidx[h][p / IPR] = (bidx[h][p / IPR] & ~field) | (cr & field);
                 }
             }
         }
@@ -493,7 +504,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         for (int p = 0; p < kP; ++p) {
             const int y = y0 + warp * kP + p;
             if (x < prm.N && y < prm.M && best[h][p] > 0.f) {
-                const unsigned cwin = (bidx[h][p / 2] >> ((p & 1) * 16)) & 0xFFFFu;
+                const unsigned cwin = (bidx[h][p / IPR] >> ((p % IPR) * IB)) & IMASK;
                 const unsigned idx = cwin * (unsigned)prm.idx_c + (unsigned)(plane * prm.idx_p);
                 const unsigned long long k =
                     ((unsigned long long)__float_as_uint(best[h][p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
@@ -814,7 +825,7 @@ static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int ca
     GPA_REQUIRE(N % S == 0 && M % S == 0, "frame (%d x %d) is not divisible by the stride %d", N, M, S);
     GPA_REQUIRE(n_rows >= 1 && n_planes >= 1, "empty candidate set");
     GPA_REQUIRE(2 * Rax + 1 <= N && 2 * Ray + 1 <= M, "decimation filter must fit the frame");
-    GPA_REQUIRE(Rb >= 1 && Rb / S <= kMrHL && (Rb + S - 1) / S <= kMrW - 1 - kMrHL,
+    GPA_REQUIRE(Rb >= 1 && Rb <= kMrHL * S,
                 "interpolation radius %d does not fit the %d-tap window at stride %d", Rb, kMrW, S);
     GPA_REQUIRE(N / S >= kMrW && M / S >= kMrW, "frame too small for the multirate sweep");
     g.N = N; g.M = M; g.S = S; g.Nd = N / S; g.Md = M / S; g.n_rows = n_rows; g.n_planes = n_planes;
@@ -892,12 +903,13 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
         p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
         p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0;
-        const size_t smem = (size_t)S * (kTile + g.Jy + kAhead + 1) * 33 * sizeof(float2);
+        constexpr int W1 = S == 8 ? 4 : 8;
+        const size_t smem = (size_t)S * (W1 * kP + g.Jy + kAhead + 1) * 33 * sizeof(float2);
         GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, kTile), count);
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1<S, W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, W1 * kP), count);
         KernelTimer timer("k_mr_pass1", st);
-        k_mr_pass1<S><<<grid, kWarps * 32, smem, st>>>(p, ty);
+        k_mr_pass1<S, W1><<<grid, W1 * 32, smem, st>>>(p, ty);
     }
     {   // stage 2
         MrPass2Params p;
@@ -917,12 +929,17 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         MrInterpParams p;
         p.p2 = g.p2; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
-        constexpr int CX = kMrTX / S + kMrW - 1, CY = kMrTY / S + kMrW - 1;
-        const size_t smem = (size_t)(CX * CY + CY * (kMrTX + 1)) * sizeof(float2);
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
+        const size_t smem = (size_t)(2 * CX * CY + CY * (kMrTX + 1)) * sizeof(float2);
         dim3 grid(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX), count);
         KernelTimer timer("k_mr_interp", st);
-        k_mr_interp<S><<<grid, 256, smem, st>>>(p, tb);
+        if (g.n_cand <= 256) {
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            k_mr_interp<S, 8><<<grid, 256, smem, st>>>(p, tb);
+        } else {
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            k_mr_interp<S, 16><<<grid, 256, smem, st>>>(p, tb);
+        }
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
