@@ -177,7 +177,7 @@ def run_ours(args, cfg):
     for k in ks:
         wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
         assert len(wxs) == NGRID and len(wys) == NGRID
-        plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev))
+        plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=world > 1))
     taps = 2 * plans[0].rx + 1
 
     def step():
@@ -212,7 +212,7 @@ def run_ours(args, cfg):
     gpu_launches = engine.launch_count - launches0
     tot, n = ctypes.c_double(0), ctypes.c_int(0)
     kernels = {}
-    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_interp", "k_pass1", "k_pass2_argmax", "k_finalize")
+    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_interp", "k_mr_finalize", "k_pass1", "k_pass2_argmax", "k_finalize")
     for name in names:
         _lib.check(lib.gpa_profile_read(name.encode(), ctypes.byref(tot), ctypes.byref(n), 0))
         kernels[name] = (tot.value, n.value)

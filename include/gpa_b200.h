@@ -134,6 +134,18 @@ int gpa_sweep_argmax_mr(const float* img, int N, int M,
                         const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
                         unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
 
+/* gpa_sweep_finalize computed from the coarse grids gpa_sweep_argmax_mr left in ws (same ws, same
+ * geometry arguments, every plane of [plane_begin, plane_end) resident, nothing else enqueued on ws in
+ * between): the winner and its four neighbours are interpolated instead of re-filtered.  Outputs
+ * and conventions as gpa_sweep_finalize.  Returns GPA_ERR_WORKSPACE if the range was chunked. */
+int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows /*host*/, int n_rows,
+                          const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                          int plane_begin, int plane_end, int stride, int Rax, int Ray,
+                          const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
+                          const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
+                          int out_f64, void* lockin, void* grad, void* w, int* kidx,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* For every pixel whose winning candidate (decoded from key) lies in planes
  * [plane_begin, plane_end): recompute that candidate's lock-in at the pixel and its four
  * neighbours and write

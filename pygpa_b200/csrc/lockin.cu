@@ -557,6 +557,57 @@ struct real_of<float2> { using type = float; };
 template <>
 struct real_of<double2> { using type = double; };
 
+// Shared tail of the finalize kernels: re-reference the winner to kref, phase gradient, w, k-index.
+template <typename T2>
+__device__ __forceinline__ void finalize_store(const FinalizeParams& prm, size_t pix, int x, int y, unsigned idx, int row,
+                                               int plane, float2 s_0, float2 s_m, float2 s_p, float2 s_ym, float2 s_yp) {
+    using R = typename real_of<T2>::type;
+    T2* const o_lockin = static_cast<T2*>(prm.lockin);
+    R* const o_grad = static_cast<R*>(prm.grad);
+    R* const o_w = static_cast<R*>(prm.w);
+    const size_t npix = (size_t)prm.N * prm.M;
+    const int N = prm.N, M = prm.M;
+    const bool want_grad = o_grad != nullptr && prm.grad_mode != GPA_GRAD_NONE;
+    const double dkx = prm.wx_rows[row] - prm.kref_x;
+    const double dky = prm.wy_planes[plane] - prm.kref_y;
+    const float2 rot = phasor_turns(-(dkx * (double)x + dky * (double)y));
+    {
+        const float2 v = cmul(s_0, rot);
+        T2 o;
+        o.x = v.x;
+        o.y = v.y;
+        o_lockin[pix] = o;
+    }
+    if (o_w) {
+        o_w[pix] = (R)prm.wx_rows[row];
+        o_w[npix + pix] = (R)prm.wy_planes[plane];
+    }
+    if (prm.kidx) prm.kidx[pix] = (int)idx;
+    if (want_grad) {
+        const double four_pi = 12.566370614359172953850573533118;
+        double g0, g1;
+        if (prm.grad_mode == GPA_GRAD_CENTRAL) {
+            // np.gradient: central inside, one-sided (x2 after the final doubling) at the frame edge
+            double d0, d1;
+            if (x == 0) d0 = 2.0 * neg_arg_conj(s_p, s_0);
+            else if (x == N - 1) d0 = 2.0 * neg_arg_conj(s_0, s_m);
+            else d0 = neg_arg_conj(s_p, s_m);
+            if (y == 0) d1 = 2.0 * neg_arg_conj(s_yp, s_0);
+            else if (y == M - 1) d1 = 2.0 * neg_arg_conj(s_0, s_ym);
+            else d1 = neg_arg_conj(s_yp, s_ym);
+            g0 = 0.5 * wrap_to_pi(d0 + four_pi * dkx);
+            g1 = 0.5 * wrap_to_pi(d1 + four_pi * dky);
+        } else {
+            // cuGPA.py:58-62 grad='diff': forward difference, NaN past the end
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            g0 = (x == N - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_p, s_0) + four_pi * dkx);
+            g1 = (y == M - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_yp, s_0) + four_pi * dky);
+        }
+        o_grad[2 * pix] = (R)g0;
+        o_grad[2 * pix + 1] = (R)g1;
+    }
+}
+
 template <typename T2>   // float2: c64 / f32 outputs, double2: c128 / f64 outputs (the reference's dtypes)
 __global__ void __launch_bounds__(256)
 k_finalize(const FinalizeParams prm, const __grid_constant__ TapTable taps) {
@@ -638,44 +689,116 @@ k_finalize(const FinalizeParams prm, const __grid_constant__ TapTable taps) {
         }
     }
 
-    const double dkx = prm.wx_rows[row] - prm.kref_x;
-    const double dky = prm.wy_planes[plane] - prm.kref_y;
-    const float2 rot = phasor_turns(-(dkx * (double)x + dky * (double)y));
-    {
-        const float2 v = cmul(s_0, rot);
-        T2 o;
-        o.x = v.x;
-        o.y = v.y;
-        o_lockin[pix] = o;
-    }
-    if (o_w) {
-        o_w[pix] = (R)prm.wx_rows[row];
-        o_w[npix + pix] = (R)prm.wy_planes[plane];
-    }
-    if (prm.kidx) prm.kidx[pix] = (int)idx;
-    if (want_grad) {
-        const double four_pi = 12.566370614359172953850573533118;
-        double g0, g1;
-        if (prm.grad_mode == GPA_GRAD_CENTRAL) {
-            // np.gradient: central inside, one-sided (x2 after the final doubling) at the frame edge
-            double d0, d1;
-            if (x == 0) d0 = 2.0 * neg_arg_conj(s_p, s_0);
-            else if (x == N - 1) d0 = 2.0 * neg_arg_conj(s_0, s_m);
-            else d0 = neg_arg_conj(s_p, s_m);
-            if (y == 0) d1 = 2.0 * neg_arg_conj(s_yp, s_0);
-            else if (y == M - 1) d1 = 2.0 * neg_arg_conj(s_0, s_ym);
-            else d1 = neg_arg_conj(s_yp, s_ym);
-            g0 = 0.5 * wrap_to_pi(d0 + four_pi * dkx);
-            g1 = 0.5 * wrap_to_pi(d1 + four_pi * dky);
-        } else {
-            // cuGPA.py:58-62 grad='diff': forward difference, NaN past the end
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            g0 = (x == N - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_p, s_0) + four_pi * dkx);
-            g1 = (y == M - 1) ? nan : 0.5 * wrap_to_pi(2.0 * neg_arg_conj(s_yp, s_0) + four_pi * dky);
+    finalize_store<T2>(prm, pix, x, y, idx, row, plane, s_0, s_m, s_p, s_ym, s_yp);
+}
+
+// Multirate twin of k_finalize: the winner's sf at the pixel and its four neighbours is interpolated
+// from the candidate's coarse grid P2 (still resident after gpa_sweep_argmax_mr) instead of being
+// re-filtered from full-resolution planes, which removes the extra full-rate pass 1.
+struct MrFinalizeParams {
+    FinalizeParams f;      // planes / phx unused
+    const float2* p2;      // [chunk][n_cand][Nd][Md]
+    int Nd, Md, n_cand, S;
+};
+
+template <int S, typename T2>
+__global__ void __launch_bounds__(256)
+k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
+    const FinalizeParams& prm = mp.f;
+    using R = typename real_of<T2>::type;
+    const int y = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int x = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= prm.N || y >= prm.M) return;
+    const size_t pix = (size_t)x * prm.M + y;
+    const size_t npix = (size_t)prm.N * prm.M;
+    const unsigned long long k = prm.key[pix];
+    if ((k >> 32) == 0ull) {
+        T2 z;
+        z.x = 0;
+        z.y = 0;
+        static_cast<T2*>(prm.lockin)[pix] = z;
+        if (prm.grad) {
+            static_cast<R*>(prm.grad)[2 * pix] = 0;
+            static_cast<R*>(prm.grad)[2 * pix + 1] = 0;
         }
-        o_grad[2 * pix] = (R)g0;
-        o_grad[2 * pix + 1] = (R)g1;
+        if (prm.w) {
+            static_cast<R*>(prm.w)[pix] = 0;
+            static_cast<R*>(prm.w)[npix + pix] = 0;
+        }
+        if (prm.kidx) prm.kidx[pix] = -1;
+        return;
     }
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    int plane, row, cand;
+    if (prm.list_mode) {
+        plane = (int)idx; row = plane; cand = 0;
+    } else {
+        plane = (int)(idx % (unsigned)prm.n_planes);
+        row = (int)(idx / (unsigned)prm.n_planes);
+        cand = row;
+    }
+    if (plane < prm.plane_begin || plane >= prm.plane_end) return;
+    const int Nd = mp.Nd, Md = mp.Md;
+    const float2* __restrict__ P = mp.p2 + ((size_t)(plane - prm.plane0) * mp.n_cand + cand) * Nd * Md;
+    // Fine positions x-1, x, x+1 and y-1, y, y+1 in UNWRAPPED coordinates (the coarse grid is circular
+    // like the frame; the reference never uses the values beyond the frame edge, they are ignored).
+    // The three positions span at most two adjacent coarse cells, so a 12 x 12 coarse window holds
+    // every sample: row i <-> coarse row cx0 - HL + i, column j <-> cy0 - HL + j.
+    auto fdiv = [](int a, int b) { return (a >= 0 ? a : a - b + 1) / b; };
+    int offx[3], phx_[3], offy[3];
+    const int cx0 = fdiv(x - 1, S), cy0 = fdiv(y - 1, S);
+    float gy[3][kMrW];          // y taps of the three y positions aligned to the 12-column window
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int cx = fdiv(x - 1 + e, S), cy = fdiv(y - 1 + e, S);
+        offx[e] = cx - cx0;
+        phx_[e] = x - 1 + e - S * cx;
+        offy[e] = cy - cy0;
+        const int phy_ = y - 1 + e - S * cy;
+#pragma unroll
+        for (int j = 0; j < kMrW; ++j) {
+            const int v = j - offy[e];
+            gy[e][j] = (v >= 0 && v < kMrW - 1) ? taps.g[S * kMrW + phy_ * kMrW + v].x : 0.f;
+        }
+    }
+    int colj[kMrW];
+#pragma unroll
+    for (int j = 0; j < kMrW; ++j) {
+        int c = (cy0 - kMrHL + j) % Md;
+        colj[j] = c < 0 ? c + Md : c;
+    }
+    float2 s_xm = make_float2(0.f, 0.f), s_0 = s_xm, s_xp = s_xm, s_ym = s_xm, s_yp = s_xm;
+#pragma unroll 1
+    for (int i = 0; i < kMrW; ++i) {
+        int r = (cx0 - kMrHL + i) % Nd;
+        if (r < 0) r += Nd;
+        const float2* __restrict__ prow = P + (size_t)r * Md;
+        float2 rv[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) rv[d] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kMrW; ++j) {
+            const float2 smp = __ldg(prow + colj[j]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                rv[d].x = fmaf(gy[d][j], smp.x, rv[d].x);
+                rv[d].y = fmaf(gy[d][j], smp.y, rv[d].y);
+            }
+        }
+        // x taps are warp-uniform (a warp shares x)
+        float gx[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int w = i - offx[e];
+            gx[e] = (w >= 0 && w < kMrW - 1) ? taps.g[phx_[e] * kMrW + w].x : 0.f;
+        }
+        s_xm.x = fmaf(gx[0], rv[1].x, s_xm.x); s_xm.y = fmaf(gx[0], rv[1].y, s_xm.y);
+        s_0.x = fmaf(gx[1], rv[1].x, s_0.x);   s_0.y = fmaf(gx[1], rv[1].y, s_0.y);
+        s_xp.x = fmaf(gx[2], rv[1].x, s_xp.x); s_xp.y = fmaf(gx[2], rv[1].y, s_xp.y);
+        s_ym.x = fmaf(gx[1], rv[0].x, s_ym.x); s_ym.y = fmaf(gx[1], rv[0].y, s_ym.y);
+        s_yp.x = fmaf(gx[1], rv[2].x, s_yp.x); s_yp.y = fmaf(gx[1], rv[2].y, s_yp.y);
+    }
+    finalize_store<T2>(prm, pix, x, y, idx, row, plane, s_0, s_xm, s_xp, s_ym, s_yp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -994,6 +1117,52 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
         else rc = launch_mr<8>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
         if (rc) return rc;
     }
+    return GPA_OK;
+}
+
+// Finalize from the coarse grids left in the workspace by gpa_sweep_argmax_mr.  Requires that call to
+// have covered exactly [plane_begin, plane_end) with all its planes resident (same ws, same arguments).
+extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
+                                     int n_planes, int cand_mode, int plane_begin, int plane_end, int S, int Rax,
+                                     int Ray, const float* taps_bx, const float* taps_by, int Rb,
+                                     const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
+                                     int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
+                                     size_t ws_bytes, void* stream) {
+    MrGeometry g;
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    if (rc) return rc;
+    GPA_REQUIRE(wx_rows && wy_planes && ws && key && lockin, "null pointer argument");
+    GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes, "bad plane range");
+    GPA_REQUIRE(grad_mode == GPA_GRAD_CENTRAL || grad_mode == GPA_GRAD_FORWARD || grad_mode == GPA_GRAD_NONE,
+                "bad grad_mode %d", grad_mode);
+    GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr, "grad is null but a gradient was requested");
+    if (plane_begin == plane_end) return GPA_OK;
+    const int chunk = fit_chunk_mr(g, ws, ws_bytes, plane_end - plane_begin);
+    if (chunk != plane_end - plane_begin) {
+        set_error("gpa_sweep_finalize_mr needs every plane of the range resident (workspace holds %d of %d)", chunk,
+                  plane_end - plane_begin);
+        return GPA_ERR_WORKSPACE;
+    }
+    TapTable tb;
+    if ((rc = fill_interp(tb, taps_bx, taps_by, Rb, S))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MrFinalizeParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    FinalizeParams& f = mp.f;
+    f.wx_rows = g.wx_d; f.wy_planes = g.wy_d; f.key = key;
+    f.lockin = lockin; f.grad = grad_mode == GPA_GRAD_NONE ? nullptr : grad; f.w = w; f.kidx = kidx;
+    f.kref_x = kref_x; f.kref_y = kref_y; f.N = N; f.M = M;
+    f.plane0 = plane_begin; f.plane_begin = plane_begin; f.plane_end = plane_end;
+    f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
+    mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S;
+    dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
+    KernelTimer timer("k_mr_finalize", st);
+#define GPA_MRFIN(SS)                                                              \
+    if (out_f64) k_mr_finalize<SS, double2><<<grid, 256, 0, st>>>(mp, tb);         \
+    else k_mr_finalize<SS, float2><<<grid, 256, 0, st>>>(mp, tb)
+    if (S == 2) { GPA_MRFIN(2); } else if (S == 4) { GPA_MRFIN(4); } else { GPA_MRFIN(8); }
+#undef GPA_MRFIN
+    GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }
 

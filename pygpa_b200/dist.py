@@ -82,8 +82,11 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None):
     keys = list(stacked.unbind(0))
     outs = []
     for plan, key, kref, (lo, hi) in zip(plans, keys, krefs, ranges):
-        # the shared workspace now holds another peak's planes: pass 1 is redone for [lo, hi)
-        out = plan.finalize(img_dev, key, kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False)
+        # plans with a private workspace still hold what their argmax() left (the multirate coarse
+        # grids / the first-pass planes), so the finalize is the same computation as on one GPU and
+        # the result stays bit-identical; with the shared workspace pass 1 is redone for [lo, hi)
+        out = plan.finalize(img_dev, key, kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
+                            planes_valid=plan._private)
         out["key"] = key
         outs.append(out)
     merge_payload([o["lockin"] for o in outs] + [o["grad"] for o in outs], group)

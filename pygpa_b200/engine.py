@@ -120,8 +120,10 @@ class SweepPlan:
     """Geometry + scratch of one sweep call (candidate axes, taps, workspace)."""
 
     def __init__(self, shape, wx_rows, wy_planes, sigma, cand_mode=CAND_GRID, trunc=DEFAULT_TRUNC,
-                 planes_in_flight=None, device=None, method="auto"):
+                 planes_in_flight=None, device=None, method="auto", private_ws=False):
         self.device = device or require_cuda()
+        self._private = bool(private_ws)       # own scratch: what argmax() leaves survives other plans' calls
+        self._ws = None
         self.n, self.m = int(shape[0]), int(shape[1])
         self.wx = np.ascontiguousarray(wx_rows, dtype=np.float64)
         self.wy = np.ascontiguousarray(wy_planes, dtype=np.float64)
@@ -169,6 +171,13 @@ class SweepPlan:
                 p = int(max(1, min(self.wy.size, (budget - base) // per + 1)))
         return p, need(p)
 
+    def _workspace(self):
+        if not self._private:
+            return workspace(self.ws_bytes, self.device)
+        if self._ws is None or self._ws.numel() < self.ws_bytes:
+            self._ws = torch.empty(int(self.ws_bytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
     def _geom(self):
         return (self.n, self.m, _lib.as_pd(self.wx), self.wx.size, _lib.as_pd(self.wy), self.wy.size, self.cand_mode)
 
@@ -179,7 +188,7 @@ class SweepPlan:
         """key (N, M) int64 CUDA tensor, updated in place with this plane range's candidates."""
         lib = _lib.load()
         plane_end = self.wy.size if plane_end is None else plane_end
-        ws = workspace(self.ws_bytes, self.device)
+        ws = self._workspace()
         if self.mr is not None:
             mr = self.mr
             _lib.check(lib.gpa_sweep_argmax_mr(_ptr(img_dev), *self._geom(), plane_begin, plane_end, mr["S"],
@@ -196,6 +205,9 @@ class SweepPlan:
 
     def finalize(self, img_dev, key, kref, grad_mode=GRAD_CENTRAL, out_f64=False, want_w=False, want_kidx=True,
                  plane_begin=0, plane_end=None, planes_valid=False, out=None):
+        """Winner's lock-in / gradient / w / k-index for pixels won by planes [plane_begin, plane_end).
+        planes_valid: the workspace still holds what argmax() left for exactly this range (then the
+        multirate path interpolates from its coarse grids and the direct path skips pass 1)."""
         lib = _lib.load()
         plane_end = self.wy.size if plane_end is None else plane_end
         n, m, dev = self.n, self.m, self.device
@@ -209,7 +221,18 @@ class SweepPlan:
             out["grad"] = make((n, m, 2), dtype=real, device=dev) if grad_mode != GRAD_NONE else None
             out["w"] = make((2, n, m), dtype=real, device=dev) if want_w else None
             out["kidx"] = make((n, m), dtype=torch.int32, device=dev) if want_kidx else None
-        ws = workspace(self.ws_bytes, self.device)
+        ws = self._workspace()
+        if self.mr is not None and planes_valid and plane_end - plane_begin <= self.mr_in_flight:
+            mr = self.mr
+            _lib.check(lib.gpa_sweep_finalize_mr(*self._geom(), plane_begin, plane_end, mr["S"], mr["Ra_x"], mr["Ra_y"],
+                                                 _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
+                                                 _ptr(key), float(kref[0]), float(kref[1]), grad_mode, int(out_f64),
+                                                 _ptr(out["lockin"]), _ptr(out.get("grad")), _ptr(out.get("w")),
+                                                 _ptr(out.get("kidx")), _ptr(ws), ws.numel(), _stream()))
+            _count(1)
+            return out
+        if self.mr is not None:
+            planes_valid = False       # the workspace holds coarse grids, not full-resolution planes
         _lib.check(lib.gpa_sweep_finalize(_ptr(img_dev), *self._geom(), plane_begin, plane_end, int(planes_valid),
                                           *self._taps(), _ptr(key), float(kref[0]), float(kref[1]), grad_mode,
                                           int(out_f64), _ptr(out["lockin"]), _ptr(out.get("grad")),
@@ -224,7 +247,8 @@ class SweepPlan:
         if self.mr is not None:
             key = torch.zeros((self.n, self.m), dtype=torch.int64, device=self.device)
             self.argmax(img_dev, key)
-            out = self.finalize(img_dev, key, kref, grad_mode, out_f64, want_w, want_kidx)
+            out = self.finalize(img_dev, key, kref, grad_mode, out_f64, want_w, want_kidx,
+                                planes_valid=self.mr_in_flight == self.wy.size)
             out["key"] = key
             return out
         lib = _lib.load()
@@ -235,7 +259,7 @@ class SweepPlan:
                "grad": torch.empty((n, m, 2), dtype=real, device=dev) if grad_mode != GRAD_NONE else None,
                "w": torch.empty((2, n, m), dtype=real, device=dev) if want_w else None,
                "kidx": torch.empty((n, m), dtype=torch.int32, device=dev) if want_kidx else None}
-        ws = workspace(self.ws_bytes, dev)
+        ws = self._workspace()
         _lib.check(lib.gpa_wfr_sweep(_ptr(img_dev), *self._geom(), *self._taps(), float(kref[0]), float(kref[1]),
                                      grad_mode, int(out_f64), _ptr(out["key"]), _ptr(out["lockin"]),
                                      _ptr(out["grad"]), _ptr(out["w"]), _ptr(out["kidx"]), _ptr(ws), ws.numel(),

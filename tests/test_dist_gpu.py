@@ -27,7 +27,7 @@ def _worker(rank, world, port, img, ks, kw, kstep, sigma, out_dir):
         plans = []
         for k in ks:
             wxs, wys = engine.grid_axes(k[0], k[1], kw, kstep)
-            plans.append(engine.SweepPlan(d_img.shape, wxs, wys, sigma, device=dev))
+            plans.append(engine.SweepPlan(d_img.shape, wxs, wys, sigma, device=dev, private_ws=True))
         outs = gdist.sharded_sweep(d_img, plans, ks)
         if rank == 0:
             single = [p.run(d_img, k) for p, k in zip(plans, ks)]

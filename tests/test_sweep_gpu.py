@@ -157,32 +157,46 @@ def _run_device(img, plan, kref, **kw):
     return plan.run(img, kref, **kw)
 
 
-def test_plane_chunking_and_range_merge_are_bit_exact(noisy_case):
+def _same(a, b):
+    return torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b)
+
+
+@pytest.mark.parametrize("method", ["direct", "multirate"])
+def test_plane_chunking_and_range_merge_are_bit_exact(noisy_case, method):
     """Resident-plane chunking and splitting the plane range over several calls (the multi-GPU
-    k-grid sharding) must not change a single bit."""
+    k-grid sharding) must not change a single bit of the arg-max; with per-plan workspaces the
+    finalized payload is bit-identical too."""
     c = noisy_case
     dev = engine.require_cuda()
     img = engine.image_to_device(c["img"], dev)
     k = c["ks"][2]
     wxs, wys = engine.grid_axes(k[0], k[1], c["kw"], c["kstep"])
-    full = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev).run(img, k, want_w=True)
-    chunked = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], planes_in_flight=3, device=dev).run(img, k, want_w=True)
-    for key in ("key", "lockin", "grad", "w", "kidx"):
-        assert torch.equal(torch.view_as_real(full[key]) if full[key].is_complex() else full[key],
-                           torch.view_as_real(chunked[key]) if chunked[key].is_complex() else chunked[key]), key
-    # two "ranks": planes [0,3) and [3,ny)
-    plan = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev)
+    full = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev, method=method).run(img, k, want_w=True)
+    chunked = engine.SweepPlan(img.shape, wxs, wys, c["sigma"], planes_in_flight=3, device=dev, method=method).run(img, k, want_w=True)
+    assert torch.equal(full["key"], chunked["key"]) and torch.equal(full["kidx"], chunked["kidx"])
+    if method == "direct":
+        for key in ("lockin", "grad", "w"):
+            assert _same(full[key], chunked[key]), key
+    else:   # chunked multirate falls back to the direct-form finalize: same winners, values to rounding
+        assert _same(full["w"], chunked["w"])
+        amax = full["lockin"].abs().max().item()
+        assert (full["lockin"] - chunked["lockin"]).abs().max().item() < 1e-4 * amax
+    # two "ranks": planes [0,3) and [3,ny), each with its own plan + private workspace
+    ranges = ((0, 3), (3, len(wys)))
+    plans = [engine.SweepPlan(img.shape, wxs, wys, c["sigma"], device=dev, method=method, private_ws=True) for _ in ranges]
     keys = []
-    for lo, hi in ((0, 3), (3, len(wys))):
+    for plan, (lo, hi) in zip(plans, ranges):
         kk = torch.zeros(img.shape, dtype=torch.int64, device=dev)
         plan.argmax(img, kk, lo, hi)
         keys.append(kk)
     # keys are unsigned 64-bit with the top bit clear (|sf|^2 >= 0), so a signed max is the same
     merged = torch.maximum(keys[0], keys[1])
     assert torch.equal(merged, full["key"])
-    parts = [plan.finalize(img, merged, k, plane_begin=lo, plane_end=hi, want_w=True) for lo, hi in ((0, 3), (3, len(wys)))]
-    assert torch.equal(torch.view_as_real(parts[0]["lockin"] + parts[1]["lockin"]), torch.view_as_real(full["lockin"]))
-    assert torch.equal(parts[0]["grad"] + parts[1]["grad"], full["grad"])
+    parts = [plan.finalize(img, merged, k, plane_begin=lo, plane_end=hi, want_w=True, planes_valid=True)
+             for plan, (lo, hi) in zip(plans, ranges)]
+    assert _same(parts[0]["lockin"] + parts[1]["lockin"], full["lockin"])
+    assert _same(parts[0]["grad"] + parts[1]["grad"], full["grad"])
+    assert _same(parts[0]["w"] + parts[1]["w"], full["w"])
 
 
 def test_zero_image_keeps_zeros():
