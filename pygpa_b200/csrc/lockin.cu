@@ -345,12 +345,17 @@ struct MrPass2Params {
 };
 
 // decimating version of k_pass2: lane = decimated column, warp w owns decimated rows [w*P, w*P+P);
-// the result of every candidate goes to HBM (coarse grid: 1/S^2 of a frame per candidate)
-template <int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+// the result of every candidate goes to HBM (coarse grid: 1/S^2 of a frame per candidate).
+// The shared-memory plane tile (S (WARPS P + J) rows) allows one CTA per SM, so the CTA carries
+// GROUPS independent warp groups that share the tile and split the candidates between them
+// (named barriers per group): twice the resident warps for the same shared memory.
+template <int S, int WARPS, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * WARPS * 32, 1)
 k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     extern __shared__ float2 smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int GT = WARPS * 32;                        // threads per group
+    const int group = threadIdx.x / GT, tig = threadIdx.x % GT;
+    const int lane = tig & 31, warp = tig >> 5;
     const int my0 = blockIdx.x * kLanes;
     const int mx0 = blockIdx.y * (WARPS * kP);
     const int pl = blockIdx.z;
@@ -359,18 +364,33 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     const int n_samp = S * (WARPS * kP + J + kAhead + 1);
     {
         const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
-        for (int j = warp; j < n_samp; j += WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
+        for (int j = threadIdx.x >> 5; j < n_samp; j += GROUPS * WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
     }
-    __syncthreads();
     const float2* col = smem + (S * warp * kP) * kLanes + lane;
     const int my = my0 + lane;
-    for (int c = 0; c < prm.n_cand; ++c) {
-        const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * (mx0 + warp * kP);
+    // carrier of the tile rows, staged per candidate in shared memory (double buffered per group):
+    // cheap 32-bit addressing in the FIR loop instead of 64-bit global address arithmetic per sample
+    float2* const sph = smem + (size_t)n_samp * kLanes + (size_t)group * 2 * n_samp;     // [2][n_samp]
+    auto stage_carrier = [&](int c, int slot) {
+        const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * mx0;
+        float2* dst = sph + slot * n_samp;
+        for (int j = tig; j < n_samp; j += GT) dst[j] = __ldg(ph + j);
+    };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory"); };
+    if (group < prm.n_cand) stage_carrier(group, 0);
+    __syncthreads();
+    int slot = 0;
+    for (int c = group; c < prm.n_cand; c += GROUPS, slot ^= 1) {
+        if (c + GROUPS < prm.n_cand) stage_carrier(c + GROUPS, slot ^ 1);
+        const float2* ph = sph + slot * n_samp + S * warp * kP;
         float2 acc[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
-        for (int q = 0; q < S; ++q)
-            fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(col[(S * j + q) * kLanes], __ldg(ph + S * j + q)); });
+        for (int q = 0; q < S; ++q) {
+            const float2* colq = col + q * kLanes;
+            const float2* phq = ph + q;
+            fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(colq[j * (S * kLanes)], phq[j * S]); });
+        }
         float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * prm.Nd * prm.Md;
         if (my < prm.Md) {
 #pragma unroll
@@ -379,6 +399,7 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
                 if (mx < prm.Nd) out[(size_t)mx * prm.Md + my] = acc[p];
             }
         }
+        group_sync();     // this group's next carrier is complete; the current one is no longer read
     }
 }
 
@@ -1041,12 +1062,14 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.row_c = 1; p.row_p = 0; } else { p.row_c = 0; p.row_p = 1; }
         constexpr int W2 = S == 8 ? 4 : 8;
-        const size_t smem = (size_t)S * (W2 * kP + g.Jx + kAhead + 1) * kLanes * sizeof(float2);
+        constexpr int G2 = 2;
+        const size_t n_samp2 = (size_t)S * (W2 * kP + g.Jx + kAhead + 1);
+        const size_t smem = n_samp2 * (kLanes + 2 * G2) * sizeof(float2);   // plane tile + 2 carrier buffers per group
         GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2<S, W2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2<S, W2, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, W2 * kP), count);
         KernelTimer timer("k_mr_pass2", st);
-        k_mr_pass2<S, W2><<<grid, W2 * 32, smem, st>>>(p, tx);
+        k_mr_pass2<S, W2, G2><<<grid, G2 * W2 * 32, smem, st>>>(p, tx);
     }
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;
