@@ -405,19 +405,21 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
 
 // 16 consecutive fine outputs from kP/S + kMrW - 1 coarse samples; tb[phi * kMrW + w] are the
 // interpolation taps (S G_b(phi + S (HL - w)), zero outside the truncation radius)
-template <int S>
-__device__ __forceinline__ void interp16(float2 (&acc)[kP], const float2 (&smp)[kP / S + kMrW - 2],
-                                         const TapTable& taps, int tb) {
-    // With Rb <= 5 S (enforced by plan_mr) the distance phi + S (HL - w) exceeds Rb for w = 11 (every
-    // phase) and for w = 0 unless phi = 0: those taps are identically zero and are not issued.
+template <int S, int Q>
+__device__ __forceinline__ void interp_block(float2 (&acc)[Q], const float2 (&smp)[Q / S + kMrW - 2],
+                                             const TapTable& taps, int tb) {
+    // Q consecutive fine outputs from Q/S + 10 coarse samples.  With Rb <= 5 S (enforced by plan_mr)
+    // the distance phi + S (HL - w) exceeds Rb for w = 11 (every phase) and for w = 0 unless
+    // phi = 0: those taps are identically zero and are not issued.
+    static_assert(Q % S == 0, "block must hold whole coarse cells");
 #pragma unroll
-    for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+    for (int p = 0; p < Q; ++p) acc[p] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < kP; p += S) acc[p] = __ffma2_rn(taps.g[tb], smp[p / S], acc[p]);
+    for (int p = 0; p < Q; p += S) acc[p] = __ffma2_rn(taps.g[tb], smp[p / S], acc[p]);
 #pragma unroll
     for (int w = 1; w < kMrW - 1; ++w) {
 #pragma unroll
-        for (int p = 0; p < kP; ++p) acc[p] = __ffma2_rn(taps.g[tb + (p % S) * kMrW + w], smp[p / S + w], acc[p]);
+        for (int p = 0; p < Q; ++p) acc[p] = __ffma2_rn(taps.g[tb + (p % S) * kMrW + w], smp[p / S + w], acc[p]);
     }
 }
 
@@ -448,8 +450,12 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     constexpr int PER = (CX * CY + 255) / 256;
     constexpr int IPR = 32 / IB;                    // indices per register
     constexpr unsigned IMASK = (1u << IB) - 1u;
+    constexpr int Q3 = S < 4 ? 8 : S;               // outputs per x-interpolation task (whole cells)
+    constexpr int NS3 = Q3 / S + kMrW - 2;
+    constexpr int N3 = CY * (kMrTX / Q3);           // x-interpolation tasks per candidate
     extern __shared__ float2 smem[];
-    float2* const p3t = smem + 2 * CX * CY;         // [CY][P3P]; smem[0 .. 2 CX CY) = two coarse tiles [CX][CY]
+    // smem: two coarse tiles [CX][CY] (cp.async targets), two x-interpolated tiles [CY][P3P]
+    float2* const p3t0 = smem + 2 * CX * CY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
     const int pl = blockIdx.z, plane = prm.plane0 + pl;
@@ -475,38 +481,51 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     }
     const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
     auto fetch = [&](int c) {
-        const float2* __restrict__ g = src + (size_t)c * Nd * Md;
-        float2* dst = smem + (c & 1) * CX * CY;
+        if (c < prm.n_cand) {
+            const float2* __restrict__ g = src + (size_t)c * Nd * Md;
+            float2* dst = smem + (c & 1) * CX * CY;
 #pragma unroll
-        for (int e = 0; e < PER; ++e)
-            if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
+            for (int e = 0; e < PER; ++e)
+                if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
+        }
         cp_async_commit();
     };
+    // along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy], tasks of Q3 outputs
+    auto interp_x = [&](int c) {
+        const float2* p2c = smem + (c & 1) * CX * CY;
+        float2* p3t = p3t0 + (c & 1) * CY * P3P;
+        for (int t = threadIdx.x; t < N3; t += 256) {
+            const int cy = t % CY, xb = t / CY;
+            float2 smp[NS3], acc[Q3];
+#pragma unroll
+            for (int i = 0; i < NS3; ++i) smp[i] = p2c[(xb * (Q3 / S) + i) * CY + cy];
+            interp_block<S, Q3>(acc, smp, taps, 0);
+#pragma unroll
+            for (int p = 0; p < Q3; ++p) p3t[cy * P3P + xb * Q3 + p] = acc[p];
+        }
+    };
+    // Software pipeline over candidates, ONE barrier per candidate: in phase c every thread
+    // interpolates candidate c+1 along x (into the other p3t buffer) and candidate c along y (+ arg-max),
+    // while cp.async brings in the coarse tile of candidate c+2.
     fetch(0);
+    fetch(1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    interp_x(0);
     for (int c = 0; c < prm.n_cand; ++c) {
         cp_async_wait_all();
-        __syncthreads();                       // coarse tile c landed; p3t and the other buffer are free
-        if (c + 1 < prm.n_cand) fetch(c + 1);
-        const float2* p2c = smem + (c & 1) * CX * CY;
-        // ---- along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy]
-        for (int t = threadIdx.x; t < CY * (kMrTX / kP); t += 256) {
-            const int cy = t % CY, xb = t / CY;
-            float2 smp[NS], acc[kP];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) smp[i] = p2c[(xb * (kP / S) + i) * CY + cy];
-            interp16<S>(acc, smp, taps, 0);
-#pragma unroll
-            for (int p = 0; p < kP; ++p) p3t[cy * P3P + xb * kP + p] = acc[p];
-        }
-        __syncthreads();
+        __syncthreads();          // tile c+1 landed, p3t[c] complete, buffers of phase c-1 released
+        fetch(c + 2);
+        if (c + 1 < prm.n_cand) interp_x(c + 1);
         // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
+        const float2* p3t = p3t0 + (c & 1) * CY * P3P;
         const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float2 smp[NS], acc[kP];
 #pragma unroll
             for (int i = 0; i < NS; ++i) smp[i] = p3t[(warp * (kP / S) + i) * P3P + lane + 32 * h];
-            interp16<S>(acc, smp, taps, S * kMrW);
+            interp_block<S, kP>(acc, smp, taps, S * kMrW);
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
@@ -518,6 +537,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             }
         }
     }
+    cp_async_wait_all();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int x = x0 + lane + 32 * h;
@@ -1076,14 +1096,14 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.p2 = g.p2; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
-        const size_t smem = (size_t)(2 * CX * CY + CY * (kMrTX + 1)) * sizeof(float2);
+        const size_t smem = (size_t)(2 * CX * CY + 2 * CY * (kMrTX + 1)) * sizeof(float2);
         dim3 grid(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX), count);
         KernelTimer timer("k_mr_interp", st);
         if (g.n_cand <= 256) {
-            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             k_mr_interp<S, 8><<<grid, 256, smem, st>>>(p, tb);
         } else {
-            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             k_mr_interp<S, 16><<<grid, 256, smem, st>>>(p, tb);
         }
     }
