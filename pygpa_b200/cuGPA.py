@@ -42,11 +42,27 @@ def _to_host(t):
     return host
 
 
+_plans = {}
+
+
+def _plan_for(shape, sigma, kx, ky, kw, kstep, device):
+    """SweepPlan cache: the geometry (candidate axes, taps, scratch sizing) of a call depends only on
+    these arguments, and building it costs a few ms of host time (cudaMemGetInfo, tap tables)."""
+    key = (tuple(shape), float(sigma), float(kx), float(ky), float(kw), float(kstep), str(device))
+    plan = _plans.get(key)
+    if plan is None:
+        if len(_plans) >= 64:
+            _plans.clear()
+        wxs, wys = engine.grid_axes(kx, ky, kw, kstep)
+        plan = engine.SweepPlan(shape, wxs, wys, sigma, engine.CAND_GRID, device=device)
+        _plans[key] = plan
+    return plan
+
+
 def _sweep(image, sigma, kx, ky, kw, kstep, grad_mode, want_w, want_grad=True):
     device = engine.require_cuda()
     img = engine.image_to_device(image, device)
-    wxs, wys = engine.grid_axes(kx, ky, kw, kstep)
-    plan = engine.SweepPlan(img.shape, wxs, wys, sigma, engine.CAND_GRID, device=device)
+    plan = _plan_for(img.shape, sigma, kx, ky, kw, kstep, device)
     res = plan.run(img, (kx, ky), grad_mode if want_grad else engine.GRAD_NONE, out_f64=True,
                    want_w=want_w, want_kidx=False)
     host = {k: _to_host(res[k]) for k in ("lockin", "w", "grad") if res.get(k) is not None}
