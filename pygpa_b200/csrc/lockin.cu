@@ -287,22 +287,25 @@ struct MrPass1Params {
     const float2* phy;
     float2* p1;            // [chunk][n_alloc][pitch_d]
     size_t plane_stride;
-    int N, M, Md, pitch_d, n_rows_filled, Rax, Ray, J /* taps per phase */, plane0;
+    int N, M, Md, pitch_d, n_rows_filled, Rax, Ray, J /* taps per phase */, plane0, count, planes_per_cta;
 };
 
-// decimating version of k_pass1: lane = padded row, warp w owns decimated outputs [w*P, w*P+P)
+// decimating version of k_pass1: lane = padded row, warp w owns decimated outputs [w*P, w*P+P).
+// The image tile is plane independent, so it is staged ONCE per CTA as raw float samples
+// (transposed, pitch 33) and the CTA loops over `planes_per_cta` planes; per plane only the
+// carrier of the tile columns is staged (double buffered) and applied on the fly (2 FMUL/sample).
 template <int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS * 32, 2)
 k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
-    extern __shared__ float2 smem[];
+    extern __shared__ float smem_f[];
     constexpr int SP = 33;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = blockIdx.x * 32;
     const int m0 = blockIdx.y * (WARPS * kP);          // first decimated output column
-    const int pl = blockIdx.z;
     const int M = prm.M, N = prm.N, J = prm.J;
     const int n_samp = S * (WARPS * kP + J + kAhead + 1);
-    const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
+    float* const tile = smem_f;                                              // [n_samp][SP] float
+    float2* const car = reinterpret_cast<float2*>(smem_f + (size_t)n_samp * SP + (n_samp * SP & 1));   // [2][n_samp]
     int cbase = (S * m0 - prm.Ray) % M;
     if (cbase < 0) cbase += M;
     for (int rr = warp; rr < 32; rr += WARPS) {
@@ -312,27 +315,50 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
         for (int j = lane; j < n_samp; j += 32) {
             int c = cbase + j;
             if (c >= M) c %= M;
-            const float v = __ldg(row + c);
-            const float2 ph = __ldg(phy + c);
-            smem[j * SP + rr] = make_float2(v * ph.x, v * ph.y);
+            tile[j * SP + rr] = __ldg(row + c);
         }
     }
+    const int pl0 = blockIdx.z * prm.planes_per_cta;
+    const int pl1 = min(pl0 + prm.planes_per_cta, prm.count);
+    auto stage_carrier = [&](int pl, int slot) {
+        const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
+        float2* dst = car + slot * n_samp;
+        for (int j = threadIdx.x; j < n_samp; j += WARPS * 32) {
+            int c = cbase + j;
+            if (c >= M) c %= M;
+            dst[j] = __ldg(phy + c);
+        }
+    };
+    stage_carrier(pl0, 0);
     __syncthreads();
-    const float2* col = smem + (S * warp * kP) * SP + lane;
-    float2 acc[kP];
-#pragma unroll
-    for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
-    for (int q = 0; q < S; ++q)
-        fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return col[(S * j + q) * SP]; });
+    const float* col = tile + (S * warp * kP) * SP + lane;
     const int r = r0 + lane;
     const int m = m0 + warp * kP;
-    if (r < prm.n_rows_filled) {
-        float2* out = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)r * prm.pitch_d + m;
+    int slot = 0;
+    for (int pl = pl0; pl < pl1; ++pl, slot ^= 1) {
+        if (pl + 1 < pl1) stage_carrier(pl + 1, slot ^ 1);
+        const float2* ph = car + slot * n_samp + S * warp * kP;
+        float2 acc[kP];
 #pragma unroll
-        for (int p = 0; p < kP; p += 2) {
-            if (m + p + 1 < prm.pitch_d) *reinterpret_cast<float4*>(out + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
-            else if (m + p < prm.pitch_d) out[p] = acc[p];
+        for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+        for (int q = 0; q < S; ++q) {
+            const float* colq = col + q * SP;
+            const float2* phq = ph + q;
+            fir_phase<kP>(acc, taps, q * J, J, [&](int j) {
+                const float v = colq[j * (S * SP)];
+                const float2 c = phq[j * S];
+                return make_float2(v * c.x, v * c.y);
+            });
         }
+        if (r < prm.n_rows_filled) {
+            float2* out = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)r * prm.pitch_d + m;
+#pragma unroll
+            for (int p = 0; p < kP; p += 2) {
+                if (m + p + 1 < prm.pitch_d) *reinterpret_cast<float4*>(out + p) = make_float4(acc[p].x, acc[p].y, acc[p + 1].x, acc[p + 1].y);
+                else if (m + p < prm.pitch_d) out[p] = acc[p];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1067,11 +1093,17 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
         p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
         p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0;
-        constexpr int W1 = S == 8 ? 4 : 8;
-        const size_t smem = (size_t)S * (W1 * kP + g.Jy + kAhead + 1) * 33 * sizeof(float2);
+        constexpr int W1 = 8;
+        const size_t n_samp1 = (size_t)S * (W1 * kP + g.Jy + kAhead + 1);
+        const size_t smem = (n_samp1 * 33 + 1) * sizeof(float) + 2 * n_samp1 * sizeof(float2);
         GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
         GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1<S, W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, W1 * kP), count);
+        // planes per CTA: amortise the tile fill but keep >= ~4 waves of CTAs
+        const int tiles = ceil_div(g.n_rows_filled, 32) * ceil_div(g.pitch_d, W1 * kP);
+        int ppc = 1;
+        while (ppc < 8 && (long long)tiles * ceil_div(count, ppc * 2) >= 4 * 296) ppc *= 2;
+        p.count = count; p.planes_per_cta = ppc;
+        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, W1 * kP), ceil_div(count, ppc));
         KernelTimer timer("k_mr_pass1", st);
         k_mr_pass1<S, W1><<<grid, W1 * 32, smem, st>>>(p, ty);
     }
