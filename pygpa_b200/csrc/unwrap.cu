@@ -9,7 +9,7 @@
 // enqueues (it polls the flag every few iterations to stop enqueueing early).
 //
 // DCT-II / DCT-III (scipy.fft.dctn / idctn, unnormalised): one row per CTA in shared memory.
-// Power-of-two lengths use Makhoul's N-point complex FFT (radix-2 Stockham in place, twiddles
+// Power-of-two lengths use Makhoul's N-point complex FFT (radix-4 Stockham in place, twiddles
 // from a table); other lengths use the O(n^2) cosine-table sum (any n, slower).  The 2-D
 // transform is row pass -> transpose -> row pass; the 1/scale of the Poisson solve is fused into
 // the second forward pass and <r, z> into the last inverse pass.
@@ -48,17 +48,14 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // ------------------------------------------------------------------------------------------
 // tables
 // ------------------------------------------------------------------------------------------
-// tw[t] = exp(-2 pi i t / n), t < n/2 ;  mk[k] = exp(-i pi k / (2n)), k < n ; ct[j] = cos(pi j / (2n)), j < 4n
+// tw[t] = exp(-2 pi i t / n), t < n ;  mk[k] = exp(-i pi k / (2n)), k < n ; ct[j] = cos(pi j / (2n)), j < 4n
 __global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (pow2) {
-        if (i < n / 2) {
+        if (i < n) {
             double s, c;
             sincospi(-2.0 * (double)i / (double)n, &s, &c);
             tw[i] = make_double2(c, s);
-        }
-        if (i < n) {
-            double s, c;
             sincospi(-(double)i / (2.0 * (double)n), &s, &c);
             mk[i] = make_double2(c, s);
         }
@@ -68,35 +65,72 @@ __global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow
 }
 
 // ------------------------------------------------------------------------------------------
-// in-place radix-2 Stockham FFT of buf[0..n) (forward, e^{-2 pi i jk/n}); all threads of the CTA
+// in-place Stockham FFT of buf[0..n) (forward, e^{-2 pi i jk/n}); all threads of the CTA.
+// Radix-4 stages (half the shared-memory round trips of radix 2), preceded by one radix-2 stage
+// when log2(n) is odd.  MAXB = radix-4 butterflies per thread; tw[t] = e^{-2 pi i t/n}, t < n.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 zmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
 template <int MAXB>
 __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __restrict__ tw) {
-    const int half = n >> 1;
     const int nthr = blockDim.x;
-    for (int ns = 1; ns < n; ns <<= 1) {
-        double2 a[MAXB], b[MAXB];
-        const int tstep = half / ns;   // twiddle index stride: exp(-2 pi i k/(2 ns)) = tw[k * n/(2 ns)]
+    int ns = 1;
+    if (__popc(n - 1) & 1) {                         // log2(n) odd: one radix-2 stage
+        const int half = n >> 1;
+        double2 a[2 * MAXB], b[2 * MAXB];
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                a[q] = buf[j];
+                b[q] = buf[j + half];                // ns = 1: twiddle is 1
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                buf[2 * j] = make_double2(a[q].x + b[q].x, a[q].y + b[q].y);
+                buf[2 * j + 1] = make_double2(a[q].x - b[q].x, a[q].y - b[q].y);
+            }
+        }
+        __syncthreads();
+        ns = 2;
+    }
+    const int quarter = n >> 2;
+    for (; ns < n; ns <<= 2) {
+        double2 v[MAXB][4];
+        const int tstep = quarter / ns;              // e^{-2 pi i r k/(4 ns)} = tw[r k n/(4 ns)]
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
-            if (j < half) {
+            if (j < quarter) {
                 const int k = j & (ns - 1);
-                const double2 w = __ldg(tw + k * tstep);
-                const double2 x = buf[j + half];
-                a[q] = buf[j];
-                b[q] = make_double2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                v[q][0] = buf[j];
+                v[q][1] = zmul(buf[j + quarter], __ldg(tw + k * tstep));
+                v[q][2] = zmul(buf[j + 2 * quarter], __ldg(tw + 2 * k * tstep));
+                v[q][3] = zmul(buf[j + 3 * quarter], __ldg(tw + 3 * k * tstep));
             }
         }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
-            if (j < half) {
+            if (j < quarter) {
                 const int k = j & (ns - 1);
-                const int j0 = ((j - k) << 1) + k;
-                buf[j0] = make_double2(a[q].x + b[q].x, a[q].y + b[q].y);
-                buf[j0 + ns] = make_double2(a[q].x - b[q].x, a[q].y - b[q].y);
+                const int j0 = ((j - k) << 2) + k;
+                const double2 y0 = make_double2(v[q][0].x + v[q][2].x, v[q][0].y + v[q][2].y);
+                const double2 y1 = make_double2(v[q][0].x - v[q][2].x, v[q][0].y - v[q][2].y);
+                const double2 y2 = make_double2(v[q][1].x + v[q][3].x, v[q][1].y + v[q][3].y);
+                // -i (v1 - v3)
+                const double2 y3 = make_double2(v[q][1].y - v[q][3].y, -(v[q][1].x - v[q][3].x));
+                buf[j0] = make_double2(y0.x + y2.x, y0.y + y2.y);
+                buf[j0 + ns] = make_double2(y1.x + y3.x, y1.y + y3.y);
+                buf[j0 + 2 * ns] = make_double2(y0.x - y2.x, y0.y - y2.y);
+                buf[j0 + 3 * ns] = make_double2(y1.x - y3.x, y1.y - y3.y);
             }
         }
         __syncthreads();
@@ -126,7 +160,7 @@ __device__ __forceinline__ double poisson_scale(int I, int J, int dimN, int dimM
 
 // forward DCT-II of every row:  y[k] = 2 sum_m x[m] cos(pi k (2m+1) / (2n))
 template <int MAXB>
-__global__ void k_dct2_rows_pow2(const DctArgs a) {
+__global__ void __launch_bounds__(512, MAXB >= 4 ? 1 : 2) k_dct2_rows_pow2(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double2 cbuf[];
     const int n = a.n, row = blockIdx.x;
@@ -149,7 +183,7 @@ __global__ void k_dct2_rows_pow2(const DctArgs a) {
 
 // inverse (scipy idct type 2, norm=None): x = dct2^{-1}(y)
 template <int MAXB>
-__global__ void k_idct2_rows_pow2(const DctArgs a) {
+__global__ void __launch_bounds__(512, MAXB >= 4 ? 1 : 2) k_idct2_rows_pow2(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double2 cbuf[];
     __shared__ double red[1024];
@@ -303,7 +337,7 @@ __device__ __forceinline__ double sum_partials(const double* part, int n, double
 }
 
 __global__ void k_sc_init(UwScalars* sc, const double* part, int n, int kmax) {
-    __shared__ double sh[256];
+    __shared__ double sh[1024];
     const double s = sum_partials(part, n, sh);
     if (threadIdx.x == 0) {
         sc->r0sq = s;
@@ -316,7 +350,7 @@ __global__ void k_sc_init(UwScalars* sc, const double* part, int n, int kmax) {
 }
 
 __global__ void k_sc_beta(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[256];
+    __shared__ double sh[1024];
     if (sc->done) return;
     const double s = sum_partials(part, n, sh);
     if (threadIdx.x == 0) {
@@ -328,7 +362,7 @@ __global__ void k_sc_beta(UwScalars* sc, const double* part, int n) {
 }
 
 __global__ void k_sc_alpha(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[256];
+    __shared__ double sh[1024];
     if (sc->done) return;
     const double s = sum_partials(part, n, sh);
     if (threadIdx.x == 0) {
@@ -338,7 +372,7 @@ __global__ void k_sc_alpha(UwScalars* sc, const double* part, int n) {
 }
 
 __global__ void k_sc_stop(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[256];
+    __shared__ double sh[1024];
     if (sc->done) return;
     const double s = sum_partials(part, n, sh);
     if (threadIdx.x == 0) {
@@ -431,7 +465,7 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     for (AxisTables* ax : {&u.axN, &u.axM}) {
         const int n = ax == &u.axN ? N : M;
         ax->n = n; ax->pow2 = is_pow2(n) && n <= kMaxFftLen;
-        ax->tw = a.take<double2>(n / 2 + 1);
+        ax->tw = a.take<double2>(n + 1);
         ax->mk = a.take<double2>(n);
         ax->ct = a.take<double>(ax->pow2 ? 1 : 4 * (size_t)n);
     }
@@ -443,9 +477,11 @@ template <int INVERSE>
 static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
     a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n;
     if (ax.pow2) {
-        const int half = ax.n / 2;
-        int threads = half < 32 ? 32 : (half > 512 ? 512 : half);
-        const int per = (half + threads - 1) / threads;     // butterflies per thread
+        const int quarter = ax.n / 4 > 0 ? ax.n / 4 : 1;
+        // two radix-4 butterflies per thread where the row is long enough (ILP), at most 512 threads
+        int threads = quarter >= 128 ? quarter / 2 : quarter;
+        threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
+        const int per = (quarter + threads - 1) / threads;  // radix-4 butterflies per thread
         const size_t smem = (size_t)ax.n * sizeof(double2);
         auto go = [&](auto kern) -> int {
             GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
@@ -454,8 +490,7 @@ static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
         };
         if (per <= 1) return INVERSE ? go(k_idct2_rows_pow2<1>) : go(k_dct2_rows_pow2<1>);
         if (per <= 2) return INVERSE ? go(k_idct2_rows_pow2<2>) : go(k_dct2_rows_pow2<2>);
-        if (per <= 4) return INVERSE ? go(k_idct2_rows_pow2<4>) : go(k_dct2_rows_pow2<4>);
-        return INVERSE ? go(k_idct2_rows_pow2<8>) : go(k_dct2_rows_pow2<8>);
+        return INVERSE ? go(k_idct2_rows_pow2<4>) : go(k_dct2_rows_pow2<4>);
     }
     GPA_REQUIRE((size_t)ax.n * sizeof(double) <= 200 * 1024, "axis of length %d is too long for the direct DCT", ax.n);
     const size_t smem = (size_t)ax.n * sizeof(double);
@@ -531,7 +566,7 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
         s.wwx = u.wwx; s.wwy = u.wwy; s.r = u.r; s.phi = phi; s.partial = u.partial; s.N = N; s.M = M;
         KernelTimer timer("uw_setup", st);
         k_uw_setup<<<g2, 256, 0, st>>>(s);
-        k_sc_init<<<1, 256, 0, st>>>(u.sc, u.partial, n2, kmax);
+        k_sc_init<<<1, 1024, 0, st>>>(u.sc, u.partial, n2, kmax);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     // The reference always runs at least one iteration (k is tested after the update), so kmax <= 1
@@ -541,14 +576,14 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     for (int k = 0; k < iters; ++k) {
         int rc = poisson_solve(u, st);                       // t = z
         if (rc) return rc;
-        k_sc_beta<<<1, 256, 0, st>>>(u.sc, u.partial, N);
+        k_sc_beta<<<1, 1024, 0, st>>>(u.sc, u.partial, N);
         {
             KernelTimer timer("uw_vector_ops", st);
             k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
             k_uw_apply_q<<<g2, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
-            k_sc_alpha<<<1, 256, 0, st>>>(u.sc, u.partial, n2);
+            k_sc_alpha<<<1, 1024, 0, st>>>(u.sc, u.partial, n2);
             k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
-            k_sc_stop<<<1, 256, 0, st>>>(u.sc, u.partial, g1);
+            k_sc_stop<<<1, 1024, 0, st>>>(u.sc, u.partial, g1);
         }
         GPA_CHECK_CUDA(cudaGetLastError());
         if ((k & 7) == 7 && k + 1 < iters) {                 // stop enqueueing once converged
