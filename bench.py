@@ -112,7 +112,10 @@ def run_reference(args, cfg):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampling in the background.  The process is started before the warm-up (it needs
+    ~0.2 s to produce its first line) and samples every 50 ms with a timestamp; stop() keeps the
+    samples that fall inside the timed window [mark(), stop()]."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -120,34 +123,50 @@ class ClockSampler:
         self.idx = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
+        t1 = datetime.datetime.now()
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        rows = [[c.strip() for c in r.split(",")] for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 9]
         os.unlink(self.f.name)
-        if not rows:
+
+        def stamp(r):
+            try:
+                return datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                return None
+        pad = datetime.timedelta(milliseconds=60)
+        inside = [r for r in rows if stamp(r) is not None and self.t0 is not None and self.t0 - pad <= stamp(r) <= t1 + pad]
+        used, where = (inside, "timed region") if inside else (rows[-4:], "last samples before the end of the timed region")
+        if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = [float(r[1]) for r in rows]
+        sm = [float(r[2]) for r in used]
         reasons = set()
-        for r in rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower() == "active":
+        for r in used:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                if v.lower() == "active":
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(used[0][3]), "reasons": sorted(reasons),
+                "samples": len(used), "window": where, "power_w_max": max(float(r[4]) for r in used)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -181,23 +200,24 @@ def run_ours(args, cfg):
     taps = 2 * plans[0].rx + 1
 
     def step():
-        return gdist.sharded_sweep(img, plans, ks)
+        return gdist.sharded_sweep(img, plans, ks, dst=0 if world > 1 else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     lib.gpa_profile_enable(1)
     launches0 = engine.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -250,7 +270,7 @@ def run_ours(args, cfg):
             im = torch.empty(staged.shape, dtype=torch.float32, device=dev)
             _lib.check(lib.gpa_cast_f64_to_f32(ctypes.c_void_p(staged.data_ptr()), ctypes.c_void_p(im.data_ptr()),
                                                staged.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            outs = gdist.sharded_sweep(im, plans, ks)
+            outs = gdist.sharded_sweep(im, plans, ks, dst=0)
             if rank == 0:
                 host = [(cuGPA._to_host(o["lockin"]), cuGPA._to_host(o["grad"]), cuGPA._to_host(o["kidx"])) for o in outs]
                 torch.cuda.current_stream().synchronize()

@@ -33,11 +33,18 @@ struct PrefilterArgs {
     int pad;
     double scale;
     int boundary;           // kNearest -> reflect init, kConstant -> mirror init
-    int dst_stride;         // elements between consecutive i (>= cols); lets pass 1 write every 2nd slot
-    int dst_elem;           // element stride within a row (1, or 2 for the interleaved layout)
+    double gain;            // (1 - z)(1 - 1/z) = 6 per axis pass
 };
 
-__global__ void __launch_bounds__(128) k_prefilter_axis0(const PrefilterArgs a) {
+constexpr int kSegLen = 64;     // outputs per thread along the filter axis
+constexpr int kWarm = 40;       // warm-up samples of a segment's recursion: |pole|^40 = 1.3e-23
+
+// The recursions c+[i] = s[i] + z c+[i-1] and c[i] = z (c[i+1] - c+[i]) forget their start after
+// ~40 samples (|z| = 0.268), so each column is cut into segments of kSegLen outputs that run in
+// parallel, each warming its recursion up on the kWarm samples before (after) the segment; only the
+// first (last) segment uses scipy's exact boundary initialisation.  Threads of a warp sit on
+// adjacent columns (coalesced); results are exact to double rounding.
+__global__ void __launch_bounds__(128) k_prefilter_causal(const PrefilterArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.cols) return;
     const double z = kPole;
@@ -47,49 +54,85 @@ __global__ void __launch_bounds__(128) k_prefilter_axis0(const PrefilterArgs a) 
     auto s = [&](int i) -> double {
         int r = i - a.pad;
         r = r < 0 ? 0 : (r >= a.src_n ? a.src_n - 1 : r);
-        return 6.0 * a.scale * a.src[(size_t)r * a.src_cols + cs];
+        return a.gain * a.scale * a.src[(size_t)r * a.src_cols + cs];
     };
-    double* out = a.dst + (size_t)c * a.dst_elem;    // may alias a.src (in-place second pass)
-    const size_t st = (size_t)a.dst_stride;
+    double* out = a.dst + c;
+    const size_t st = (size_t)a.cols;
     if (n == 1) {
         out[0] = a.scale * a.src[cs];
         return;
     }
-    // ---- causal initial condition
-    double c0;
-    const int terms = n < kInitTerms ? n : kInitTerms;
-    if (a.boundary == kNearest) {          // reflect (half-sample symmetric)
-        const double zn = pow(z, (double)n);
-        double acc = 0.0, zi = 1.0;
-        for (int i = 0; i < terms; ++i) {
-            acc += zi * (s(i) + zn * s(n - 1 - i));
-            zi *= z;
+    const int i0 = blockIdx.y * kSegLen;
+    const int i1 = min(i0 + kSegLen, n);
+    double prev;
+    int i;
+    if (i0 == 0) {
+        // exact causal initial condition (scipy _init_causal_reflect / _init_causal_mirror)
+        const int terms = n < kInitTerms ? n : kInitTerms;
+        if (a.boundary == kNearest) {
+            const double zn = pow(z, (double)n);
+            double acc = 0.0, zi = 1.0;
+            for (int t = 0; t < terms; ++t) {
+                acc += zi * (s(t) + zn * s(n - 1 - t));
+                zi *= z;
+            }
+            prev = acc * z / (1.0 - zn * zn) + s(0);
+        } else {
+            const double zn1 = pow(z, (double)(n - 1));
+            double acc = s(0) + zn1 * s(n - 1), zi = z;
+            const int last = (n - 1) < kInitTerms ? (n - 1) : kInitTerms;
+            for (int t = 1; t < last; ++t) {
+                acc += zi * (s(t) + zn1 * s(n - 1 - t));
+                zi *= z;
+            }
+            prev = acc / (1.0 - zn1 * zn1);
         }
-        c0 = acc * z / (1.0 - zn * zn) + s(0);
-    } else {                               // mirror (whole-sample symmetric)
-        const double zn1 = pow(z, (double)(n - 1));
-        double acc = s(0) + zn1 * s(n - 1), zi = z;
-        const int last = (n - 1) < kInitTerms ? (n - 1) : kInitTerms;
-        for (int i = 1; i < last; ++i) {
-            acc += zi * (s(i) + zn1 * s(n - 1 - i));
-            zi *= z;
-        }
-        c0 = acc / (1.0 - zn1 * zn1);
+        out[0] = prev;
+        i = 1;
+    } else {
+        const int w0 = i0 - kWarm;           // i0 >= kSegLen > kWarm
+        prev = s(w0) / (1.0 - z);
+        for (int t = w0 + 1; t < i0; ++t) prev = fma(z, prev, s(t));
+        i = i0;
     }
-    // ---- causal sweep
-    double prev = c0;
-    out[0] = prev;
-    for (int i = 1; i < n; ++i) {
+    for (; i < i1; ++i) {
         prev = fma(z, prev, s(i));
         out[i * st] = prev;
     }
-    // ---- anti-causal initial condition and sweep
+}
+
+// src = c+ (n x cols), dst = c (n x cols); never in place (a segment reads its successor's c+)
+__global__ void __launch_bounds__(128) k_prefilter_anticausal(const double* __restrict__ cp, double* __restrict__ dst,
+                                                                int n, int cols, int boundary) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const double z = kPole;
+    const double* __restrict__ in = cp + c;
+    double* out = dst + c;
+    const size_t st = (size_t)cols;
+    if (n == 1) {
+        out[0] = in[0];
+        return;
+    }
+    const int i0 = blockIdx.y * kSegLen;
+    const int i1 = min(i0 + kSegLen, n);
     double nxt;
-    if (a.boundary == kNearest) nxt = prev * (z / (z - 1.0));
-    else nxt = (z * out[(size_t)(n - 2) * st] + prev) * z / (z * z - 1.0);
-    out[(size_t)(n - 1) * st] = nxt;
-    for (int i = n - 2; i >= 0; --i) {
-        nxt = z * (nxt - out[i * st]);
+    int i;
+    if (i1 + kWarm >= n) {
+        // the true end is within reach: exact anti-causal initial condition, then run down to i1
+        if (boundary == kNearest) nxt = in[(size_t)(n - 1) * st] * (z / (z - 1.0));
+        else nxt = (z * in[(size_t)(n - 2) * st] + in[(size_t)(n - 1) * st]) * z / (z * z - 1.0);
+        if (i1 == n) out[(size_t)(n - 1) * st] = nxt;
+        for (int t = n - 2; t >= i1; --t) nxt = z * (nxt - in[t * st]);
+        i = (i1 == n ? n - 2 : i1 - 1);
+    } else {
+        const int w1 = i1 + kWarm - 1;
+        nxt = in[w1 * st] * (z / (z - 1.0));
+        for (int t = w1 - 1; t >= i1; --t) nxt = z * (nxt - in[t * st]);
+        i = i1 - 1;
+    }
+    for (; i >= i0; --i) {
+        nxt = z * (nxt - in[i * st]);
         out[i * st] = nxt;
     }
 }
@@ -211,15 +254,18 @@ static int prefilter_2d(const double* src, int N, int M, double scale, int bound
     const int Np = N + 2 * pad, Mp = M + 2 * pad;
     PrefilterArgs a;
     a.src = src; a.dst = tmp0; a.n = Np; a.cols = Mp; a.src_n = N; a.src_cols = M; a.pad = pad; a.scale = scale;
-    a.boundary = boundary; a.dst_stride = Mp; a.dst_elem = 1;
-    k_prefilter_axis0<<<ceil_div(Mp, 128), 128, 0, st>>>(a);                       // along axis 0 (+ padding)
+    a.boundary = boundary; a.gain = 6.0;
+    dim3 gA(ceil_div(Mp, 128), ceil_div(Np, kSegLen));
+    k_prefilter_causal<<<gA, 128, 0, st>>>(a);                                      // along axis 0 (+ padding): tmp0 = c+
+    k_prefilter_anticausal<<<gA, 128, 0, st>>>(tmp0, tmp1, Np, Mp, boundary);       // tmp1 = c
     dim3 g1(ceil_div(Mp, 32), ceil_div(Np, 32));
-    k_transpose_plain<<<g1, dim3(32, 8), 0, st>>>(tmp0, tmp1, Np, Mp, 1, 0);        // tmp1: (Mp, Np)
-    a.src = tmp1; a.dst = tmp1; a.n = Mp; a.cols = Np; a.src_n = Mp; a.src_cols = Np; a.pad = 0; a.scale = 1.0;
-    a.dst_stride = Np;
-    k_prefilter_axis0<<<ceil_div(Np, 128), 128, 0, st>>>(a);                       // along axis 1
+    k_transpose_plain<<<g1, dim3(32, 8), 0, st>>>(tmp1, tmp0, Np, Mp, 1, 0);        // tmp0: (Mp, Np)
+    a.src = tmp0; a.dst = tmp1; a.n = Mp; a.cols = Np; a.src_n = Mp; a.src_cols = Np; a.pad = 0; a.scale = 1.0;
+    dim3 gB(ceil_div(Np, 128), ceil_div(Mp, kSegLen));
+    k_prefilter_causal<<<gB, 128, 0, st>>>(a);                                      // along axis 1: tmp1 = c+
+    k_prefilter_anticausal<<<gB, 128, 0, st>>>(tmp1, tmp0, Mp, Np, boundary);       // tmp0 = c
     dim3 g2(ceil_div(Np, 32), ceil_div(Mp, 32));
-    k_transpose_plain<<<g2, dim3(32, 8), 0, st>>>(tmp1, dst, Mp, Np, dst_elem, dst_off);
+    k_transpose_plain<<<g2, dim3(32, 8), 0, st>>>(tmp0, dst, Mp, Np, dst_elem, dst_off);
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }
