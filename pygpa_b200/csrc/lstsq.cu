@@ -76,21 +76,22 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
         const double f2 = swap ? n1 : n0;
         if (f2 > 0.0) {
             const double f = sqrt(f2);
+            const double inv_f = 1.0 / f;
+            double q[kMaxD];
             double g = 0.0, z1 = 0.0;
 #pragma unroll
             for (int i = 0; i < kMaxD; ++i) {
                 if (i < p.d) {
-                    const double q = (swap ? a1[i] : a0[i]) / f;
-                    g = fma(q, swap ? a0[i] : a1[i], g);
-                    z1 = fma(q, y[i], z1);
+                    q[i] = (swap ? a1[i] : a0[i]) * inv_f;
+                    g = fma(q[i], swap ? a0[i] : a1[i], g);
+                    z1 = fma(q[i], y[i], z1);
                 }
             }
             double h2 = 0.0, z2h = 0.0;   // second column orthogonalised against the first
 #pragma unroll
             for (int i = 0; i < kMaxD; ++i) {
                 if (i < p.d) {
-                    const double q = (swap ? a1[i] : a0[i]) / f;
-                    const double e = (swap ? a0[i] : a1[i]) - g * q;
+                    const double e = (swap ? a0[i] : a1[i]) - g * q[i];
                     h2 = fma(e, e, h2);
                     z2h = fma(e, y[i], z2h);     // = h * z2
                 }
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
             double u0, u1;
             if (s2 > 2.220446049250313e-16 * s1) {
                 u1 = z2h / h2;                 // z2 / h
-                u0 = (z1 - g * u1) / f;
+                u0 = (z1 - g * u1) * inv_f;
             } else {                            // rank 1: minimum-norm solution of [f g] u = z1
                 const double nn = f * f + g * g;
                 u0 = f * z1 / nn;
