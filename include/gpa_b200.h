@@ -64,6 +64,9 @@ int gpa_profile_read(const char* kernel, double* total_ms, int* launches, int re
  * (cp.asarray(image), cuGPA.py:52); the kernels read float32. */
 int gpa_cast_f64_to_f32(const double* in, float* out, size_t n, void* stream);
 
+/* Decode merged arg-max keys (see gpa_sweep_argmax): kidx[i] = flat candidate index, -1 where nothing won. */
+int gpa_key_to_kidx(const unsigned long long* key, int* kidx, size_t n, void* stream);
+
 /* Glue of extract_displacement_field (geometric_phase_analysis.py:922-926) kept on the device:
  * phases = angle(lockin), weights = |lockin| * (mask + eps) with mask = 1 on the interior
  * [border, N-border) x [border, M-border).  lockin is float2 (is_f64 = 0) or double2. */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "gpa_profile_enable": (c_int, [c_int]),
     "gpa_profile_read": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_double), ctypes.POINTER(c_int), c_int]),
     "gpa_cast_f64_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_key_to_kidx": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_phase_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "gpa_lockin_workspace_bytes": (c_int, [c_int] * 7 + [ctypes.POINTER(c_size_t)]),
     "gpa_lockin_fixed": (c_int, [c_void_p, c_int, c_int, c_double, c_double, _pf, c_int, _pf, c_int,

@@ -1,0 +1,81 @@
+"""Frame-batch driver (BASELINE config 4): a time series of frames, each run through the whole
+adaptive pipeline — sweep per primary k-vector, displacement field, Lawler-Fujita undistortion —
+entirely on the device.  Frames are independent, so a multi-GPU job shards them over the ranks
+with no collective on the data path (weak scaling); results are gathered by the caller.
+
+The per-frame chain is the device-resident twin of
+    u = extract_displacement_field(frame, kvecs)        (geometric_phase_analysis.py:907-932)
+    corrected = undistort_image(frame, -u)               (:935-974; u = -extracted field, tests :63)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import engine, solvers
+
+__all__ = ["FramePipeline", "shard_frames", "process_frames"]
+
+
+class FramePipeline:
+    """Plans (candidate axes, taps, scratch) for one frame shape, reused for every frame."""
+
+    def __init__(self, shape, kvecs, sigma=None, kwscale=2.5, ksteps=3, n_grid=None, device=None):
+        self.device = device or engine.require_cuda()
+        self.kvecs = np.asarray(kvecs, dtype=np.float64)
+        norms = np.linalg.norm(self.kvecs, axis=1)
+        self.kw = float(norms.mean() / kwscale)
+        self.sigma = int(np.ceil(1 / norms.min())) if sigma is None else sigma
+        self.kstep = 2 * self.kw / (n_grid - 0.5) if n_grid else self.kw / ksteps
+        self.plans = []
+        for pk in self.kvecs:
+            wxs, wys = engine.grid_axes(pk[0], pk[1], self.kw, self.kstep)
+            self.plans.append(engine.SweepPlan(shape, wxs, wys, self.sigma, device=self.device))
+
+    def displacement(self, frame_dev):
+        """frame (N, M) float32 CUDA tensor (mean already removed) -> u (2, N, M) float64 CUDA tensor,
+        the field extract_displacement_field returns."""
+        phs, wts = [], []
+        for plan, pk in zip(self.plans, self.kvecs):
+            res = plan.run(frame_dev, pk, engine.GRAD_NONE, want_kidx=False)
+            ph, wt = solvers.phase_weight(res["lockin"], 2 * int(self.sigma))
+            phs.append(ph)
+            wts.append(wt)
+        return solvers.displacement_from_phases(self.kvecs, torch.stack(phs), torch.stack(wts))
+
+    def __call__(self, frame, undistort=True):
+        """One frame (NumPy or tensor) -> dict(u, corrected) of CUDA tensors (float64)."""
+        arr = frame if isinstance(frame, torch.Tensor) else np.asarray(frame, dtype=np.float64)
+        arr = arr - arr.mean()
+        f32 = engine.image_to_device(arr, self.device)
+        u = self.displacement(f32)
+        out = {"u": u}
+        if undistort:
+            # the extracted field is minus the physical displacement (lock-in phase = -2 pi k.u)
+            out["corrected"] = solvers.undistort(f32.double(), -u)
+        return out
+
+
+def shard_frames(n_frames, world, rank):
+    """Contiguous, balanced share of the frame indices for `rank`."""
+    lo = (n_frames * rank) // world
+    hi = (n_frames * (rank + 1)) // world
+    return range(lo, hi)
+
+
+def process_frames(frames, kvecs, sigma=None, n_grid=None, undistort=True, group=None):
+    """Run this rank's share of `frames` (sequence or (T, N, M) array).  Returns {index: dict of
+    NumPy arrays}; no communication happens here."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = shard_frames(len(frames), world, rank)
+    pipe = None
+    out = {}
+    for t in mine:
+        frame = np.asarray(frames[t])
+        if pipe is None:
+            pipe = FramePipeline(frame.shape, kvecs, sigma=sigma, n_grid=n_grid)
+        res = pipe(frame, undistort=undistort)
+        out[t] = {k: v.cpu().numpy() for k, v in res.items()}
+    return out

@@ -50,3 +50,23 @@ extern "C" int gpa_phase_weight(const void* lockin, int is_f64, int N, int M, in
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }
+
+namespace gpa {
+// kidx = flat candidate index packed in the key, -1 where no candidate won (high word 0)
+__global__ void k_key_to_kidx(const unsigned long long* __restrict__ key, int* __restrict__ kidx, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = key[i];
+        kidx[i] = (k >> 32) == 0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+    }
+}
+}  // namespace gpa
+
+extern "C" int gpa_key_to_kidx(const unsigned long long* key, int* kidx, size_t n, void* stream) {
+    GPA_REQUIRE(key && kidx, "null pointer argument");
+    if (n == 0) return GPA_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gpa::k_key_to_kidx<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(key, kidx, n);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}

@@ -67,40 +67,46 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     plans: one engine.SweepPlan per peak (identical on every rank; give them private workspaces so
     the finalize reuses what the arg-max left and stays bit-identical to one GPU).
     Returns [dict(lockin, grad, kidx, key)] per peak — on every rank, or with dst=<rank> the payload
-    (lockin, grad) is only reduced to that rank (half the NVLink traffic of an all-reduce).
+    (lockin, grad) is only reduced to that rank.
 
-    The collectives are asynchronous and pipelined per peak: the MAX all-reduce of peak p's keys
-    runs on NCCL's stream while the arg-max kernels of peak p+1 execute, and the payload reduction
-    of peak p overlaps the finalize of peak p+1."""
+    Exactly two collectives per frame, each issued when every rank has finished its local work:
+    one MAX all-reduce of the stacked keys (8 B/pixel/peak) and one SUM reduction of the stacked
+    payload (16 B/pixel/peak).  They are deliberately NOT overlapped with the arg-max kernels: the
+    plane shares of the ranks start at different peaks, so an early collective would make NCCL's
+    CTAs spin on the slower peer while occupying SMs the sweep kernels need (measured: +4 ms per
+    frame on 2 GPUs, against 0.75 ms for the two collectives issued at the end)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world == 1:
         return [plan.run(img_dev, kref, grad_mode) for plan, kref in zip(plans, krefs)]
-    ranges = shard_units(len(plans), plans[0].wy.size, world, rank)
-    keys, key_work = [], []
-    for plan, (lo, hi) in zip(plans, ranges):
-        key = torch.zeros((plan.n, plan.m), dtype=torch.int64, device=img_dev.device)
+    n_peaks, n, m, dev = len(plans), plans[0].n, plans[0].m, img_dev.device
+    ranges = shard_units(n_peaks, plans[0].wy.size, world, rank)
+    keys = torch.zeros((n_peaks, n, m), dtype=torch.int64, device=dev)
+    for p, (plan, (lo, hi)) in enumerate(zip(plans, ranges)):
         if hi > lo:
-            plan.argmax(img_dev, key, lo, hi)
-        keys.append(key)
-        key_work.append(dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group, async_op=True))
-    outs, pay_work = [], []
-    for plan, key, work, kref, (lo, hi) in zip(plans, keys, key_work, krefs, ranges):
-        work.wait()
-        out = plan.finalize(img_dev, key, kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
-                            planes_valid=plan._private)
-        out["key"] = key
+            plan.argmax(img_dev, keys[p], lo, hi)
+    dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    want_grad = grad_mode != 2
+    # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)] float32, zero where this rank owns nothing
+    payload = torch.zeros((2 if want_grad else 1, n_peaks, n, m, 2), dtype=torch.float32, device=dev)
+    lockin = torch.view_as_complex(payload[0])
+    outs = []
+    for p, (plan, kref, (lo, hi)) in enumerate(zip(plans, krefs, ranges)):
+        out = {"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None}
+        plan.finalize(img_dev, keys[p], kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
+                      planes_valid=plan._private, out=out)
+        out["key"] = keys[p]
         outs.append(out)
-        for t in (out["lockin"], out["grad"]):
-            if t is None:
-                continue
-            flat = torch.view_as_real(t) if t.is_complex() else t
-            if dst is None:
-                pay_work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
-            else:
-                pay_work.append(dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group, async_op=True))
-    for w in pay_work:
-        w.wait()
-    for o in outs:
-        o["kidx"] = unpack_key(o["key"])[1].to(torch.int32)
+    if dst is None:
+        dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(payload, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    kidx = torch.empty((n_peaks, n, m), dtype=torch.int32, device=dev)
+    if dev.type == "cuda":
+        from . import _lib, engine
+        _lib.check(_lib.load().gpa_key_to_kidx(engine._ptr(keys), engine._ptr(kidx), keys.numel(), engine._stream()))
+    else:
+        kidx.copy_(unpack_key(keys)[1])
+    for p, o in enumerate(outs):
+        o["kidx"] = kidx[p]
     return outs

@@ -1,0 +1,34 @@
+"""Frame-batch driver (config 4 in miniature): device-resident chain == the NumPy-API chain == oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from parity import DISP_TOL
+from pygpa_b200 import batch, synth
+from pygpa_b200 import geometric_phase_analysis as GPA
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shard_frames():
+    assert [len(batch.shard_frames(512, 8, r)) for r in range(8)] == [64] * 8
+    assert sorted(i for r in range(3) for i in batch.shard_frames(10, 3, r)) == list(range(10))
+
+
+def test_frame_series_matches_single_frame_api_and_oracle():
+    shape = (128, 160)
+    ks = synth.primary_ks(0.1, 7.0, 3)
+    base = synth.smooth_random_field(shape, 0.05, seed=3)
+    frames = []
+    for t in range(3):
+        u = base * (1 + 0.2 * np.sin(2 * np.pi * t / 3))
+        frames.append(synth.lattice_image(shape, ks, u, noise=0.1, seed=100 + t) * (1 + 0.1 * t))
+    res = batch.process_frames(frames, ks)
+    assert sorted(res) == [0, 1, 2]
+    for t, frame in enumerate(frames):
+        u_api = GPA.extract_displacement_field(frame, ks)
+        assert np.abs(res[t]["u"] - u_api).max() < 1e-9
+        assert res[t]["corrected"].shape == shape
+        assert np.abs(res[t]["corrected"] - GPA.undistort_image(frame - frame.mean(), -u_api)).max() < 1e-5
+    u_ref = oracle.extract_displacement_field(frames[1], ks)
+    assert np.percentile(np.abs(res[1]["u"] - u_ref), 99.9) < DISP_TOL
