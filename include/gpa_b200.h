@@ -5,7 +5,7 @@
  * The reference (TAdeJong/pyGPA) is pure Python and has no FFI: its boundary for this
  * path is a set of module-level functions taking and returning NumPy arrays.  Each entry
  * point below names the reference function(s) whose arithmetic it replaces
- * (paths relative to the reference checkout).  pygpa_b200/*.py binds these with ctypes
+ * (paths relative to the reference checkout).  the modules under pygpa_b200/ bind these with ctypes
  * and re-exports the reference signatures; INTEGRATION.md shows the stub a pyGPA
  * maintainer would add.
  *
@@ -89,6 +89,16 @@ int gpa_phase_weight(const void* lockin, int is_f64, int N, int M, int border, d
  * The caller supplies the taps (host float arrays of 2R+1 entries; the Python host derives
  * them from scipy's exact transfer function, see pygpa_b200/_taps.py).
  * ------------------------------------------------------------------------------------------ */
+
+/* Host-side helpers (no CUDA): the taps of the reference's Gaussian low-pass on a circular axis of
+ * length n (real-space kernel of exp(-2 pi^2 sigma^2 f^2), |d| <= R), the default truncation radius
+ * min(ceil(trunc * sigma), (n-1)/2), and the multirate plan: returns the stride (2, 4, 8; 0 = use the
+ * direct form) and sigma_a, sigma_b, Ra = ceil(4.5 sigma_a), Rb = ceil(4.5 sigma_b); the taps for
+ * gpa_sweep_argmax_mr are then gpa_gaussian_taps(N, sigma_a, Ra), (M, sigma_a, Ra), (N, sigma_b, Rb),
+ * (M, sigma_b, Rb). */
+int gpa_gaussian_taps(int n, double sigma, int R, float* taps /*host, 2R+1*/);
+int gpa_default_radius(int n, double sigma, double trunc);
+int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, double* sigma_b, int* Ra, int* Rb);
 
 /* Scratch for a sweep / fixed lock-in over `n_rows` axis-0 carriers and `n_planes` first-pass
  * planes, keeping `planes_in_flight` (1..n_planes) planes resident at a time.  Keeping all

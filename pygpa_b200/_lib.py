@@ -26,6 +26,9 @@ SIGNATURES = {
     "gpa_cast_f64_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_key_to_kidx": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_phase_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "gpa_gaussian_taps": (c_int, [c_int, c_double, c_int, _pf]),
+    "gpa_default_radius": (c_int, [c_int, c_double, c_double]),
+    "gpa_multirate_plan": (c_int, [c_int, c_int, c_double, _pd, _pd, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "gpa_lockin_workspace_bytes": (c_int, [c_int] * 7 + [ctypes.POINTER(c_size_t)]),
     "gpa_lockin_fixed": (c_int, [c_void_p, c_int, c_int, c_double, c_double, _pf, c_int, _pf, c_int,
                                  c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -69,3 +69,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), f"{f} references the oracle / reference"
+
+
+@pytest.mark.parametrize("n,sigma", [(64, 4.0), (500, 10.0), (2048, 8.98), (2048, 4.4), (33, 2.5)])
+def test_c_side_taps_and_multirate_plan_agree_with_python(n, sigma):
+    """The C ABI's host helpers (for non-Python hosts) reproduce pygpa_b200/_taps.py."""
+    import ctypes
+    lib = _lib.load()
+    ref, r = _taps.axis_taps(n, sigma)
+    assert lib.gpa_default_radius(n, sigma, 4.5) == r
+    got = np.zeros(2 * r + 1, dtype=np.float32)
+    assert lib.gpa_gaussian_taps(n, sigma, r, _lib.as_pf(got)) == 0
+    assert np.abs(got - ref).max() <= 2e-7 * ref.max()
+    for size, sg in ((2048, 10.0), (1024, 10.0), (256, 5.0), (2048, 22.0), (64, 4.0), (500, 9.0), (250, 10.0)):
+        sa, sb = ctypes.c_double(0), ctypes.c_double(0)
+        ra, rb = ctypes.c_int(0), ctypes.c_int(0)
+        s_c = lib.gpa_multirate_plan(size, size, sg, ctypes.byref(sa), ctypes.byref(sb), ctypes.byref(ra), ctypes.byref(rb))
+        mr = _taps.multirate_taps(size, size, sg)
+        assert s_c == (mr["S"] if mr else 0)
+        if mr:
+            assert (ra.value, rb.value) == (mr["Ra_x"], mr["Rb"]) and abs(sa.value - mr["sigma_a"]) < 1e-12
