@@ -137,6 +137,11 @@ int gpa_sweep_argmax(const float* img, int N, int M,
  * arg-max decision uses these amplitudes: gpa_sweep_finalize recomputes the winner in the direct
  * form.  taps_a*: decimation filter (2 Ra + 1 taps per axis); taps_b*: interpolation filter
  * (2 Rb + 1 taps, not yet multiplied by the stride).  N and M must be multiples of stride. */
+/* The multirate arg-max drops, per 64 x 128 pixel tile, every candidate whose coarse-grid amplitude
+ * bound cannot beat the winners already recorded in `key` (exact branch and bound: results are
+ * bit-identical with it on or off; it only changes how much work is done).  On by default. */
+int gpa_set_pruning(int on);
+
 int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int stride,
                                  int Rax, int Ray, int Rb, int planes_in_flight, size_t* bytes);
 int gpa_sweep_argmax_mr(const float* img, int N, int M,

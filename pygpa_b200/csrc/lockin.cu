@@ -367,7 +367,8 @@ struct MrPass2Params {
     size_t plane_stride;
     const float2* phx;     // [n_rows][n_alloc], padded-row carrier
     float2* p2;            // [chunk][n_cand][Nd][Md]
-    int Nd, Md, pitch_d, n_alloc, J, plane0, n_cand, row_c, row_p;
+    float* pmax;           // [chunk][n_cand][nbx][nby]: max |P2|^2 over blocks of 16 x 32 coarse cells
+    int Nd, Md, pitch_d, n_alloc, J, plane0, n_cand, row_c, row_p, nbx, nby;   // nbx, nby: ALLOCATED block grid
 };
 
 // decimating version of k_pass2: lane = decimated column, warp w owns decimated rows [w*P, w*P+P);
@@ -418,13 +419,22 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
             fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(colq[j * (S * kLanes)], phq[j * S]); });
         }
         float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * prm.Nd * prm.Md;
+        float a2max = 0.f;
         if (my < prm.Md) {
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const int mx = mx0 + warp * kP + p;
-                if (mx < prm.Nd) out[(size_t)mx * prm.Md + my] = acc[p];
+                if (mx < prm.Nd) {
+                    out[(size_t)mx * prm.Md + my] = acc[p];
+                    a2max = fmaxf(a2max, fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y));
+                }
             }
         }
+        // block maximum for the interpolation kernel's branch-and-bound (a warp = 16 x 32 coarse cells)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a2max = fmaxf(a2max, __shfl_xor_sync(0xffffffffu, a2max, o));
+        if (lane == 0)
+            prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + (mx0 / kP + warp)) * prm.nby + blockIdx.x] = a2max;
         group_sync();     // this group's next carrier is complete; the current one is no longer read
     }
 }
@@ -451,9 +461,12 @@ __device__ __forceinline__ void interp_block(float2 (&acc)[Q], const float2 (&sm
 
 struct MrInterpParams {
     const float2* p2;      // [chunk][n_cand][Nd][Md]
+    const float* pmax;     // [chunk][n_cand][nbx][nby] block maxima of |P2|^2 (k_mr_pass2)
     unsigned long long* key;
-    int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p;
+    int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p, nbx, nby, nbx_alloc, nby_alloc, count, prune;   // nbx, nby: logical (wrap) block grid
 };
+
+constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor list can hold
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -484,8 +497,72 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     float2* const p3t0 = smem + 2 * CX * CY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
-    const int pl = blockIdx.z, plane = prm.plane0 + pl;
+    // planes are visited centre-out (blockIdx.z = 0 is the middle plane of the chunk): the planes
+    // nearest the nominal k-vector usually hold the winners, so later CTAs find high thresholds
+    const int zz = blockIdx.z, mid = (prm.count - 1) >> 1;
+    const int pl = (zz & 1) ? mid + ((zz + 1) >> 1) : mid - (zz >> 1);
+    const int plane = prm.plane0 + pl;
     const int Nd = prm.Nd, Md = prm.Md;
+    // ---- branch and bound: a candidate whose |P2|^2 block maxima over this tile's coarse window
+    // stay below the smallest winning |sf|^2 already recorded for the tile's pixels cannot win
+    // anywhere in the tile (the interpolation taps are non-negative and sum to <= 1), so it is
+    // dropped before any work is spent on it.  The thresholds come from `key`, which only grows.
+    __shared__ float s_thr[8];
+    __shared__ int s_cnt;
+    __shared__ unsigned short s_list[kMaxPruneCand];
+    int n_live = prm.n_cand;
+    const bool prune = prm.prune != 0;
+    if (prune) {
+        float tmin = 3.4e38f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int x = x0 + lane + 32 * h;
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int y = y0 + warp * kP + p;
+                if (x < prm.N && y < prm.M) tmin = fminf(tmin, __uint_as_float((unsigned)(prm.key[(size_t)x * prm.M + y] >> 32)));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        if (lane == 0) s_thr[warp] = tmin;
+        __syncthreads();
+        if (warp == 0) {
+            float thr = s_thr[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) thr = fminf(thr, s_thr[i]);
+            // coarse window of the tile: rows [x0/S - HL, +CX), columns [y0/S - HL, +CY); blocks of 16 x 32
+            const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
+            const int bx0 = (r_lo >= 0 ? r_lo : r_lo - 15) / 16, bx1 = (r_lo + CX - 1 >= 0 ? r_lo + CX - 1 : r_lo + CX - 16) / 16;
+            const int by0 = (c_lo >= 0 ? c_lo : c_lo - 31) / 32, by1 = (c_lo + CY - 1 >= 0 ? c_lo + CY - 1 : c_lo + CY - 32) / 32;
+            int cnt = 0;
+            for (int base = 0; base < prm.n_cand; base += 32) {
+                const int c = base + lane;
+                bool keep = false;
+                if (c < prm.n_cand) {
+                    const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
+                    float m = 0.f;
+                    for (int bx = bx0; bx <= bx1; ++bx) {
+                        int wx = bx % prm.nbx;
+                        if (wx < 0) wx += prm.nbx;
+                        for (int by = by0; by <= by1; ++by) {
+                            int wy = by % prm.nby;
+                            if (wy < 0) wy += prm.nby;
+                            m = fmaxf(m, __ldg(pm + wx * prm.nby_alloc + wy));
+                        }
+                    }
+                    keep = !(m * 1.0002f < thr);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)c;
+                cnt += __popc(bal);
+            }
+            if (lane == 0) s_cnt = cnt;
+        }
+        __syncthreads();
+        n_live = s_cnt;
+    }
+    auto cand_of = [&](int i) -> int { return prune ? (int)s_list[i] : i; };
     // this thread's share of the coarse tile: fixed (row, col) offsets, wrapped once
     int off[PER];
 #pragma unroll
@@ -506,10 +583,10 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         for (int p = 0; p < kP / IPR; ++p) bidx[h][p] = 0u;
     }
     const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
-    auto fetch = [&](int c) {
-        if (c < prm.n_cand) {
-            const float2* __restrict__ g = src + (size_t)c * Nd * Md;
-            float2* dst = smem + (c & 1) * CX * CY;
+    auto fetch = [&](int i) {
+        if (i < n_live) {
+            const float2* __restrict__ g = src + (size_t)cand_of(i) * Nd * Md;
+            float2* dst = smem + (i & 1) * CX * CY;
 #pragma unroll
             for (int e = 0; e < PER; ++e)
                 if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
@@ -537,14 +614,15 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     fetch(1);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    interp_x(0);
-    for (int c = 0; c < prm.n_cand; ++c) {
+    if (n_live > 0) interp_x(0);
+    for (int i = 0; i < n_live; ++i) {
+        const int c = cand_of(i);
         cp_async_wait_all();
-        __syncthreads();          // tile c+1 landed, p3t[c] complete, buffers of phase c-1 released
-        fetch(c + 2);
-        if (c + 1 < prm.n_cand) interp_x(c + 1);
+        __syncthreads();          // tile i+1 landed, p3t[i] complete, buffers of phase i-1 released
+        fetch(i + 2);
+        if (i + 1 < n_live) interp_x(i + 1);
         // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
-        const float2* p3t = p3t0 + (c & 1) * CY * P3P;
+        const float2* p3t = p3t0 + (i & 1) * CY * P3P;
         const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1002,11 +1080,15 @@ static int check_common(const float* img, const double* wx_rows, const double* w
 // ---------------------------------------------------------------------------------------------
 // multirate host side
 // ---------------------------------------------------------------------------------------------
+static int g_prune_enabled = 1;
+
 struct MrGeometry {
     int N, M, S, Nd, Md, pitch_d, n_rows, n_planes, Rax, Ray, Rb, Jx, Jy, txd, warps2, n_alloc, n_rows_filled, n_cand;
-    size_t plane_stride, p2_stride;   // elements per plane
+    int nbx_alloc, nby_alloc, can_prune;
+    size_t plane_stride, p2_stride, pm_stride;   // elements per plane
     double *wx_d, *wy_d;
     float2 *phx, *phy, *p1, *p2;
+    float* pmax;
     int chunk;
 };
 
@@ -1030,6 +1112,10 @@ static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int ca
     g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
     g.n_cand = cand_mode == GPA_CAND_GRID ? n_rows : 1;
     g.p2_stride = (size_t)g.n_cand * g.Nd * g.Md;
+    g.nbx_alloc = ceil_div(g.Nd, g.txd) * (g.txd / kP);
+    g.nby_alloc = g.pitch_d / kLanes;
+    g.pm_stride = (size_t)g.n_cand * g.nbx_alloc * g.nby_alloc;
+    g.can_prune = g.Nd % kP == 0 && g.Md % kLanes == 0 && g.n_cand <= kMaxPruneCand;
     return GPA_OK;
 }
 
@@ -1041,13 +1127,14 @@ static size_t carve_mr(MrGeometry& g, void* ws, size_t ws_bytes, int chunk) {
     g.phy = a.take<float2>((size_t)g.n_planes * g.M);
     g.p1 = a.take<float2>((size_t)chunk * g.plane_stride);
     g.p2 = a.take<float2>((size_t)chunk * g.p2_stride);
+    g.pmax = a.take<float>((size_t)chunk * g.pm_stride);
     g.chunk = chunk;
     return a.off;
 }
 
 static int fit_chunk_mr(MrGeometry& g, void* ws, size_t ws_bytes, int want) {
     const size_t fixed = carve_mr(g, nullptr, 0, 0);
-    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + 512;
+    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + g.pm_stride * sizeof(float) + 1024;
     if (ws_bytes < fixed + per_plane + 512) return 0;
     size_t c = (ws_bytes - fixed - 512) / per_plane;
     const int chunk = (int)(c < (size_t)want ? c : (size_t)want);
@@ -1109,7 +1196,8 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
     }
     {   // stage 2
         MrPass2Params p;
-        p.p1 = g.p1; p.plane_stride = g.plane_stride; p.phx = g.phx; p.p2 = g.p2;
+        p.p1 = g.p1; p.plane_stride = g.plane_stride; p.phx = g.phx; p.p2 = g.p2; p.pmax = g.pmax;
+        p.nbx = g.nbx_alloc; p.nby = g.nby_alloc;
         p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = g.Jx; p.plane0 = plane0;
         p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.row_c = 1; p.row_p = 0; } else { p.row_c = 0; p.row_p = 1; }
@@ -1125,7 +1213,9 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
     }
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;
-        p.p2 = g.p2; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
+        p.p2 = g.p2; p.pmax = g.pmax; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
+        p.nbx = g.Nd / kP; p.nby = g.Md / kLanes; p.nbx_alloc = g.nbx_alloc; p.nby_alloc = g.nby_alloc; p.count = count;
+        p.prune = g.can_prune && g_prune_enabled;
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
         const size_t smem = (size_t)(2 * CX * CY + 2 * CY * (kMrTX + 1)) * sizeof(float2);
@@ -1147,6 +1237,11 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
 
 using namespace gpa;
 
+extern "C" int gpa_set_pruning(int on) {
+    g_prune_enabled = on != 0;
+    return GPA_OK;
+}
+
 extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax,
                                             int Ray, int Rb, int planes_in_flight, size_t* bytes) {
     MrGeometry g;
@@ -1154,7 +1249,7 @@ extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_plan
     if (rc) return rc;
     GPA_REQUIRE(bytes != nullptr, "bytes is null");
     GPA_REQUIRE(planes_in_flight >= 1 && planes_in_flight <= n_planes, "planes_in_flight out of range");
-    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 512 + 1024;
+    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 1024 + 2048;
     return GPA_OK;
 }
 

@@ -47,6 +47,11 @@ def workspace(nbytes, device):
     return ws
 
 
+def set_pruning(on):
+    """Toggle the exact branch-and-bound candidate pruning of the multirate arg-max (default on)."""
+    _lib.check(_lib.load().gpa_set_pruning(int(bool(on))))
+
+
 def release_workspaces():
     _workspaces.clear()
 

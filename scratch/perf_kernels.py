@@ -5,7 +5,10 @@ dev = engine.require_cuda(); lib = _lib.load()
 size, ng = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2048, 41)
 method = sys.argv[3] if len(sys.argv) > 3 else "auto"
 ks = synth.primary_ks(0.05, 7.0, 3); kw, kstep = synth.sweep_params(ks, ng)
-img = torch.from_numpy(np.random.default_rng(0).normal(size=(size, size)).astype(np.float32)).to(dev)
+if len(sys.argv) > 4 and sys.argv[4] == "noise":
+    img = torch.from_numpy(np.random.default_rng(0).normal(size=(size, size)).astype(np.float32)).to(dev)
+else:
+    img = engine.image_to_device(synth.make_config('C3', size=size, n_grid=ng)['image'], dev)
 k = ks[0]; wxs, wys = engine.grid_axes(k[0], k[1], kw, kstep)
 plan = engine.SweepPlan(img.shape, wxs, wys, 10, device=dev, method=method)
 for _ in range(3): plan.run(img, k)

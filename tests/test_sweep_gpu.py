@@ -115,6 +115,30 @@ def test_multirate_and_direct_forms_agree(shape, sigma, stride):
     assert torch.equal(chunked["key"], res["multirate"]["key"])
 
 
+def test_pruning_is_exact():
+    """Branch-and-bound pruning of the multirate arg-max must not change a single key bit, on a
+    structured frame (where it removes most candidates) and on pure noise (where it removes few)."""
+    dev = engine.require_cuda()
+    cfg = synth.make_config('C2', size=512)
+    noise = np.random.default_rng(0).normal(size=(512, 512))
+    for img in (cfg["image"], noise):
+        d_img = engine.image_to_device(img, dev)
+        for k in cfg["ks"][:2]:
+            wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+            plan = engine.SweepPlan(d_img.shape, wxs, wys, cfg["sigma"], device=dev, method="multirate")
+            try:
+                engine.set_pruning(False)
+                ref = plan.run(d_img, k)
+                engine.set_pruning(True)
+                got = plan.run(d_img, k)
+                again = plan.run(d_img, k)
+            finally:
+                engine.set_pruning(True)
+            assert torch.equal(ref["key"], got["key"]) and torch.equal(got["key"], again["key"])
+            assert torch.equal(torch.view_as_real(ref["lockin"]), torch.view_as_real(got["lockin"]))
+            assert torch.equal(ref["grad"], got["grad"])
+
+
 def test_many_rows_uses_wide_index_packing():
     """More than 256 candidate rows per plane switches the packed winner index from 8 to 16 bits."""
     shape = (96, 128)
