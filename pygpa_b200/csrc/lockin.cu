@@ -281,6 +281,7 @@ constexpr int kMrW = 12;      // coarse taps per output (11 used, padded to 12)
 constexpr int kMrHL = 5;      // coarse samples to the left of an output's own cell
 constexpr int kMrTX = 64;     // k_mr_interp tile: rows
 constexpr int kMrTY = 128;    //                   columns
+constexpr int kPmB = 8;       // bound blocks for the pruning: kPmB x kPmB coarse cells
 
 struct MrPass1Params {
     const float* img;
@@ -367,7 +368,7 @@ struct MrPass2Params {
     size_t plane_stride;
     const float2* phx;     // [n_rows][n_alloc], padded-row carrier
     float2* p2;            // [chunk][n_cand][Nd][Md]
-    float* pmax;           // [chunk][n_cand][nbx][nby]: max |P2|^2 over blocks of 16 x 32 coarse cells
+    float* pmax;           // [chunk][n_cand][nbx][nby]: max |P2|^2 over blocks of kPmB x kPmB coarse cells
     int Nd, Md, pitch_d, n_alloc, J, plane0, n_cand, row_c, row_p, nbx, nby;   // nbx, nby: ALLOCATED block grid
 };
 
@@ -419,22 +420,28 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
             fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(colq[j * (S * kLanes)], phq[j * S]); });
         }
         float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * prm.Nd * prm.Md;
-        float a2max = 0.f;
+        float a2max[kP / kPmB];
+#pragma unroll
+        for (int hb = 0; hb < kP / kPmB; ++hb) a2max[hb] = 0.f;
         if (my < prm.Md) {
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const int mx = mx0 + warp * kP + p;
                 if (mx < prm.Nd) {
                     out[(size_t)mx * prm.Md + my] = acc[p];
-                    a2max = fmaxf(a2max, fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y));
+                    a2max[p / kPmB] = fmaxf(a2max[p / kPmB], fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y));
                 }
             }
         }
-        // block maximum for the interpolation kernel's branch-and-bound (a warp = 16 x 32 coarse cells)
+        // block maxima (kPmB x kPmB coarse cells) for the interpolation kernel's branch and bound
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a2max = fmaxf(a2max, __shfl_xor_sync(0xffffffffu, a2max, o));
-        if (lane == 0)
-            prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + (mx0 / kP + warp)) * prm.nby + blockIdx.x] = a2max;
+        for (int hb = 0; hb < kP / kPmB; ++hb) {
+#pragma unroll
+            for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
+            if ((lane & (kPmB - 1)) == 0)
+                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
+                         (my0 + lane) / kPmB] = a2max[hb];
+        }
         group_sync();     // this group's next carrier is complete; the current one is no longer read
     }
 }
@@ -462,11 +469,51 @@ __device__ __forceinline__ void interp_block(float2 (&acc)[Q], const float2 (&sm
 struct MrInterpParams {
     const float2* p2;      // [chunk][n_cand][Nd][Md]
     const float* pmax;     // [chunk][n_cand][nbx][nby] block maxima of |P2|^2 (k_mr_pass2)
+    const unsigned short* perm;   // [tiles][count] plane order per tile (k_mr_order); used when prune != 0
     unsigned long long* key;
     int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p, nbx, nby, nbx_alloc, nby_alloc, count, prune;   // nbx, nby: logical (wrap) block grid
 };
 
 constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor list can hold
+
+// Per tile of k_mr_interp: order the planes of the chunk by how large their best candidate can get
+// inside the tile (max over candidates and over the tile's coarse-window blocks of pmax), most
+// promising first.  CTA (tile, z) of k_mr_interp then handles plane perm[tile][z], so the z = 0 wave
+// already records near-final winners in `key` and every later CTA prunes against tight thresholds.
+template <int S>
+__global__ void __launch_bounds__(64) k_mr_order(const float* __restrict__ pmax, int n_cand, int count, int nbx, int nby,
+                                                 int nbx_alloc, int nby_alloc, unsigned short* __restrict__ perm) {
+    constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
+    __shared__ float bound[256];
+    const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
+    const int bx0 = (r_lo >= 0 ? r_lo : r_lo - (kPmB - 1)) / kPmB, bx1 = (r_lo + CX - 1 >= 0 ? r_lo + CX - 1 : r_lo + CX - kPmB) / kPmB;
+    const int by0 = (c_lo >= 0 ? c_lo : c_lo - (kPmB - 1)) / kPmB, by1 = (c_lo + CY - 1 >= 0 ? c_lo + CY - 1 : c_lo + CY - kPmB) / kPmB;
+    for (int pl = threadIdx.x; pl < count; pl += blockDim.x) {
+        float m = 0.f;
+        for (int c = 0; c < n_cand; ++c) {
+            const float* __restrict__ pm = pmax + ((size_t)pl * n_cand + c) * nbx_alloc * nby_alloc;
+            for (int bx = bx0; bx <= bx1; ++bx) {
+                int wx = bx % nbx;
+                if (wx < 0) wx += nbx;
+                for (int by = by0; by <= by1; ++by) {
+                    int wy = by % nby;
+                    if (wy < 0) wy += nby;
+                    m = fmaxf(m, __ldg(pm + wx * nby_alloc + wy));
+                }
+            }
+        }
+        bound[pl] = m;
+    }
+    __syncthreads();
+    for (int pl = threadIdx.x; pl < count; pl += blockDim.x) {
+        const float b = bound[pl];
+        int rank = 0;
+        for (int q = 0; q < count; ++q) rank += (bound[q] > b) || (bound[q] == b && q < pl);
+        perm[(size_t)tile * count + rank] = (unsigned short)pl;
+    }
+}
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -497,61 +544,88 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     float2* const p3t0 = smem + 2 * CX * CY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
-    // planes are visited centre-out (blockIdx.z = 0 is the middle plane of the chunk): the planes
-    // nearest the nominal k-vector usually hold the winners, so later CTAs find high thresholds
-    const int zz = blockIdx.z, mid = (prm.count - 1) >> 1;
-    const int pl = (zz & 1) ? mid + ((zz + 1) >> 1) : mid - (zz >> 1);
+    // with pruning every tile visits the planes in its own order, most promising first (k_mr_order)
+    const int pl = prm.prune ? (int)prm.perm[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * prm.count + blockIdx.z]
+                             : (int)blockIdx.z;
     const int plane = prm.plane0 + pl;
     const int Nd = prm.Nd, Md = prm.Md;
     // ---- branch and bound: a candidate whose |P2|^2 block maxima over this tile's coarse window
     // stay below the smallest winning |sf|^2 already recorded for the tile's pixels cannot win
     // anywhere in the tile (the interpolation taps are non-negative and sum to <= 1), so it is
     // dropped before any work is spent on it.  The thresholds come from `key`, which only grows.
-    __shared__ float s_thr[8];
+    constexpr int SBX = kMrTX / S / kPmB, SBY = kMrTY / S / kPmB;   // bound blocks inside the tile (2 x 4 at S = 4)
+    static_assert(SBX >= 1 && SBY >= 1 && kMrTX / S % kPmB == 0 && kMrTY / S % kPmB == 0, "tile must hold whole bound blocks");
+    static_assert(kMrHL <= kPmB, "the interpolation halo must stay within one neighbouring bound block");
+    __shared__ float s_thr[2][8];
     __shared__ int s_cnt;
     __shared__ unsigned short s_list[kMaxPruneCand];
     int n_live = prm.n_cand;
     const bool prune = prm.prune != 0;
     if (prune) {
-        float tmin = 3.4e38f;
+        // smallest recorded winner per (row half h, warp column block): thread = (x = lane + 32 h, 16 columns of `warp`)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            float tmin = 3.4e38f;
             const int x = x0 + lane + 32 * h;
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const int y = y0 + warp * kP + p;
                 if (x < prm.N && y < prm.M) tmin = fminf(tmin, __uint_as_float((unsigned)(prm.key[(size_t)x * prm.M + y] >> 32)));
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-        if (lane == 0) s_thr[warp] = tmin;
+            for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+            if (lane == 0) s_thr[h][warp] = tmin;
+        }
         __syncthreads();
         if (warp == 0) {
-            float thr = s_thr[0];
+            // thresholds per bound block of the tile (pixels 32 h .. 32 h + 31  <->  kPmB coarse rows when S = 4, ...)
+            float thr[SBX][SBY];
 #pragma unroll
-            for (int i = 1; i < 8; ++i) thr = fminf(thr, s_thr[i]);
-            // coarse window of the tile: rows [x0/S - HL, +CX), columns [y0/S - HL, +CY); blocks of 16 x 32
-            const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
-            const int bx0 = (r_lo >= 0 ? r_lo : r_lo - 15) / 16, bx1 = (r_lo + CX - 1 >= 0 ? r_lo + CX - 1 : r_lo + CX - 16) / 16;
-            const int by0 = (c_lo >= 0 ? c_lo : c_lo - 31) / 32, by1 = (c_lo + CY - 1 >= 0 ? c_lo + CY - 1 : c_lo + CY - 32) / 32;
+            for (int i = 0; i < SBX; ++i)
+#pragma unroll
+                for (int j = 0; j < SBY; ++j) {
+                    float t = 3.4e38f;
+                    // pixel rows of block i: [i kPmB S, (i+1) kPmB S) -> halves h; pixel columns -> warps of 16 columns
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const bool rows = (32 * h) / (kPmB * S) <= i && i <= (32 * h + 31) / (kPmB * S);
+                            const bool cols = (16 * w) / (kPmB * S) <= j && j <= (16 * w + 15) / (kPmB * S);
+                            if (rows && cols) t = fminf(t, s_thr[h][w]);
+                        }
+                    thr[i][j] = t;
+                }
+            const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;      // window: one block around the tile's blocks
             int cnt = 0;
             for (int base = 0; base < prm.n_cand; base += 32) {
                 const int c = base + lane;
                 bool keep = false;
                 if (c < prm.n_cand) {
                     const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
-                    float m = 0.f;
-                    for (int bx = bx0; bx <= bx1; ++bx) {
-                        int wx = bx % prm.nbx;
+                    float m[SBX + 2][SBY + 2];
+#pragma unroll
+                    for (int i = 0; i < SBX + 2; ++i) {
+                        int wx = (bx0 + i) % prm.nbx;
                         if (wx < 0) wx += prm.nbx;
-                        for (int by = by0; by <= by1; ++by) {
-                            int wy = by % prm.nby;
+#pragma unroll
+                        for (int j = 0; j < SBY + 2; ++j) {
+                            int wy = (by0 + j) % prm.nby;
                             if (wy < 0) wy += prm.nby;
-                            m = fmaxf(m, __ldg(pm + wx * prm.nby_alloc + wy));
+                            m[i][j] = __ldg(pm + wx * prm.nby_alloc + wy);
                         }
                     }
-                    keep = !(m * 1.0002f < thr);
+#pragma unroll
+                    for (int i = 0; i < SBX; ++i)
+#pragma unroll
+                        for (int j = 0; j < SBY; ++j) {
+                            float mm = 0.f;
+#pragma unroll
+                            for (int di = 0; di < 3; ++di)
+#pragma unroll
+                                for (int dj = 0; dj < 3; ++dj) mm = fmaxf(mm, m[i + di][j + dj]);
+                            keep = keep || !(mm * 1.0002f < thr[i][j]);
+                        }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)c;
@@ -1089,6 +1163,7 @@ struct MrGeometry {
     double *wx_d, *wy_d;
     float2 *phx, *phy, *p1, *p2;
     float* pmax;
+    unsigned short* perm;
     int chunk;
 };
 
@@ -1112,10 +1187,10 @@ static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int ca
     g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
     g.n_cand = cand_mode == GPA_CAND_GRID ? n_rows : 1;
     g.p2_stride = (size_t)g.n_cand * g.Nd * g.Md;
-    g.nbx_alloc = ceil_div(g.Nd, g.txd) * (g.txd / kP);
-    g.nby_alloc = g.pitch_d / kLanes;
+    g.nbx_alloc = ceil_div(g.Nd, g.txd) * (g.txd / kPmB);
+    g.nby_alloc = g.pitch_d / kPmB;
     g.pm_stride = (size_t)g.n_cand * g.nbx_alloc * g.nby_alloc;
-    g.can_prune = g.Nd % kP == 0 && g.Md % kLanes == 0 && g.n_cand <= kMaxPruneCand;
+    g.can_prune = g.Nd % kPmB == 0 && g.Md % kPmB == 0 && g.n_cand <= kMaxPruneCand && g.n_planes <= 256;
     return GPA_OK;
 }
 
@@ -1128,13 +1203,15 @@ static size_t carve_mr(MrGeometry& g, void* ws, size_t ws_bytes, int chunk) {
     g.p1 = a.take<float2>((size_t)chunk * g.plane_stride);
     g.p2 = a.take<float2>((size_t)chunk * g.p2_stride);
     g.pmax = a.take<float>((size_t)chunk * g.pm_stride);
+    g.perm = a.take<unsigned short>((size_t)chunk * ceil_div(g.N, kMrTX) * ceil_div(g.M, kMrTY));
     g.chunk = chunk;
     return a.off;
 }
 
 static int fit_chunk_mr(MrGeometry& g, void* ws, size_t ws_bytes, int want) {
     const size_t fixed = carve_mr(g, nullptr, 0, 0);
-    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + g.pm_stride * sizeof(float) + 1024;
+    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + g.pm_stride * sizeof(float) +
+                             (size_t)ceil_div(g.N, kMrTX) * ceil_div(g.M, kMrTY) * sizeof(unsigned short) + 1024;
     if (ws_bytes < fixed + per_plane + 512) return 0;
     size_t c = (ws_bytes - fixed - 512) / per_plane;
     const int chunk = (int)(c < (size_t)want ? c : (size_t)want);
@@ -1214,8 +1291,14 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;
         p.p2 = g.p2; p.pmax = g.pmax; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
-        p.nbx = g.Nd / kP; p.nby = g.Md / kLanes; p.nbx_alloc = g.nbx_alloc; p.nby_alloc = g.nby_alloc; p.count = count;
+        p.nbx = g.Nd / kPmB; p.nby = g.Md / kPmB; p.nbx_alloc = g.nbx_alloc; p.nby_alloc = g.nby_alloc; p.count = count;
         p.prune = g.can_prune && g_prune_enabled;
+        p.perm = g.perm;
+        if (p.prune) {
+            dim3 tg(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX));
+            KernelTimer timer("k_mr_order", st);
+            k_mr_order<S><<<tg, 64, 0, st>>>(g.pmax, g.n_cand, count, p.nbx, p.nby, g.nbx_alloc, g.nby_alloc, g.perm);
+        }
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
         const size_t smem = (size_t)(2 * CX * CY + 2 * CY * (kMrTX + 1)) * sizeof(float2);
