@@ -61,6 +61,11 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
         sigma_a = float(np.sqrt(sigma ** 2 - sigma_b ** 2))
         rb = int(np.ceil(trunc * sigma_b))
         ra = int(np.ceil(trunc * sigma_a))
+        # the decimating pass has statically scheduled kernels for an EVEN number of taps per phase:
+        # round the filter length up to the next such size and spend the extra taps (at most one per
+        # phase) on a slightly larger truncation radius
+        jt = 2 * (-(-(-(-(2 * ra + 1) // s)) // 2))
+        ra = max(ra, (s * jt - 1) // 2)
         if rb > MR_HL * s:
             continue
         if 2 * ra + 1 > min(n, m) or s * (-(-(2 * ra + 1) // s)) + 2 > MAX_TAPS:

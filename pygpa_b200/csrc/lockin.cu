@@ -446,6 +446,85 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     }
 }
 
+// Statically scheduled variant of k_mr_pass2 for JT taps per phase (JT a compile-time multiple of 4):
+// the JT tap pairs of a phase sit in uniform registers, every sample is demodulated once and applied
+// to all the outputs it reaches with compile-time tap / accumulator indices — no rotating window, no
+// register moves, no tail branches.  acc[p] += g_q[k - p] * sample_q[k], 0 <= k - p < JT.
+template <int S, int WARPS, int GROUPS, int JT>
+__global__ void __launch_bounds__(GROUPS * WARPS * 32, 1)
+k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    constexpr int GT = WARPS * 32;
+    const int group = threadIdx.x / GT, tig = threadIdx.x % GT;
+    const int lane = tig & 31, warp = tig >> 5;
+    const int my0 = blockIdx.x * kLanes;
+    const int mx0 = blockIdx.y * (WARPS * kP);
+    const int pl = blockIdx.z;
+    const int plane = prm.plane0 + pl;
+    constexpr int n_samp = S * (WARPS * kP + JT);
+    {
+        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
+        for (int j = threadIdx.x >> 5; j < n_samp; j += GROUPS * WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
+    }
+    const float2* col = smem + (S * warp * kP) * kLanes + lane;
+    const int my = my0 + lane;
+    float2* const sph = smem + (size_t)n_samp * kLanes + (size_t)group * 2 * n_samp;     // [2][n_samp]
+    auto stage_carrier = [&](int c, int slot) {
+        const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * mx0;
+        float2* dst = sph + slot * n_samp;
+        for (int j = tig; j < n_samp; j += GT) dst[j] = __ldg(ph + j);
+    };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory"); };
+    if (group < prm.n_cand) stage_carrier(group, 0);
+    __syncthreads();
+    int slot = 0;
+    for (int c = group; c < prm.n_cand; c += GROUPS, slot ^= 1) {
+        if (c + GROUPS < prm.n_cand) stage_carrier(c + GROUPS, slot ^ 1);
+        const float2* ph = sph + slot * n_samp + S * warp * kP;
+        float2 acc[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int q = 0; q < S; ++q) {
+            const float2* colq = col + q * kLanes;
+            const float2* phq = ph + q;
+            float2 g[JT];
+#pragma unroll
+            for (int j = 0; j < JT; ++j) g[j] = taps.g[q * JT + j];
+#pragma unroll
+            for (int k = 0; k < kP + JT - 1; ++k) {
+                const float2 smp = cmul(colq[k * (S * kLanes)], phq[k * S]);
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+                    if (k - p >= 0 && k - p < JT) acc[p] = __ffma2_rn(g[k - p], smp, acc[p]);
+            }
+        }
+        float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * prm.Nd * prm.Md;
+        float a2max[kP / kPmB];
+#pragma unroll
+        for (int hb = 0; hb < kP / kPmB; ++hb) a2max[hb] = 0.f;
+        if (my < prm.Md) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int mx = mx0 + warp * kP + p;
+                if (mx < prm.Nd) {
+                    out[(size_t)mx * prm.Md + my] = acc[p];
+                    a2max[p / kPmB] = fmaxf(a2max[p / kPmB], fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y));
+                }
+            }
+        }
+#pragma unroll
+        for (int hb = 0; hb < kP / kPmB; ++hb) {
+#pragma unroll
+            for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
+            if ((lane & (kPmB - 1)) == 0)
+                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
+                         (my0 + lane) / kPmB] = a2max[hb];
+        }
+        group_sync();
+    }
+}
+
 // 16 consecutive fine outputs from kP/S + kMrW - 1 coarse samples; tb[phi * kMrW + w] are the
 // interpolation taps (S G_b(phi + S (HL - w)), zero outside the truncation radius)
 template <int S, int Q>
@@ -1286,7 +1365,26 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2<S, W2, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, W2 * kP), count);
         KernelTimer timer("k_mr_pass2", st);
-        k_mr_pass2<S, W2, G2><<<grid, G2 * W2 * 32, smem, st>>>(p, tx);
+        bool launched = false;
+        if constexpr (S >= 4) {   // statically scheduled variant for the common filter lengths (even taps per phase)
+            const size_t ns = (size_t)S * (W2 * kP + g.Jx);
+            const size_t smem_s = ns * (kLanes + 2 * G2) * sizeof(float2);
+#define GPA_P2S(JTV)                                                                                                   \
+    case JTV:                                                                                                          \
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2s<S, W2, G2, JTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            227 * 1024));                                                              \
+        k_mr_pass2s<S, W2, G2, JTV><<<grid, G2 * W2 * 32, smem_s, st>>>(p, tx);                                        \
+        launched = true;                                                                                               \
+        break;
+            if (smem_s <= 227 * 1024) {
+                switch (g.Jx) {
+                    GPA_P2S(18) GPA_P2S(20) GPA_P2S(22) GPA_P2S(24) GPA_P2S(26) GPA_P2S(28) GPA_P2S(30) GPA_P2S(32)
+                    default: break;
+                }
+            }
+#undef GPA_P2S
+        }
+        if (!launched) k_mr_pass2<S, W2, G2><<<grid, G2 * W2 * 32, smem, st>>>(p, tx);
     }
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;

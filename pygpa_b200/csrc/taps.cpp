@@ -59,7 +59,13 @@ extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, d
         if (c > 1.1) c = 1.1;
         if (c < 1.0) continue;
         const double sb = c * s, sa = std::sqrt(sigma * sigma - sb * sb);
-        const int rb = (int)std::ceil(trunc * sb), ra = (int)std::ceil(trunc * sa);
+        const int rb = (int)std::ceil(trunc * sb);
+        int ra = (int)std::ceil(trunc * sa);
+        {   // even number of taps per phase (statically scheduled pass-2 kernels); extra taps widen the radius
+            const int j0 = (2 * ra + 1 + s - 1) / s, jt = 2 * ((j0 + 1) / 2);
+            const int ra2 = (s * jt - 1) / 2;
+            if (ra2 > ra) ra = ra2;
+        }
         if (rb > 5 * s) continue;
         if (2 * ra + 1 > (N < M ? N : M) || s * ((2 * ra + 1 + s - 1) / s) + 2 > 446) continue;
         if (sigma_a) *sigma_a = sa;

@@ -62,7 +62,7 @@ def merge_payload(tensors, group=None):
     return tensors
 
 
-def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
+def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None, seed_center=True):
     """All peaks of one frame, k-grid sharded over the ranks of `group`.
     plans: one engine.SweepPlan per peak (identical on every rank; give them private workspaces so
     the finalize reuses what the arg-max left and stays bit-identical to one GPU).
@@ -84,6 +84,13 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     keys = torch.zeros((n_peaks, n, m), dtype=torch.int64, device=dev)
     for p, (plan, (lo, hi)) in enumerate(zip(plans, ranges)):
         if hi > lo:
+            # Seed the keys with the centre plane (the one most likely to hold winners) when it is not
+            # part of this rank's share: the exact pruning of the multirate arg-max works against the
+            # winners recorded so far, and a rank that only owns outlying planes would otherwise prune
+            # almost nothing.  Costs 1/n_planes of redundant work; max-merging duplicates is harmless.
+            mid = plan.wy.size // 2
+            if plan.mr is not None and seed_center and not (lo <= mid < hi):
+                plan.argmax(img_dev, keys[p], mid, mid + 1)
             plan.argmax(img_dev, keys[p], lo, hi)
     dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
     want_grad = grad_mode != 2
