@@ -136,7 +136,10 @@ int gpa_sweep_argmax(const float* img, int N, int M,
  * strides the host chooses (pygpa_b200/_taps.py), far inside the near-tie budget.  Only the
  * arg-max decision uses these amplitudes: gpa_sweep_finalize recomputes the winner in the direct
  * form.  taps_a*: decimation filter (2 Ra + 1 taps per axis); taps_b*: interpolation filter
- * (2 Rb + 1 taps, not yet multiplied by the stride).  N and M must be multiples of stride. */
+ * (2 Rb + 1 taps, not yet multiplied by the stride).  N and M must be multiples of stride.
+ * The call covers planes plane_begin, plane_begin + plane_step, ... < plane_end: an interleaved
+ * share (plane_step = number of ranks) gives every rank planes near the centre of the grid, which
+ * keeps the exact pruning effective when the k-grid is sharded. */
 /* The multirate arg-max drops, per 64 x 128 pixel tile, every candidate whose coarse-grid amplitude
  * bound cannot beat the winners already recorded in `key` (exact branch and bound: results are
  * bit-identical with it on or off; it only changes how much work is done).  On by default. */
@@ -147,7 +150,7 @@ int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int can
 int gpa_sweep_argmax_mr(const float* img, int N, int M,
                         const double* wx_rows /*host*/, int n_rows,
                         const double* wy_planes /*host*/, int n_planes, int cand_mode,
-                        int plane_begin, int plane_end, int stride,
+                        int plane_begin, int plane_end, int plane_step, int stride,
                         const float* taps_ax /*host*/, int Rax, const float* taps_ay /*host*/, int Ray,
                         const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
                         unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
@@ -158,7 +161,7 @@ int gpa_sweep_argmax_mr(const float* img, int N, int M,
  * and conventions as gpa_sweep_finalize.  Returns GPA_ERR_WORKSPACE if the range was chunked. */
 int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows /*host*/, int n_rows,
                           const double* wy_planes /*host*/, int n_planes, int cand_mode,
-                          int plane_begin, int plane_end, int stride, int Rax, int Ray,
+                          int plane_begin, int plane_end, int plane_step, int stride, int Rax, int Ray,
                           const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
                           const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
                           int out_f64, void* lockin, void* grad, void* w, int* kidx,

@@ -288,7 +288,7 @@ struct MrPass1Params {
     const float2* phy;
     float2* p1;            // [chunk][n_alloc][pitch_d]
     size_t plane_stride;
-    int N, M, Md, pitch_d, n_rows_filled, Rax, Ray, J /* taps per phase */, plane0, count, planes_per_cta;
+    int N, M, Md, pitch_d, n_rows_filled, Rax, Ray, J /* taps per phase */, plane0, pstep, count, planes_per_cta;
 };
 
 // decimating version of k_pass1: lane = padded row, warp w owns decimated outputs [w*P, w*P+P).
@@ -322,7 +322,7 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
     const int pl0 = blockIdx.z * prm.planes_per_cta;
     const int pl1 = min(pl0 + prm.planes_per_cta, prm.count);
     auto stage_carrier = [&](int pl, int slot) {
-        const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl) * M;
+        const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl * prm.pstep) * M;
         float2* dst = car + slot * n_samp;
         for (int j = threadIdx.x; j < n_samp; j += WARPS * 32) {
             int c = cbase + j;
@@ -369,7 +369,7 @@ struct MrPass2Params {
     const float2* phx;     // [n_rows][n_alloc], padded-row carrier
     float2* p2;            // [chunk][n_cand][Nd][Md]
     float* pmax;           // [chunk][n_cand][nbx][nby]: max |P2|^2 over blocks of kPmB x kPmB coarse cells
-    int Nd, Md, pitch_d, n_alloc, J, plane0, n_cand, row_c, row_p, nbx, nby;   // nbx, nby: ALLOCATED block grid
+    int Nd, Md, pitch_d, n_alloc, J, plane0, pstep, n_cand, row_c, row_p, nbx, nby;   // nbx, nby: ALLOCATED block grid
 };
 
 // decimating version of k_pass2: lane = decimated column, warp w owns decimated rows [w*P, w*P+P);
@@ -387,7 +387,7 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     const int my0 = blockIdx.x * kLanes;
     const int mx0 = blockIdx.y * (WARPS * kP);
     const int pl = blockIdx.z;
-    const int plane = prm.plane0 + pl;
+    const int plane = prm.plane0 + pl * prm.pstep;
     const int J = prm.J;
     const int n_samp = S * (WARPS * kP + J + kAhead + 1);
     {
@@ -460,7 +460,7 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     const int my0 = blockIdx.x * kLanes;
     const int mx0 = blockIdx.y * (WARPS * kP);
     const int pl = blockIdx.z;
-    const int plane = prm.plane0 + pl;
+    const int plane = prm.plane0 + pl * prm.pstep;
     constexpr int n_samp = S * (WARPS * kP + JT);
     {
         const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
@@ -550,7 +550,7 @@ struct MrInterpParams {
     const float* pmax;     // [chunk][n_cand][nbx][nby] block maxima of |P2|^2 (k_mr_pass2)
     const unsigned short* perm;   // [tiles][count] plane order per tile (k_mr_order); used when prune != 0
     unsigned long long* key;
-    int N, M, Nd, Md, plane0, n_cand, idx_c, idx_p, nbx, nby, nbx_alloc, nby_alloc, count, prune;   // nbx, nby: logical (wrap) block grid
+    int N, M, Nd, Md, plane0, pstep, n_cand, idx_c, idx_p, nbx, nby, nbx_alloc, nby_alloc, count, prune;   // nbx, nby: logical (wrap) block grid
 };
 
 constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor list can hold
@@ -560,18 +560,20 @@ constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor 
 // promising first.  CTA (tile, z) of k_mr_interp then handles plane perm[tile][z], so the z = 0 wave
 // already records near-final winners in `key` and every later CTA prunes against tight thresholds.
 template <int S>
-__global__ void __launch_bounds__(64) k_mr_order(const float* __restrict__ pmax, int n_cand, int count, int nbx, int nby,
-                                                 int nbx_alloc, int nby_alloc, unsigned short* __restrict__ perm) {
+__global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax, int n_cand, int count, int nbx, int nby,
+                                                  int nbx_alloc, int nby_alloc, unsigned short* __restrict__ perm) {
     constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
     __shared__ float bound[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
     const int bx0 = (r_lo >= 0 ? r_lo : r_lo - (kPmB - 1)) / kPmB, bx1 = (r_lo + CX - 1 >= 0 ? r_lo + CX - 1 : r_lo + CX - kPmB) / kPmB;
     const int by0 = (c_lo >= 0 ? c_lo : c_lo - (kPmB - 1)) / kPmB, by1 = (c_lo + CY - 1 >= 0 ? c_lo + CY - 1 : c_lo + CY - kPmB) / kPmB;
-    for (int pl = threadIdx.x; pl < count; pl += blockDim.x) {
+    // one warp per plane, lanes over candidates
+    for (int pl = warp; pl < count; pl += 8) {
         float m = 0.f;
-        for (int c = 0; c < n_cand; ++c) {
+        for (int c = lane; c < n_cand; c += 32) {
             const float* __restrict__ pm = pmax + ((size_t)pl * n_cand + c) * nbx_alloc * nby_alloc;
             for (int bx = bx0; bx <= bx1; ++bx) {
                 int wx = bx % nbx;
@@ -583,7 +585,9 @@ __global__ void __launch_bounds__(64) k_mr_order(const float* __restrict__ pmax,
                 }
             }
         }
-        bound[pl] = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) bound[pl] = m;
     }
     __syncthreads();
     for (int pl = threadIdx.x; pl < count; pl += blockDim.x) {
@@ -626,7 +630,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     // with pruning every tile visits the planes in its own order, most promising first (k_mr_order)
     const int pl = prm.prune ? (int)prm.perm[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * prm.count + blockIdx.z]
                              : (int)blockIdx.z;
-    const int plane = prm.plane0 + pl;
+    const int plane = prm.plane0 + pl * prm.pstep;
     const int Nd = prm.Nd, Md = prm.Md;
     // ---- branch and bound: a candidate whose |P2|^2 block maxima over this tile's coarse window
     // stay below the smallest winning |sf|^2 already recorded for the tile's pixels cannot win
@@ -996,7 +1000,7 @@ k_finalize(const FinalizeParams prm, const __grid_constant__ TapTable taps) {
 struct MrFinalizeParams {
     FinalizeParams f;      // planes / phx unused
     const float2* p2;      // [chunk][n_cand][Nd][Md]
-    int Nd, Md, n_cand, S;
+    int Nd, Md, n_cand, S, pstep;
 };
 
 template <int S, typename T2>
@@ -1035,9 +1039,9 @@ k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) 
         row = (int)(idx / (unsigned)prm.n_planes);
         cand = row;
     }
-    if (plane < prm.plane_begin || plane >= prm.plane_end) return;
+    if (plane < prm.plane_begin || plane >= prm.plane_end || (plane - prm.plane_begin) % mp.pstep != 0) return;
     const int Nd = mp.Nd, Md = mp.Md;
-    const float2* __restrict__ P = mp.p2 + ((size_t)(plane - prm.plane0) * mp.n_cand + cand) * Nd * Md;
+    const float2* __restrict__ P = mp.p2 + ((size_t)((plane - prm.plane0) / mp.pstep) * mp.n_cand + cand) * Nd * Md;
     // Fine positions x-1, x, x+1 and y-1, y, y+1 in UNWRAPPED coordinates (the coarse grid is circular
     // like the frame; the reference never uses the values beyond the frame edge, they are ignored).
     // The three positions span at most two adjacent coarse cells, so a 12 x 12 coarse window holds
@@ -1330,12 +1334,12 @@ static int fill_interp(TapTable& t, const float* bx, const float* by, int Rb, in
 
 template <int S>
 static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, const TapTable& tx, const TapTable& tb,
-                     int plane0, int count, int cand_mode, unsigned long long* key, cudaStream_t st) {
+                     int plane0, int pstep, int count, int cand_mode, unsigned long long* key, cudaStream_t st) {
     {   // stage 1
         MrPass1Params p;
         p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
         p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
-        p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0;
+        p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0; p.pstep = pstep;
         constexpr int W1 = 8;
         const size_t n_samp1 = (size_t)S * (W1 * kP + g.Jy + kAhead + 1);
         const size_t smem = (n_samp1 * 33 + 1) * sizeof(float) + 2 * n_samp1 * sizeof(float2);
@@ -1354,7 +1358,7 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         MrPass2Params p;
         p.p1 = g.p1; p.plane_stride = g.plane_stride; p.phx = g.phx; p.p2 = g.p2; p.pmax = g.pmax;
         p.nbx = g.nbx_alloc; p.nby = g.nby_alloc;
-        p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = g.Jx; p.plane0 = plane0;
+        p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = g.Jx; p.plane0 = plane0; p.pstep = pstep;
         p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.row_c = 1; p.row_p = 0; } else { p.row_c = 0; p.row_p = 1; }
         constexpr int W2 = S == 8 ? 4 : 8;
@@ -1388,14 +1392,14 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
     }
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;
-        p.p2 = g.p2; p.pmax = g.pmax; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.n_cand = g.n_cand;
+        p.p2 = g.p2; p.pmax = g.pmax; p.key = key; p.N = g.N; p.M = g.M; p.Nd = g.Nd; p.Md = g.Md; p.plane0 = plane0; p.pstep = pstep; p.n_cand = g.n_cand;
         p.nbx = g.Nd / kPmB; p.nby = g.Md / kPmB; p.nbx_alloc = g.nbx_alloc; p.nby_alloc = g.nby_alloc; p.count = count;
         p.prune = g.can_prune && g_prune_enabled;
         p.perm = g.perm;
         if (p.prune) {
             dim3 tg(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX));
             KernelTimer timer("k_mr_order", st);
-            k_mr_order<S><<<tg, 64, 0, st>>>(g.pmax, g.n_cand, count, p.nbx, p.nby, g.nbx_alloc, g.nby_alloc, g.perm);
+            k_mr_order<S><<<tg, 256, 0, st>>>(g.pmax, g.n_cand, count, p.nbx, p.nby, g.nbx_alloc, g.nby_alloc, g.perm);
         }
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
@@ -1436,7 +1440,7 @@ extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_plan
 
 extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double* wx_rows, int n_rows,
                                    const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
-                                   int plane_end, int S, const float* taps_ax, int Rax, const float* taps_ay, int Ray,
+                                   int plane_end, int plane_step, int S, const float* taps_ax, int Rax, const float* taps_ay, int Ray,
                                    const float* taps_bx, const float* taps_by, int Rb, unsigned long long* key,
                                    void* ws, size_t ws_bytes, void* stream) {
     MrGeometry g;
@@ -1444,8 +1448,10 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
     if (rc) return rc;
     if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
     GPA_REQUIRE(key != nullptr, "key is null");
+    GPA_REQUIRE(plane_step >= 1, "plane_step must be >= 1");
     if (plane_begin == plane_end) return GPA_OK;
-    const int chunk = fit_chunk_mr(g, ws, ws_bytes, plane_end - plane_begin);
+    const int total = ceil_div(plane_end - plane_begin, plane_step);     // planes begin, begin+step, ... < end
+    const int chunk = fit_chunk_mr(g, ws, ws_bytes, total);
     if (chunk < 1) {
         set_error("workspace too small (%zu bytes)", ws_bytes);
         return GPA_ERR_WORKSPACE;
@@ -1461,11 +1467,12 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
         t.wx_d = g.wx_d; t.wy_d = g.wy_d; t.phx = g.phx; t.phy = g.phy;
         if ((rc = build_tables(t, wx_rows, wy_planes, st))) return rc;
     }
-    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
-        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
-        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
-        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
-        else rc = launch_mr<8>(g, img, ty, tx, tb, p0, cnt, cand_mode, key, st);
+    for (int i0 = 0; i0 < total; i0 += chunk) {
+        const int cnt = total - i0 < chunk ? total - i0 : chunk;
+        const int p0 = plane_begin + i0 * plane_step;
+        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
+        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
+        else rc = launch_mr<8>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
         if (rc) return rc;
     }
     return GPA_OK;
@@ -1474,8 +1481,8 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
 // Finalize from the coarse grids left in the workspace by gpa_sweep_argmax_mr.  Requires that call to
 // have covered exactly [plane_begin, plane_end) with all its planes resident (same ws, same arguments).
 extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
-                                     int n_planes, int cand_mode, int plane_begin, int plane_end, int S, int Rax,
-                                     int Ray, const float* taps_bx, const float* taps_by, int Rb,
+                                     int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
+                                     int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
                                      const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
                                      int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
                                      size_t ws_bytes, void* stream) {
@@ -1487,11 +1494,12 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
     GPA_REQUIRE(grad_mode == GPA_GRAD_CENTRAL || grad_mode == GPA_GRAD_FORWARD || grad_mode == GPA_GRAD_NONE,
                 "bad grad_mode %d", grad_mode);
     GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr, "grad is null but a gradient was requested");
+    GPA_REQUIRE(plane_step >= 1, "plane_step must be >= 1");
     if (plane_begin == plane_end) return GPA_OK;
-    const int chunk = fit_chunk_mr(g, ws, ws_bytes, plane_end - plane_begin);
-    if (chunk != plane_end - plane_begin) {
-        set_error("gpa_sweep_finalize_mr needs every plane of the range resident (workspace holds %d of %d)", chunk,
-                  plane_end - plane_begin);
+    const int total = ceil_div(plane_end - plane_begin, plane_step);
+    const int chunk = fit_chunk_mr(g, ws, ws_bytes, total);
+    if (chunk != total) {
+        set_error("gpa_sweep_finalize_mr needs every plane of the range resident (workspace holds %d of %d)", chunk, total);
         return GPA_ERR_WORKSPACE;
     }
     TapTable tb;
@@ -1505,7 +1513,7 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
     f.kref_x = kref_x; f.kref_y = kref_y; f.N = N; f.M = M;
     f.plane0 = plane_begin; f.plane_begin = plane_begin; f.plane_end = plane_end;
     f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
-    mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S;
+    mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S; mp.pstep = plane_step;
     dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
     KernelTimer timer("k_mr_finalize", st);
 #define GPA_MRFIN(SS)                                                              \

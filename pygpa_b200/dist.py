@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_units", "merge_keys", "merge_payload", "pack_key", "unpack_key", "sharded_sweep"]
+__all__ = ["shard_units", "shard_units_interleaved", "merge_keys", "merge_payload", "pack_key", "unpack_key", "sharded_sweep"]
 
 
 def shard_units(n_peaks, n_planes, world, rank):
@@ -29,6 +29,18 @@ def shard_units(n_peaks, n_planes, world, rank):
     for p in range(n_peaks):
         a, b = max(lo, p * n_planes), min(hi, (p + 1) * n_planes)
         out.append((a - p * n_planes, b - p * n_planes) if b > a else (0, 0))
+    return out
+
+
+def shard_units_interleaved(n_peaks, n_planes, world, rank):
+    """Round-robin share of the flattened (peak, plane) list: unit u = peak * n_planes + plane goes
+    to rank u % world.  Returns [(plane_begin, plane_end, plane_step)] * n_peaks.  Every rank gets
+    planes spread over the whole grid (in particular some near its centre, where the winners
+    usually are), which keeps the exact pruning of the multirate arg-max effective on every rank."""
+    out = []
+    for p in range(n_peaks):
+        begin = (rank - p * n_planes) % world
+        out.append((begin, n_planes, world) if begin < n_planes else (0, 0, 1))
     return out
 
 
@@ -62,7 +74,7 @@ def merge_payload(tensors, group=None):
     return tensors
 
 
-def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None, seed_center=True):
+def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     """All peaks of one frame, k-grid sharded over the ranks of `group`.
     plans: one engine.SweepPlan per peak (identical on every rank; give them private workspaces so
     the finalize reuses what the arg-max left and stays bit-identical to one GPU).
@@ -80,28 +92,28 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None, seed
     if world == 1:
         return [plan.run(img_dev, kref, grad_mode) for plan, kref in zip(plans, krefs)]
     n_peaks, n, m, dev = len(plans), plans[0].n, plans[0].m, img_dev.device
-    ranges = shard_units(n_peaks, plans[0].wy.size, world, rank)
+    # multirate plans with their own workspace take an interleaved share (good pruning thresholds on
+    # every rank); otherwise contiguous plane ranges
+    interleave = all(p.mr is not None and p._private and p.mr_in_flight >= -(-p.wy.size // world) for p in plans)
+    if interleave:
+        ranges = shard_units_interleaved(n_peaks, plans[0].wy.size, world, rank)
+    else:
+        ranges = [(lo, hi, 1) for lo, hi in shard_units(n_peaks, plans[0].wy.size, world, rank)]
     keys = torch.zeros((n_peaks, n, m), dtype=torch.int64, device=dev)
-    for p, (plan, (lo, hi)) in enumerate(zip(plans, ranges)):
+    for p, (plan, (lo, hi, step)) in enumerate(zip(plans, ranges)):
         if hi > lo:
-            # Seed the keys with the centre plane (the one most likely to hold winners) when it is not
-            # part of this rank's share: the exact pruning of the multirate arg-max works against the
-            # winners recorded so far, and a rank that only owns outlying planes would otherwise prune
-            # almost nothing.  Costs 1/n_planes of redundant work; max-merging duplicates is harmless.
-            mid = plan.wy.size // 2
-            if plan.mr is not None and seed_center and not (lo <= mid < hi):
-                plan.argmax(img_dev, keys[p], mid, mid + 1)
-            plan.argmax(img_dev, keys[p], lo, hi)
+            plan.argmax(img_dev, keys[p], lo, hi, step)
     dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
     want_grad = grad_mode != 2
     # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)] float32, zero where this rank owns nothing
     payload = torch.zeros((2 if want_grad else 1, n_peaks, n, m, 2), dtype=torch.float32, device=dev)
     lockin = torch.view_as_complex(payload[0])
     outs = []
-    for p, (plan, kref, (lo, hi)) in enumerate(zip(plans, krefs, ranges)):
+    for p, (plan, kref, (lo, hi, step)) in enumerate(zip(plans, krefs, ranges)):
         out = {"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None}
-        plan.finalize(img_dev, keys[p], kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
-                      planes_valid=plan._private, out=out)
+        if hi > lo:
+            plan.finalize(img_dev, keys[p], kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
+                          planes_valid=plan._private, out=out, plane_step=step)
         out["key"] = keys[p]
         outs.append(out)
     if dst is None:

@@ -189,19 +189,23 @@ class SweepPlan:
     def _taps(self):
         return (_lib.as_pf(self.tx), self.rx, _lib.as_pf(self.ty), self.ry)
 
-    def argmax(self, img_dev, key, plane_begin=0, plane_end=None):
-        """key (N, M) int64 CUDA tensor, updated in place with this plane range's candidates."""
+    def argmax(self, img_dev, key, plane_begin=0, plane_end=None, plane_step=1):
+        """key (N, M) int64 CUDA tensor, updated in place with the candidates of planes
+        plane_begin, plane_begin + plane_step, ... < plane_end (a step > 1 needs the multirate form)."""
         lib = _lib.load()
         plane_end = self.wy.size if plane_end is None else plane_end
         ws = self._workspace()
+        if self.mr is None and plane_step != 1:
+            raise ValueError("interleaved plane shares are only available in the multirate form")
         if self.mr is not None:
             mr = self.mr
-            _lib.check(lib.gpa_sweep_argmax_mr(_ptr(img_dev), *self._geom(), plane_begin, plane_end, mr["S"],
+            _lib.check(lib.gpa_sweep_argmax_mr(_ptr(img_dev), *self._geom(), plane_begin, plane_end, plane_step, mr["S"],
                                                _lib.as_pf(mr["taps_ax"]), mr["Ra_x"], _lib.as_pf(mr["taps_ay"]), mr["Ra_y"],
                                                _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
                                                _ptr(key), _ptr(ws), ws.numel(), _stream()))
-            chunks = -(-(plane_end - plane_begin) // self.mr_in_flight) if plane_end > plane_begin else 0
-            _count(2 + 3 * chunks)
+            n_local = -(-(plane_end - plane_begin) // plane_step)
+            chunks = -(-n_local // self.mr_in_flight) if plane_end > plane_begin else 0
+            _count(2 + 4 * chunks)
             return
         _lib.check(lib.gpa_sweep_argmax(_ptr(img_dev), *self._geom(), plane_begin, plane_end, *self._taps(),
                                         _ptr(key), _ptr(ws), ws.numel(), _stream()))
@@ -209,8 +213,9 @@ class SweepPlan:
         _count(2 + 2 * chunks)
 
     def finalize(self, img_dev, key, kref, grad_mode=GRAD_CENTRAL, out_f64=False, want_w=False, want_kidx=True,
-                 plane_begin=0, plane_end=None, planes_valid=False, out=None):
-        """Winner's lock-in / gradient / w / k-index for pixels won by planes [plane_begin, plane_end).
+                 plane_begin=0, plane_end=None, planes_valid=False, out=None, plane_step=1):
+        """Winner's lock-in / gradient / w / k-index for pixels won by planes plane_begin,
+        plane_begin + plane_step, ... < plane_end.
         planes_valid: the workspace still holds what argmax() left for exactly this range (then the
         multirate path interpolates from its coarse grids and the direct path skips pass 1)."""
         lib = _lib.load()
@@ -220,16 +225,18 @@ class SweepPlan:
         cplx = torch.complex128 if out_f64 else torch.complex64
         if out is None:
             out = {}
-            full = plane_begin == 0 and plane_end == self.wy.size
+            full = plane_begin == 0 and plane_end == self.wy.size and plane_step == 1
             make = torch.empty if full else torch.zeros
             out["lockin"] = make((n, m), dtype=cplx, device=dev)
             out["grad"] = make((n, m, 2), dtype=real, device=dev) if grad_mode != GRAD_NONE else None
             out["w"] = make((2, n, m), dtype=real, device=dev) if want_w else None
             out["kidx"] = make((n, m), dtype=torch.int32, device=dev) if want_kidx else None
         ws = self._workspace()
-        if self.mr is not None and planes_valid and plane_end - plane_begin <= self.mr_in_flight:
+        if plane_step != 1 and not (self.mr is not None and planes_valid):
+            raise ValueError("an interleaved plane share can only be finalized from its resident coarse grids")
+        if self.mr is not None and planes_valid and -(-(plane_end - plane_begin) // plane_step) <= self.mr_in_flight:
             mr = self.mr
-            _lib.check(lib.gpa_sweep_finalize_mr(*self._geom(), plane_begin, plane_end, mr["S"], mr["Ra_x"], mr["Ra_y"],
+            _lib.check(lib.gpa_sweep_finalize_mr(*self._geom(), plane_begin, plane_end, plane_step, mr["S"], mr["Ra_x"], mr["Ra_y"],
                                                  _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
                                                  _ptr(key), float(kref[0]), float(kref[1]), grad_mode, int(out_f64),
                                                  _ptr(out["lockin"]), _ptr(out.get("grad")), _ptr(out.get("w")),

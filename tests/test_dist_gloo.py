@@ -29,6 +29,20 @@ def test_shard_units_balanced_and_complete():
     assert max(sum(hi - lo for lo, hi in gdist.shard_units(3, 41, 8, r)) for r in range(8)) == 16   # 96 % balance
 
 
+def test_interleaved_shares_are_balanced_and_complete():
+    for world in (2, 3, 4, 8):
+        seen = np.zeros((3, 41), dtype=int)
+        sizes = []
+        for rank in range(world):
+            total = 0
+            for p, (lo, hi, step) in enumerate(gdist.shard_units_interleaved(3, 41, world, rank)):
+                planes = list(range(lo, hi, step))
+                seen[p, planes] += 1
+                total += len(planes)
+            sizes.append(total)
+        assert (seen == 1).all() and max(sizes) - min(sizes) <= 1
+
+
 def test_pack_unpack_and_tie_break():
     amp2 = torch.tensor([0.0, 1.5, 1.5, 3.0e-20])
     idx = torch.tensor([7, 3, 2, 1680])
