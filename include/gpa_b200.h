@@ -196,6 +196,23 @@ int gpa_wfr_sweep(const float* img, int N, int M,
                   unsigned long long* key, void* lockin, void* grad, void* w, int* kidx,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* wfr4 (geometric_phase_analysis.py:839-862): sweep over an ORDERED k-list in which a pixel accepts
+ * candidate i only if |sf_i| is strictly larger than the amplitude it holds AND k_i lies within
+ * 2 sqrt(2) dk of the k-vector it currently holds (initially klist[0]).  The rule is sequential per
+ * pixel; pixels are independent, so one CTA walks the list for its tile (k_pass2_seq).
+ *   klist_x, klist_y  host, K entries each (kvec[0] / kvec[1] of the list)
+ *   allowed           DEVICE, K*K bytes: allowed[held*K + cand] = (norm(k_held - k_cand) < 2 sqrt(2) dk),
+ *                     evaluated by the caller with the reference's float64 expression (:854)
+ * Outputs as gpa_wfr_sweep with GPA_CAND_LIST and GPA_GRAD_NONE; pixels that never accept a candidate
+ * keep lockin = 0, kidx = -1 and w = klist[0] (the reference's initial state, :850-851). */
+int gpa_wfr4_sweep(const float* img, int N, int M,
+                   const double* klist_x /*host*/, const double* klist_y /*host*/, int K,
+                   const unsigned char* allowed /*device*/,
+                   const float* taps_x /*host*/, int Rx, const float* taps_y /*host*/, int Ry,
+                   double kref_x, double kref_y, int out_f64,
+                   unsigned long long* key, void* lockin, void* w, int* kidx,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 — per-pixel phase -> displacement least squares (float64 in, float64 out).
  *

@@ -16,10 +16,29 @@ from pygpa_b200 import synth
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def main():
-    gpa, pu = _refimport.load()
-    os.makedirs(OUT, exist_ok=True)
+def sorted_klist(centre, dk, half):
+    """A (2 half + 1)^2 grid of spacing dk around `centre`, nearest first — what
+    generate_klists(..., sort_list=True) (geometric_phase_analysis.py:865-889) feeds wfr4."""
+    ax = dk * np.arange(-half, half + 1)
+    kl = np.stack(np.meshgrid(ax, ax, indexing='ij'), axis=-1).reshape(-1, 2)
+    order = np.argsort(np.linalg.norm(kl, axis=1), kind='stable')
+    return np.asarray(centre) + kl[order]
 
+
+def gen_wfr4(gpa, pu):
+    """wfr4 (geometric_phase_analysis.py:839-862) on the frame of sweep_64x48.npz."""
+    g = dict(np.load(os.path.join(OUT, "sweep_64x48.npz")))
+    img, ks, sigma = g["in_image"], g["in_ks"], int(g["in_sigma"])
+    dk = 0.008
+    klist = sorted_klist(ks[1], dk, 3)
+    r = gpa.wfr4(img, sigma, klist, ks[1], dk)
+    r_far = gpa.wfr4(img, sigma, klist[::-1].copy(), ks[1], dk)     # starts far out: most pixels get stuck
+    np.savez_compressed(os.path.join(OUT, "wfr4_64x48.npz"), in_image=img, in_sigma=sigma, in_klist=klist,
+                        in_kref=ks[1], in_dk=dk, out_lockin=r['lockin'], out_w=r['w'],
+                        out_rev_lockin=r_far['lockin'], out_rev_w=r_far['w'])
+
+
+def gen_base(gpa, pu):
     # ---- adaptive sweep: wfr2_grad_opt + optwfr2, non-square frame, 3 peaks -------------
     shape = (64, 48)
     ks = synth.primary_ks(0.12, 7.0, 3)
@@ -116,6 +135,19 @@ def main():
         out_invert_edge0=gpa.invert_u_overlap(u_l),
         out_invert_edge3_it5=gpa.invert_u_overlap(u_l, iters=5, edge=3),
         out_undistorted=gpa.undistort_image(img_l, u_l))
+
+
+SECTIONS = {"base": gen_base, "wfr4": gen_wfr4}
+
+
+def main(argv=None):
+    """python -m oracle.gen_golden [section ...]   (default: every section)"""
+    import sys
+    names = list(argv if argv is not None else sys.argv[1:]) or list(SECTIONS)
+    gpa, pu = _refimport.load()
+    os.makedirs(OUT, exist_ok=True)
+    for name in names:
+        SECTIONS[name](gpa, pu)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

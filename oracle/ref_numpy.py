@@ -15,7 +15,7 @@ TWO_PI = 2.0 * np.pi
 
 __all__ = [
     "wrap_to_pi", "gaussian_transfer", "lockin_fixed", "candidate_axes", "wfr_sweep",
-    "wfr_sweep_klist", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
+    "wfr_sweep_klist", "wfr4", "wfr4_allowed", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
     "reconstruct_u_inv", "reconstruct_u_inv_from_phases", "invert_u_overlap",
     "undistort_image", "extract_displacement_field", "fixed_reference_pipeline",
 ]
@@ -134,6 +134,52 @@ def wfr_sweep(image, sigma, kx, ky, kw, kstep, grad_mode=None, want_grad=True,
     klist = np.stack(np.meshgrid(wxs, wys, indexing='ij'), axis=-1).reshape(-1, 2)
     out = wfr_sweep_klist(image, sigma, klist, (kx, ky), grad_mode, want_grad, return_diag)
     out['wxs'], out['wys'] = wxs, wys
+    return out
+
+
+def wfr4_allowed(klist, dk):
+    """The neighbourhood test of wfr4 (geometric_phase_analysis.py:854) as a (K, K) boolean table:
+    allowed[c, i] = ``np.linalg.norm(klist[c] - klist[i]) < 2*np.sqrt(2)*dk`` (c = the k-vector a
+    pixel currently holds, i = the new candidate), same float64 expression as the reference."""
+    klist = np.asarray(klist, dtype=np.float64).reshape(-1, 2)
+    return np.linalg.norm(klist[:, None, :] - klist[None, :, :], axis=-1) < 2 * np.sqrt(2) * dk
+
+
+def wfr4(image, sigma, klist, kref, dk, return_diag=False):
+    """geometric_phase_analysis.py:839-862: ordered sweep in which a pixel only accepts a new
+    candidate if its amplitude is larger AND its k lies within 2 sqrt(2) dk of the k the pixel
+    currently holds (initially klist[0]).  Sequential per pixel, order dependent.
+
+    return_diag adds 'kidx' (index of the held candidate, -1 = never accepted) and 'margin': the
+    smallest relative amplitude gap |a - |stored|| / max(a, |stored|) over all amplitude decisions
+    that mattered (candidates inside the neighbourhood) — a pixel with a small margin is a
+    near-tie and may legitimately follow another path in a different arithmetic."""
+    image = np.asarray(image, dtype=np.float64)
+    klist = np.asarray(klist, dtype=np.float64).reshape(-1, 2)
+    shape = image.shape
+    transfer = gaussian_transfer(shape, sigma)
+    x = np.arange(shape[0])[:, None]
+    y = np.arange(shape[1])[None, :]
+    lockin = np.zeros(shape, dtype=np.complex128)
+    w = np.zeros(shape + (2,))
+    w[..., 0], w[..., 1] = klist[0, 0], klist[0, 1]
+    kidx = np.full(shape, -1, dtype=np.int32)
+    margin = np.full(shape, np.inf)
+    for idx, (wx, wy) in enumerate(klist):
+        sf = np.fft.ifft2(np.fft.fft2(image * np.exp(TWO_PI * 1j * (x * wx + y * wy))) * transfer)
+        sf = sf * np.exp(-TWO_PI * 1j * ((wx - kref[0]) * x + (wy - kref[1]) * y))
+        a, stored = np.abs(sf), np.abs(lockin)
+        near = np.linalg.norm(w - np.array([wx, wy]), axis=-1) < 2 * np.sqrt(2) * dk
+        take = (a > stored) & near
+        if return_diag:
+            gap = np.abs(a - stored) / np.maximum(np.maximum(a, stored), 1e-300)
+            margin = np.where(near, np.minimum(margin, gap), margin)
+        lockin[take] = sf[take]
+        w[take] = (wx, wy)
+        kidx[take] = idx
+    out = {'lockin': lockin, 'w': np.moveaxis(w, -1, 0)}
+    if return_diag:
+        out['kidx'], out['margin'] = kidx, margin
     return out
 
 

@@ -47,6 +47,9 @@ SIGNATURES = {
     "gpa_wfr_sweep": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int,
                               _pf, c_int, _pf, c_int, c_double, c_double, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_wfr4_sweep": (c_int, [c_void_p, c_int, c_int, _pd, _pd, c_int, c_void_p, _pf, c_int, _pf, c_int,
+                               c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
     "gpa_lstsq_workspace_bytes": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
     "gpa_lstsq_u": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, _pd, c_int, c_int, c_int,
                             c_int, _pd, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -265,6 +265,82 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 2, sequential acceptance (wfr4): geometric_phase_analysis.py:839-862
+// ---------------------------------------------------------------------------------------------
+// The candidates form an ORDERED list and a pixel accepts candidate i only if |sf_i| is strictly
+// larger than what it holds AND k_i lies within 2 sqrt(2) dk of the k it currently holds.  The rule
+// is order dependent per pixel, so one CTA owns a pixel tile and walks the planes of the chunk in
+// list order; the (amplitude, held index) state lives in registers and is carried across chunks in
+// `key` (same packing as the arg-max sweeps, but plain loads/stores: no other CTA touches the tile).
+// The neighbourhood test is a host-built K x K byte table (the reference's float64 expression,
+// evaluated once per PAIR of list entries instead of once per pixel and candidate).
+__global__ void k_fill_u64(unsigned long long* __restrict__ dst, unsigned long long v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+struct SeqParams {
+    const float2* planes;
+    size_t plane_stride;
+    const float2* phx;
+    const unsigned char* allowed;   // [K][K]: allowed[held * K + candidate]
+    unsigned long long* key;
+    int N, M, pitch, n_alloc, T, plane0, count, K;
+};
+
+__global__ void __launch_bounds__(kWarps * 32, 1)
+k_pass2_seq(const SeqParams prm, const __grid_constant__ TapTable taps) {
+    extern __shared__ float2 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y0 = blockIdx.x * kLanes;
+    const int x0 = blockIdx.y * kTile;
+    const int T = prm.T;
+    const int n_samp = kTile + T + kAhead;
+    const int y = y0 + lane;
+    float best[kP];
+    int held[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+        const int x = x0 + warp * kP + p;
+        best[p] = 0.f;
+        held[p] = 0;
+        if (x < prm.N && y < prm.M) {
+            const unsigned long long k = prm.key[(size_t)x * prm.M + y];
+            best[p] = __uint_as_float((unsigned)(k >> 32));
+            held[p] = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+        }
+    }
+    const float2* col = smem + (warp * kP) * kLanes + lane;
+    for (int pl = 0; pl < prm.count; ++pl) {
+        __syncthreads();      // the previous plane's tile is no longer read
+        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride + (size_t)x0 * prm.pitch + y0 + lane;
+        for (int j = warp; j < n_samp; j += kWarps) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch);
+        __syncthreads();
+        const int cand = prm.plane0 + pl;
+        const float2* __restrict__ ph = prm.phx + (size_t)cand * prm.n_alloc + x0 + warp * kP;
+        float2 acc[kP];
+        fir_block<kP>(acc, taps, T, [&](int j) { return cmul(col[j * kLanes], __ldg(ph + j)); });
+        const unsigned char* __restrict__ ok = prm.allowed + cand;
+#pragma unroll
+        for (int p = 0; p < kP; ++p) {
+            const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
+            if (a2 > best[p] && __ldg(ok + (size_t)held[p] * prm.K)) {
+                best[p] = a2;
+                held[p] = cand;
+            }
+        }
+    }
+    if (y < prm.M) {
+#pragma unroll
+        for (int p = 0; p < kP; ++p) {
+            const int x = x0 + warp * kP + p;
+            if (x < prm.N)
+                prm.key[(size_t)x * prm.M + y] = ((unsigned long long)__float_as_uint(best[p]) << 32) |
+                                                 (unsigned long long)(0xFFFFFFFFu - (unsigned)held[p]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // multirate arg-max sweep
 // ---------------------------------------------------------------------------------------------
 // The Gaussian factorises, G_sigma = G_a * G_b with sigma_a^2 + sigma_b^2 = sigma^2, and after G_a
@@ -835,6 +911,7 @@ struct FinalizeParams {
     int plane0, plane_begin, plane_end;
     int list_mode, n_planes;
     int grad_mode;
+    double w0x, w0y;         // 'w' of pixels that never accepted a candidate (0 for the arg-max sweeps, klist[0] for wfr4)
 };
 
 __device__ __forceinline__ double wrap_to_pi(double v) {
@@ -933,8 +1010,8 @@ k_finalize(const FinalizeParams prm, const __grid_constant__ TapTable taps) {
             o_grad[2 * pix + 1] = 0;
         }
         if (o_w) {
-            o_w[pix] = 0;
-            o_w[npix + pix] = 0;
+            o_w[pix] = (R)prm.w0x;
+            o_w[npix + pix] = (R)prm.w0y;
         }
         if (prm.kidx) prm.kidx[pix] = -1;
         return;
@@ -1024,8 +1101,8 @@ k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) 
             static_cast<R*>(prm.grad)[2 * pix + 1] = 0;
         }
         if (prm.w) {
-            static_cast<R*>(prm.w)[pix] = 0;
-            static_cast<R*>(prm.w)[npix + pix] = 0;
+            static_cast<R*>(prm.w)[pix] = (R)prm.w0x;
+            static_cast<R*>(prm.w)[npix + pix] = (R)prm.w0y;
         }
         if (prm.kidx) prm.kidx[pix] = -1;
         return;
@@ -1582,6 +1659,44 @@ extern "C" int gpa_sweep_argmax(const float* img, int N, int M, const double* wx
     return GPA_OK;
 }
 
+// Direct-form finalize of planes [plane_begin, plane_end) in workspace-sized chunks (pass 1 is redone
+// per chunk unless the planes of a single chunk are still resident).
+static int finalize_direct(Geometry& g, const float* img, const double* wx_rows, const double* wy_planes, int cand_mode,
+                           int plane_begin, int plane_end, int planes_valid, const float* taps_x, const float* taps_y,
+                           const unsigned long long* key, double kref_x, double kref_y, int grad_mode, int out_f64,
+                           void* lockin, void* grad, void* w, int* kidx, double w0x, double w0y, void* ws,
+                           size_t ws_bytes, cudaStream_t st) {
+    int rc;
+    const int chunk = fit_chunk(g, ws, ws_bytes, plane_end - plane_begin);
+    if (chunk < 1) {
+        set_error("workspace too small (%zu bytes)", ws_bytes);
+        return GPA_ERR_WORKSPACE;
+    }
+    const bool reuse = planes_valid && chunk == plane_end - plane_begin;
+    TapTable tx, ty;
+    if ((rc = fill_taps(tx, taps_x, g.Rx)) || (rc = fill_taps(ty, taps_y, g.Ry))) return rc;
+    if (!reuse && (rc = build_tables(g, wx_rows, wy_planes, st))) return rc;
+    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
+        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
+        if (!reuse && (rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
+        FinalizeParams f;
+        f.planes = g.planes; f.plane_stride = g.plane_stride; f.phx = g.phx;
+        f.wx_rows = g.wx_d; f.wy_planes = g.wy_d; f.key = key;
+        f.lockin = lockin; f.grad = grad_mode == GPA_GRAD_NONE ? nullptr : grad; f.w = w; f.kidx = kidx;
+        f.kref_x = kref_x; f.kref_y = kref_y;
+        f.N = g.N; f.M = g.M; f.pitch = g.pitch; f.n_alloc = g.n_alloc; f.T = g.Tx; f.Rx = g.Rx;
+        f.plane0 = p0; f.plane_begin = p0; f.plane_end = p0 + cnt;
+        f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = g.n_planes; f.grad_mode = grad_mode;
+        f.w0x = w0x; f.w0y = w0y;
+        dim3 grid(ceil_div(g.M, 32), ceil_div(g.N, 8));
+        KernelTimer timer("k_finalize", st);
+        if (out_f64) k_finalize<double2><<<grid, 256, 0, st>>>(f, tx);
+        else k_finalize<float2><<<grid, 256, 0, st>>>(f, tx);
+        GPA_CHECK_CUDA(cudaGetLastError());
+    }
+    return GPA_OK;
+}
+
 extern "C" int gpa_sweep_finalize(const float* img, int N, int M, const double* wx_rows, int n_rows,
                                   const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
                                   int plane_end, int planes_valid, const float* taps_x, int Rx,
@@ -1597,34 +1712,55 @@ extern "C" int gpa_sweep_finalize(const float* img, int N, int M, const double* 
                 "bad grad_mode %d", grad_mode);
     GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr, "grad is null but a gradient was requested");
     if (plane_begin == plane_end) return GPA_OK;
-    const int chunk = fit_chunk(g, ws, ws_bytes, plane_end - plane_begin);
+    return finalize_direct(g, img, wx_rows, wy_planes, cand_mode, plane_begin, plane_end, planes_valid, taps_x, taps_y,
+                           key, kref_x, kref_y, grad_mode, out_f64, lockin, grad, w, kidx, 0.0, 0.0, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// wfr4 (geometric_phase_analysis.py:839-862): ordered k-list with the neighbourhood acceptance rule.
+// klist_x/klist_y: the K list entries (host); allowed: DEVICE K x K byte table, allowed[held*K + cand]
+// (host-evaluated `norm(k_held - k_cand) < 2 sqrt(2) dk`).  Outputs as gpa_wfr_sweep in list mode;
+// pixels that never accept a candidate keep lockin = 0 and w = klist[0] (the reference's initial state).
+extern "C" int gpa_wfr4_sweep(const float* img, int N, int M, const double* klist_x, const double* klist_y, int K,
+                              const unsigned char* allowed, const float* taps_x, int Rx, const float* taps_y, int Ry,
+                              double kref_x, double kref_y, int out_f64, unsigned long long* key, void* lockin,
+                              void* w, int* kidx, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = plan(g, N, M, K, K, Rx, Ry);
+    if (rc) return rc;
+    if ((rc = check_common(img, klist_x, klist_y, K, K, GPA_CAND_LIST, 0, K, ws))) return rc;
+    GPA_REQUIRE(allowed && key && lockin, "null pointer argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // initial state: amplitude 0, holding list entry 0
+    k_fill_u64<<<ceil_div(N * M, 256 * 4) < 1184 ? ceil_div(N * M, 256 * 4) : 1184, 256, 0, st>>>(key, 0x00000000FFFFFFFFull,
+                                                                                                  (size_t)N * M);
+    const int chunk = fit_chunk(g, ws, ws_bytes, K);
     if (chunk < 1) {
         set_error("workspace too small (%zu bytes)", ws_bytes);
         return GPA_ERR_WORKSPACE;
     }
-    const bool reuse = planes_valid && chunk == plane_end - plane_begin;
     TapTable tx, ty;
     if ((rc = fill_taps(tx, taps_x, Rx)) || (rc = fill_taps(ty, taps_y, Ry))) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!reuse && (rc = build_tables(g, wx_rows, wy_planes, st))) return rc;
-    for (int p0 = plane_begin; p0 < plane_end; p0 += chunk) {
-        const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
-        if (!reuse && (rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
-        FinalizeParams f;
-        f.planes = g.planes; f.plane_stride = g.plane_stride; f.phx = g.phx;
-        f.wx_rows = g.wx_d; f.wy_planes = g.wy_d; f.key = key;
-        f.lockin = lockin; f.grad = grad_mode == GPA_GRAD_NONE ? nullptr : grad; f.w = w; f.kidx = kidx;
-        f.kref_x = kref_x; f.kref_y = kref_y;
-        f.N = N; f.M = M; f.pitch = g.pitch; f.n_alloc = g.n_alloc; f.T = g.Tx; f.Rx = Rx;
-        f.plane0 = p0; f.plane_begin = p0; f.plane_end = p0 + cnt;
-        f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
-        dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
-        KernelTimer timer("k_finalize", st);
-        if (out_f64) k_finalize<double2><<<grid, 256, 0, st>>>(f, tx);
-        else k_finalize<float2><<<grid, 256, 0, st>>>(f, tx);
+    if ((rc = build_tables(g, klist_x, klist_y, st))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    for (int p0 = 0; p0 < K; p0 += chunk) {
+        const int cnt = K - p0 < chunk ? K - p0 : chunk;
+        if ((rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
+        SeqParams p;
+        p.planes = g.planes; p.plane_stride = g.plane_stride; p.phx = g.phx; p.allowed = allowed; p.key = key;
+        p.N = N; p.M = M; p.pitch = g.pitch; p.n_alloc = g.n_alloc; p.T = g.Tx; p.plane0 = p0; p.count = cnt; p.K = K;
+        const size_t smem = (size_t)(kTile + g.Tx + kAhead) * kLanes * sizeof(float2);
+        dim3 grid(g.pitch / kLanes, ceil_div(N, kTile), 1);
+        KernelTimer timer("k_pass2_seq", st);
+        k_pass2_seq<<<grid, kWarps * 32, smem, st>>>(p, tx);
         GPA_CHECK_CUDA(cudaGetLastError());
     }
-    return GPA_OK;
+    return finalize_direct(g, img, klist_x, klist_y, GPA_CAND_LIST, 0, K, chunk == K, taps_x, taps_y, key, kref_x, kref_y,
+                           GPA_GRAD_NONE, out_f64, lockin, nullptr, w, kidx, klist_x[0], klist_y[0], ws, ws_bytes, st);
 }
 
 extern "C" int gpa_wfr_sweep(const float* img, int N, int M, const double* wx_rows, int n_rows,

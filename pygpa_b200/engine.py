@@ -281,6 +281,37 @@ class SweepPlan:
         return out
 
 
+def wfr4_sweep(img_dev, sigma, klist, kref, dk, trunc=DEFAULT_TRUNC, out_f64=True):
+    """Ordered k-list sweep with the neighbourhood acceptance rule of wfr4
+    (geometric_phase_analysis.py:839-862) on a float32 CUDA image; dict of CUDA tensors."""
+    lib = _lib.load()
+    device = img_dev.device
+    n, m = img_dev.shape
+    klist = np.ascontiguousarray(klist, dtype=np.float64).reshape(-1, 2)
+    kx, ky = klist[:, 0].copy(), klist[:, 1].copy()
+    K = kx.size
+    if K == 0:
+        raise ValueError("klist is empty")
+    # the reference's test (:854), evaluated once per pair of list entries: same float64 expression
+    allowed = np.linalg.norm(klist[:, None, :] - klist[None, :, :], axis=-1) < 2 * np.sqrt(2) * dk
+    allowed_dev = torch.from_numpy(np.ascontiguousarray(allowed, dtype=np.uint8)).to(device)
+    tx, rx = axis_taps(n, sigma, trunc)
+    ty, ry = axis_taps(m, sigma, trunc)
+    in_flight, nbytes = _plan_planes(n, m, K, K, rx, ry, device, None)
+    ws = workspace(nbytes, device)
+    out = {"key": torch.empty((n, m), dtype=torch.int64, device=device),
+           "lockin": torch.empty((n, m), dtype=torch.complex128 if out_f64 else torch.complex64, device=device),
+           "w": torch.empty((2, n, m), dtype=torch.float64 if out_f64 else torch.float32, device=device),
+           "kidx": torch.empty((n, m), dtype=torch.int32, device=device)}
+    _lib.check(lib.gpa_wfr4_sweep(_ptr(img_dev), n, m, _lib.as_pd(kx), _lib.as_pd(ky), K, _ptr(allowed_dev),
+                                  _lib.as_pf(tx), rx, _lib.as_pf(ty), ry, float(kref[0]), float(kref[1]), int(out_f64),
+                                  _ptr(out["key"]), _ptr(out["lockin"]), _ptr(out["w"]), _ptr(out["kidx"]),
+                                  _ptr(ws), ws.numel(), _stream()))
+    chunks = -(-K // in_flight)
+    _count(3 + 2 * chunks + (1 if chunks == 1 else 2 + 2 * chunks))
+    return out
+
+
 def grid_axes(kx, ky, kw, kstep):
     """The reference's candidate axes, verbatim NumPy expression because the lengths are
     rounding dependent (geometric_phase_analysis.py:803-804)."""

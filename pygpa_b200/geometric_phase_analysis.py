@@ -15,8 +15,8 @@ from . import engine, solvers
 from .cuGPA import _sweep, _to_host
 from .mathtools import wrapToPi  # noqa: F401  (re-exported like the reference does)
 
-__all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_grad_opt",
-           "wfr2_grad", "wfr3", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
+__all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_only_lockin_vec",
+           "wfr2_grad_opt", "wfr2_grad", "wfr2_grad_vec", "wfr3", "wfr4", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
            "extract_displacement_field", "invert_u", "invert_u_overlap", "undistort_image"]
 
 
@@ -89,6 +89,29 @@ def wfr3(image, sigma, klist, kref):
     host = {k: _to_host(res[k]) for k in ("lockin", "w")}
     torch.cuda.current_stream().synchronize()
     return {k: v.numpy() for k, v in host.items()}
+
+
+def wfr4(image, sigma, klist, kref, dk):
+    """Ordered k-list sweep where a pixel accepts a stronger candidate only if its k lies within
+    2 sqrt(2) dk of the k the pixel currently holds (geometric_phase_analysis.py:839-862)."""
+    device = engine.require_cuda()
+    img = engine.image_to_device(image, device)
+    res = engine.wfr4_sweep(img, sigma, klist, kref, dk)
+    host = {k: _to_host(res[k]) for k in ("lockin", "w")}
+    torch.cuda.current_stream().synchronize()
+    return {k: v.numpy() for k, v in host.items()}
+
+
+def wfr2_only_lockin_vec(image, sigma, kx, ky, kw, kstep):
+    """geometric_phase_analysis.py:705-719 batches the candidates of one wx through dask; the
+    per-pixel result is that of wfr2_only_lockin, and on the GPU every candidate of a tile is
+    already processed in one kernel."""
+    return wfr2_only_lockin(image, sigma, kx, ky, kw, kstep)
+
+
+def wfr2_grad_vec(image, sigma, kx, ky, kw, kstep):
+    """geometric_phase_analysis.py:816-836: dask-batched wfr2_grad_opt, same result."""
+    return wfr2_grad_opt(image, sigma, kx, ky, kw, kstep)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -35,6 +35,20 @@ def test_wfr3_matches_reference_fixture():
     assert np.array_equal(o["w"], g["out_w"])
 
 
+def test_wfr4_matches_reference_fixture():
+    g = load_golden("wfr4_64x48.npz")
+    args = (g["in_image"], int(g["in_sigma"]))
+    for tag, kl in (("", g["in_klist"]), ("rev_", g["in_klist"][::-1].copy())):
+        o = oracle.wfr4(*args, kl, g["in_kref"], float(g["in_dk"]), return_diag=True)
+        assert np.allclose(o["lockin"], g["out_" + tag + "lockin"], **TIGHT)
+        assert np.array_equal(o["w"], g["out_" + tag + "w"])
+        held = o["kidx"] >= 0
+        assert np.array_equal(kl[o["kidx"][held]].T, o["w"][:, held])
+    # the pairwise table is the reference's per-pixel test
+    a = oracle.wfr4_allowed(g["in_klist"], float(g["in_dk"]))
+    assert a.shape == (49, 49) and a.diagonal().all() and np.array_equal(a, a.T)
+
+
 def test_tail_matches_reference_fixture():
     g = load_golden("tail_64x48.npz")
     ks, ph, w = g["in_ks"], g["in_phases"], g["in_weights"]

@@ -216,6 +216,72 @@ def test_wfr3_candidate_list():
     check_sweep(got, ref, check_grad=False)
 
 
+def _check_wfr4(got, image, sigma, klist, kref, dk, ref_lockin, ref_w):
+    """wfr4 is path dependent per pixel: a pixel whose amplitude decisions all had a relative margin
+    above the near-tie budget must follow the reference's path exactly."""
+    diag = oracle.wfr4(image, sigma, klist, kref, dk, return_diag=True)
+    assert np.array_equal(diag["w"], ref_w)
+    same = np.all(got["w"] == ref_w, axis=0)
+    clear = diag["margin"] > NEAR_TIE
+    assert not (~same & clear).any(), f"{(~same & clear).sum()} pixels follow another path away from a near-tie"
+    amax = np.abs(ref_lockin).max()
+    assert np.abs(got["lockin"] - ref_lockin)[same].max() <= 1e-4 * amax
+    m = same & (np.abs(ref_lockin) > 0.02 * amax)
+    assert np.abs(np.angle(got["lockin"][m] * np.conj(ref_lockin[m]))).max() < 1e-3
+    return same.mean()
+
+
+def test_wfr4_neighbourhood_rule_matches_reference_fixture():
+    g = load_golden("wfr4_64x48.npz")
+    img, sigma, klist, kref, dk = g["in_image"], int(g["in_sigma"]), g["in_klist"], g["in_kref"], float(g["in_dk"])
+    got = GPA.wfr4(img, sigma, klist, kref, dk)
+    assert got["lockin"].dtype == np.complex128 and got["w"].shape == (2,) + img.shape
+    assert _check_wfr4(got, img, sigma, klist, kref, dk, g["out_lockin"], g["out_w"]) > 0.99
+    # reversed list: starts far from the peak, the neighbourhood rule decides which pixels ever move
+    rev = klist[::-1].copy()
+    got = GPA.wfr4(img, sigma, rev, kref, dk)
+    assert _check_wfr4(got, img, sigma, rev, kref, dk, g["out_rev_lockin"], g["out_rev_w"]) > 0.99
+
+
+def test_wfr4_chunked_planes_and_unreachable_candidates():
+    """Workspace-limited plane chunks carry the (amplitude, held index) state through `key`; with a
+    tiny dk no candidate but the first is ever reachable, so w stays klist[0] everywhere."""
+    g = load_golden("wfr4_64x48.npz")
+    img, sigma, klist, kref, dk = g["in_image"], int(g["in_sigma"]), g["in_klist"], g["in_kref"], float(g["in_dk"])
+    dev = engine.require_cuda()
+    d_img = engine.image_to_device(img, dev)
+    full = engine.wfr4_sweep(d_img, sigma, klist, kref, dk)
+    real_plan = engine._plan_planes
+
+    def few_planes(n, m, n_rows, n_planes, rx, ry, device, planes_in_flight):
+        return real_plan(n, m, n_rows, n_planes, rx, ry, device, 5)
+    engine._plan_planes = few_planes
+    try:
+        engine.release_workspaces()
+        part = engine.wfr4_sweep(d_img, sigma, klist, kref, dk)
+    finally:
+        engine._plan_planes = real_plan
+        engine.release_workspaces()
+    assert torch.equal(full["key"], part["key"]) and torch.equal(full["kidx"], part["kidx"])
+    assert torch.equal(torch.view_as_real(full["lockin"]), torch.view_as_real(part["lockin"]))
+    stuck = GPA.wfr4(img, sigma, klist, kref, 1e-9)
+    assert np.all(stuck["w"][0] == klist[0, 0]) and np.all(stuck["w"][1] == klist[0, 1])
+    ref = oracle.wfr4(img, sigma, klist, kref, 1e-9)
+    assert np.abs(stuck["lockin"] - ref["lockin"]).max() <= 1e-4 * np.abs(ref["lockin"]).max()
+
+
+def test_vec_variants_are_the_same_sweep(noisy_case):
+    """wfr2_only_lockin_vec / wfr2_grad_vec (geometric_phase_analysis.py:705-719, 816-836) only batch
+    the candidates differently (dask); their results are those of the plain functions."""
+    c = noisy_case
+    k = c["ks"][0]
+    a = GPA.wfr2_grad_vec(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    b = GPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    for key in ("lockin", "w", "grad"):
+        assert np.array_equal(a[key], b[key])
+    assert np.array_equal(GPA.wfr2_only_lockin_vec(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"]), b["lockin"])
+
+
 def _run_device(img, plan, kref, **kw):
     return plan.run(img, kref, **kw)
 
