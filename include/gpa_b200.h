@@ -245,6 +245,33 @@ int gpa_lstsq_u(const double* src, int src_kind, const double* w, int wn, int wm
 int gpa_norm_axis0(const double* w, int d, size_t n, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5 — local lattice properties from the sweep's phase-gradient maps (float64), SURVEY 8(f) row 1.
+ *
+ * Replaces: phasegradient2J / phasegradient2Jac (property_extract.py:69-101, 55-66) and
+ * props_from_Jac / props_from_J (property_extract.py:137-178, 218-219).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Per pixel: b_i[c] = grads[order[i], x, y, c] - sub[i][c] (wrapped to [-pi, pi) when do_wrap),
+ * then for c = 0, 1 the weighted least squares argmin | weights[i] (K_i . x - b_i[c]) | with the
+ * minimum-norm rule of K3; J[x, y, a, c] = x_a / nmperpixel (+ 1 on the diagonal when add_identity:
+ * phasegradient2Jac).  The host supplies what property_extract.py:78-94 derives from the k-vectors:
+ * K = 2 pi (kvecs[order] + dks), sub = 2 pi dks (calc_diff_from_isotropic), order (sort != 0).
+ *   grads (d, N, M, 2) device, weights (d, wn, wm) device (wn >= N, wm >= M; NOT re-ordered, as in
+ *   the reference), K / sub (d, 2) host, order d host (NULL = identity), J (N, M, 2, 2) device. */
+int gpa_phasegradient_to_j(const double* grads, const double* weights, int wn, int wm,
+                           const double* K /*host*/, const double* sub /*host or NULL*/,
+                           const int* order /*host or NULL*/, int do_wrap, int d, int N, int M,
+                           double nmperpixel, int add_identity, double* J, void* stream);
+
+/* props_from_Jac on npix 2x2 Jacobians (row-major, + identity when add_identity: props_from_J):
+ * props[0] = lattice angle + refangle [deg], props[1] = anisotropy angle mod 180 [deg] (+ 90 when
+ * diff), props[2] = refscale * smaller (diff: larger) singular value, props[3] = s0 / s1; props is
+ * (4, npix).  The SVD reproduces LAPACK dgesdd's sign conventions, on which the reference's
+ * formulas depend (pygpa_b200/csrc/props_device.cuh). */
+int gpa_props_from_jac(const double* jac, size_t npix, double refangle, double refscale, int diff,
+                       int add_identity, double* props, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2 — weighted least-squares phase unwrapping (Ghiglia-Romero PCG, DCT Poisson preconditioner),
  * float64 throughout.
  *

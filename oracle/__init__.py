@@ -14,3 +14,4 @@ reference checkout is present, against the live reference in
 ``tests/test_oracle_vs_reference.py``.
 """
 from .ref_numpy import *  # noqa: F401,F403
+from .props_numpy import *  # noqa: F401,F403

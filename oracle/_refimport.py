@@ -25,6 +25,34 @@ def _stub(name, **attrs):
     return mod
 
 
+def _rotate(v, angle):
+    """Stand-in for latticegen.transformations.rotate (third party, absent offline): only reached
+    through calc_diff_from_isotropic (geometric_phase_analysis.py:318), which enumerates ALL rotations
+    of one vector by multiples of 2 pi / symmetry and keeps the nearest — the set, and so the result,
+    is the same for either sign convention of the rotation."""
+    import numpy as np
+    c, s = np.cos(angle), np.sin(angle)
+    return np.array([[c, -s], [s, c]]) @ np.asarray(v)
+
+
+def load_property_extract():
+    """The reference's pyGPA.property_extract (its latticegen / dask imports stubbed)."""
+    gpa, _ = load()
+    tr = sys.modules["latticegen.transformations"]
+    tr.rotate = _rotate
+    # property_extract.py:692-693 wraps two more latticegen helpers in numba.njit at import time (lazy:
+    # never compiled unless the Kerelsky fit is called, which the oracle does not do)
+    tr.rotation_matrix = lambda angle: None
+    tr.strain_matrix = lambda epsilon: None
+    # property_extract.py:863 decorates one function with dask.array.as_gufunc (unused here)
+    sys.modules["dask.array"].as_gufunc = lambda **kw: (lambda f: f)
+    sys.modules["dask"].array = sys.modules["dask.array"]
+    sys.modules["latticegen"].transformations = sys.modules["latticegen.transformations"]
+    gpa.rotate = _rotate          # `from latticegen.transformations import rotate` bound the stub's None
+    import pyGPA.property_extract as pe
+    return pe
+
+
 def load():
     """Returns (geometric_phase_analysis, phase_unwrap) modules of the reference."""
     if not available():

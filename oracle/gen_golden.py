@@ -38,6 +38,35 @@ def gen_wfr4(gpa, pu):
                         out_rev_lockin=r_far['lockin'], out_rev_w=r_far['w'])
 
 
+def gen_props(gpa, pu):
+    """phasegradient2J / props_from_Jac (property_extract.py:69-101, 137-178) on the gradients of
+    sweep_64x48.npz; `in_ks_ani` is a strained copy of the k-vectors so the isotropic re-referencing
+    (calc_diff_from_isotropic) is not a no-op."""
+    pe = _refimport.load_property_extract()
+    g = dict(np.load(os.path.join(OUT, "sweep_64x48.npz")))
+    ks, grads, w = g["in_ks"], g["out_grad"], np.abs(g["out_lockin"])
+    ks_ani = ks @ np.array([[1.03, 0.02], [-0.01, 0.98]]).T
+    w0 = w.copy()
+    w0[:, :2] = 0.0             # zero-weight pixels: J = 0, Jac = identity
+    w0[1:, 2:4] = 0.0           # rank-1 pixels
+    nm = 0.5
+    J_iso = pe.phasegradient2J(ks_ani, grads, w, nm)
+    Jac = np.eye(2) + J_iso
+    np.savez_compressed(
+        os.path.join(OUT, "props_64x48.npz"), in_ks=ks, in_ks_ani=ks_ani, in_grads=grads, in_weights=w,
+        in_weights_rankdef=w0, in_nmperpixel=nm,
+        out_J_iso=J_iso,
+        out_J_plain=pe.phasegradient2J(ks_ani, grads, w, nm, iso_ref=False),
+        out_J_sorted=pe.phasegradient2J(ks_ani, grads, w, nm, sort=1),
+        out_J_sorted_neg=pe.phasegradient2J(ks_ani, grads, w, nm, sort=-1),
+        out_J_rankdef=pe.phasegradient2J(ks_ani, grads, w0, nm),
+        out_Jac=pe.phasegradient2Jac(ks_ani, grads, w, nm),
+        out_props=pe.props_from_Jac(Jac),
+        out_props_diff=pe.props_from_Jac(Jac, refangle=3.0, refscale=2.0, diff=True),
+        out_props_rankdef=pe.props_from_Jac(np.eye(2) + pe.phasegradient2J(ks_ani, grads, w0, nm)),
+        out_props_from_J=pe.props_from_J(J_iso, refangle=-1.5, refscale=0.7))
+
+
 def gen_base(gpa, pu):
     # ---- adaptive sweep: wfr2_grad_opt + optwfr2, non-square frame, 3 peaks -------------
     shape = (64, 48)
@@ -137,7 +166,7 @@ def gen_base(gpa, pu):
         out_undistorted=gpa.undistort_image(img_l, u_l))
 
 
-SECTIONS = {"base": gen_base, "wfr4": gen_wfr4}
+SECTIONS = {"base": gen_base, "wfr4": gen_wfr4, "props": gen_props}
 
 
 def main(argv=None):

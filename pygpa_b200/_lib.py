@@ -53,6 +53,9 @@ SIGNATURES = {
     "gpa_lstsq_workspace_bytes": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
     "gpa_lstsq_u": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, _pd, c_int, c_int, c_int,
                             c_int, _pd, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_phasegradient_to_j": (c_int, [c_void_p, c_void_p, c_int, c_int, _pd, _pd, ctypes.POINTER(c_int), c_int, c_int,
+                                       c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
+    "gpa_props_from_jac": (c_int, [c_void_p, c_size_t, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     "gpa_norm_axis0": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

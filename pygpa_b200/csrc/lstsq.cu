@@ -8,10 +8,9 @@
 // gelsd's rank rule: singular values <= eps * s_max are dropped and the minimum-norm solution
 // returned (all-zero weights -> 0).  HBM-bound: (2d + 2) doubles per pixel.
 #include "common.cuh"
+#include "lsq_device.cuh"
 
 namespace gpa {
-
-constexpr int kMaxD = 8;
 
 struct LsqParams {
     const double* src;    // phases / gradients / unwrapped phases
@@ -24,14 +23,6 @@ struct LsqParams {
     double P[2][kMaxD];   // unweighted / two-k branch: x = P b
     int use_matrix;
 };
-
-__device__ __forceinline__ double wrap_pi(double v) {
-    const double two_pi = 6.283185307179586476925286766559;
-    const double pi = 3.141592653589793238462643383279;
-    double t = (v + pi) / two_pi;
-    t -= floor(t);
-    return t * two_pi - pi;
-}
 
 __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -59,62 +50,19 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
             }
         }
     } else {
-        double a0[kMaxD], a1[kMaxD], y[kMaxD];
-        double n0 = 0.0, n1 = 0.0;
+        double a0[kMaxD], a1[kMaxD], y[1][kMaxD], x[1][2];
 #pragma unroll
         for (int i = 0; i < kMaxD; ++i) {
             if (i < p.d) {
                 const double w = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
                 a0[i] = w * p.K[i][0];
                 a1[i] = w * p.K[i][1];
-                y[i] = w * b[i];
-                n0 = fma(a0[i], a0[i], n0);
-                n1 = fma(a1[i], a1[i], n1);
+                y[0][i] = w * b[i];
             }
         }
-        const bool swap = n1 > n0;   // column pivoting: the larger column first
-        const double f2 = swap ? n1 : n0;
-        if (f2 > 0.0) {
-            const double f = sqrt(f2);
-            const double inv_f = 1.0 / f;
-            double q[kMaxD];
-            double g = 0.0, z1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < kMaxD; ++i) {
-                if (i < p.d) {
-                    q[i] = (swap ? a1[i] : a0[i]) * inv_f;
-                    g = fma(q[i], swap ? a0[i] : a1[i], g);
-                    z1 = fma(q[i], y[i], z1);
-                }
-            }
-            double h2 = 0.0, z2h = 0.0;   // second column orthogonalised against the first
-#pragma unroll
-            for (int i = 0; i < kMaxD; ++i) {
-                if (i < p.d) {
-                    const double e = (swap ? a0[i] : a1[i]) - g * q[i];
-                    h2 = fma(e, e, h2);
-                    z2h = fma(e, y[i], z2h);     // = h * z2
-                }
-            }
-            const double h = sqrt(h2);
-            // singular values of [[f, g], [0, h]]
-            const double t = f * f + g * g + h * h;
-            const double det = f * h;
-            const double disc = sqrt(fmax(t * t - 4.0 * det * det, 0.0));
-            const double s1 = sqrt(0.5 * (t + disc));
-            const double s2 = det / s1;
-            double u0, u1;
-            if (s2 > 2.220446049250313e-16 * s1) {
-                u1 = z2h / h2;                 // z2 / h
-                u0 = (z1 - g * u1) * inv_f;
-            } else {                            // rank 1: minimum-norm solution of [f g] u = z1
-                const double nn = f * f + g * g;
-                u0 = f * z1 / nn;
-                u1 = g * z1 / nn;
-            }
-            x0 = swap ? u1 : u0;
-            x1 = swap ? u0 : u1;
-        }
+        lsq_solve2<1>(a0, a1, y, p.d, x);
+        x0 = x[0][0];
+        x1 = x[0][1];
     }
     const size_t np = (size_t)p.n * p.m;
     p.out[(size_t)r * p.m + c] = x0;

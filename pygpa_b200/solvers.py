@@ -78,6 +78,39 @@ def lstsq(src, kind, kvecs, weights=None, matrix=None, subtract_mean=False):
     return out
 
 
+def phasegradient_to_J(grads, weights, K, sub=None, order=None, do_wrap=False, nmperpixel=1.0, add_identity=False):
+    """K5a: (d, N, M, 2) phase gradients + (d, >=N, >=M) weights -> J (N, M, 2, 2) on the device
+    (property_extract.py:69-101; K, sub, order are the host-side quantities described in gpa_b200.h)."""
+    lib = _lib.load()
+    d, n, m = int(grads.shape[0]), int(grads.shape[1]), int(grads.shape[2])
+    if tuple(grads.shape) != (d, n, m, 2) or weights.shape[0] != d:
+        raise ValueError("grads must be (d, N, M, 2) and weights (d, N, M)")
+    K = np.ascontiguousarray(K, dtype=np.float64).reshape(d, 2)
+    sub_a = None if sub is None else np.ascontiguousarray(sub, dtype=np.float64).reshape(d, 2)
+    ord_a = None if order is None else np.ascontiguousarray(order, dtype=np.int32).reshape(d)
+    out = torch.empty((n, m, 2, 2), dtype=torch.float64, device=grads.device)
+    _lib.check(lib.gpa_phasegradient_to_j(_ptr(grads), _ptr(weights), int(weights.shape[1]), int(weights.shape[2]),
+                                          _lib.as_pd(K), _lib.as_pd(sub_a) if sub_a is not None else None,
+                                          ord_a.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if ord_a is not None else None,
+                                          int(do_wrap), d, n, m, float(nmperpixel), int(add_identity), _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
+def props_from_jac(jac, refangle=0.0, refscale=1.0, diff=False, add_identity=False):
+    """K5b: (..., 2, 2) Jacobians -> (4, ...) properties on the device (property_extract.py:137-178)."""
+    lib = _lib.load()
+    if jac.shape[-2:] != (2, 2):
+        raise ValueError("Jac must have shape (..., 2, 2)")
+    lead = tuple(jac.shape[:-2])
+    npix = int(np.prod(lead)) if lead else 1
+    out = torch.empty((4,) + lead, dtype=torch.float64, device=jac.device)
+    _lib.check(lib.gpa_props_from_jac(_ptr(jac), npix, float(refangle), float(refscale), int(bool(diff)),
+                                      int(bool(add_identity)), _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
 def norm_axis0(w):
     lib = _lib.load()
     out = torch.empty(w.shape[1:], dtype=torch.float64, device=w.device)
