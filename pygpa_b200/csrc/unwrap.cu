@@ -9,8 +9,9 @@
 // enqueues (it polls the flag every few iterations to stop enqueueing early).
 //
 // DCT-II / DCT-III (scipy.fft.dctn / idctn, unnormalised): one row per CTA in shared memory.
-// Power-of-two lengths use Makhoul's N-point complex FFT (radix-4 Stockham in place, twiddles
-// from a table); other lengths use the O(n^2) cosine-table sum (any n, slower).  The 2-D
+// Power-of-two lengths use Makhoul's permutation and ONE n-point complex FFT per PAIR of rows
+// (radix-8 Stockham in place, twiddles from a table); other lengths use the O(n^2) cosine-table
+// sum (any n, slower).  The 2-D
 // transform is row pass -> transpose -> row pass; the 1/scale of the Poisson solve is fused into
 // the second forward pass and <r, z> into the last inverse pass.
 #include "common.cuh"
@@ -49,6 +50,12 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // tables
 // ------------------------------------------------------------------------------------------
 // tw[t] = exp(-2 pi i t / n), t < n ;  mk[k] = exp(-i pi k / (2n)), k < n ; ct[j] = cos(pi j / (2n)), j < 4n
+// cs[i] = cos(pi i / denom), i < n
+__global__ void k_uw_cos_table(double* cs, int n, int denom) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cs[i] = cospi((double)i / (double)denom);
+}
+
 __global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (pow2) {
@@ -66,71 +73,126 @@ __global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow
 
 // ------------------------------------------------------------------------------------------
 // in-place Stockham FFT of buf[0..n) (forward, e^{-2 pi i jk/n}); all threads of the CTA.
-// Radix-4 stages (half the shared-memory round trips of radix 2), preceded by one radix-2 stage
-// when log2(n) is odd.  MAXB = radix-4 butterflies per thread; tw[t] = e^{-2 pi i t/n}, t < n.
+// Radix-8 stages (a third of the shared-memory round trips of radix 2), preceded by one radix-2 or
+// radix-4 stage when log2(n) is not a multiple of 3.  Every stage reads all its inputs into
+// registers, synchronises, and writes in autosort order: no second buffer.  MAXB = radix-8
+// butterflies per thread (blockDim.x * MAXB >= n / 8); tw[t] = e^{-2 pi i t/n}, t < n.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 zmul_mi(double2 a) { return make_double2(a.y, -a.x); }     // -i a
+
+// x <- DFT_4(x), natural order
+__device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
+    const double2 t0 = zadd(x0, x2), t1 = zsub(x0, x2), t2 = zadd(x1, x3), t3 = zmul_mi(zsub(x1, x3));
+    x0 = zadd(t0, t2);
+    x1 = zadd(t1, t3);
+    x2 = zsub(t0, t2);
+    x3 = zsub(t1, t3);
+}
+
+// u <- DFT_8(u), natural order
+__device__ __forceinline__ void dft8(double2 (&u)[8]) {
+    const double r = 0.70710678118654752440084436210485;
+    double2 a0 = zadd(u[0], u[4]), a1 = zadd(u[1], u[5]), a2 = zadd(u[2], u[6]), a3 = zadd(u[3], u[7]);
+    double2 b0 = zsub(u[0], u[4]), b1 = zsub(u[1], u[5]), b2 = zsub(u[2], u[6]), b3 = zsub(u[3], u[7]);
+    b1 = make_double2(r * (b1.x + b1.y), r * (b1.y - b1.x));       // * e^{-i pi/4}
+    b2 = zmul_mi(b2);                                              // * e^{-i pi/2}
+    b3 = make_double2(r * (b3.y - b3.x), -r * (b3.x + b3.y));      // * e^{-3 i pi/4}
+    dft4(a0, a1, a2, a3);
+    dft4(b0, b1, b2, b3);
+    u[0] = a0; u[1] = b0; u[2] = a1; u[3] = b1; u[4] = a2; u[5] = b2; u[6] = a3; u[7] = b3;
 }
 
 template <int MAXB>
 __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __restrict__ tw) {
     const int nthr = blockDim.x;
+    const int lg = 31 - __clz(n);
     int ns = 1;
-    if (__popc(n - 1) & 1) {                         // log2(n) odd: one radix-2 stage
+    if (lg % 3 == 1) {                               // one radix-2 stage (ns = 1: twiddles are 1)
         const int half = n >> 1;
-        double2 a[2 * MAXB], b[2 * MAXB];
+        double2 a[4 * MAXB], b[4 * MAXB];
 #pragma unroll
-        for (int q = 0; q < 2 * MAXB; ++q) {
+        for (int q = 0; q < 4 * MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
             if (j < half) {
                 a[q] = buf[j];
-                b[q] = buf[j + half];                // ns = 1: twiddle is 1
+                b[q] = buf[j + half];
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 2 * MAXB; ++q) {
+        for (int q = 0; q < 4 * MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
             if (j < half) {
-                buf[2 * j] = make_double2(a[q].x + b[q].x, a[q].y + b[q].y);
-                buf[2 * j + 1] = make_double2(a[q].x - b[q].x, a[q].y - b[q].y);
+                buf[2 * j] = zadd(a[q], b[q]);
+                buf[2 * j + 1] = zsub(a[q], b[q]);
             }
         }
         __syncthreads();
         ns = 2;
+    } else if (lg % 3 == 2) {                        // one radix-4 stage
+        const int quarter = n >> 2;
+        double2 v[2 * MAXB][4];
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < quarter) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[q][i] = buf[j + i * quarter];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < quarter) {
+                dft4(v[q][0], v[q][1], v[q][2], v[q][3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) buf[4 * j + i] = v[q][i];
+            }
+        }
+        __syncthreads();
+        ns = 4;
     }
-    const int quarter = n >> 2;
-    for (; ns < n; ns <<= 2) {
-        double2 v[MAXB][4];
-        const int tstep = quarter / ns;              // e^{-2 pi i r k/(4 ns)} = tw[r k n/(4 ns)]
+    const int e = n >> 3;
+    for (; ns < n; ns <<= 3) {
+        double2 u[MAXB][8];
+        const int tstep = e / ns;                    // e^{-2 pi i q k/(8 ns)} = tw[q k n/(8 ns)]
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
-            if (j < quarter) {
-                const int k = j & (ns - 1);
-                v[q][0] = buf[j];
-                v[q][1] = zmul(buf[j + quarter], __ldg(tw + k * tstep));
-                v[q][2] = zmul(buf[j + 2 * quarter], __ldg(tw + 2 * k * tstep));
-                v[q][3] = zmul(buf[j + 3 * quarter], __ldg(tw + 3 * k * tstep));
+            if (j < e) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[q][i] = buf[j + i * e];
+                if (ns > 1) {
+                    const int k = j & (ns - 1);
+                    const double2 w1 = __ldg(tw + k * tstep), w2 = __ldg(tw + 2 * k * tstep), w4 = __ldg(tw + 4 * k * tstep);
+                    const double2 w3 = zmul(w1, w2), w5 = zmul(w1, w4), w6 = zmul(w2, w4);
+                    const double2 w7 = zmul(w3, w4);
+                    u[q][1] = zmul(u[q][1], w1);
+                    u[q][2] = zmul(u[q][2], w2);
+                    u[q][3] = zmul(u[q][3], w3);
+                    u[q][4] = zmul(u[q][4], w4);
+                    u[q][5] = zmul(u[q][5], w5);
+                    u[q][6] = zmul(u[q][6], w6);
+                    u[q][7] = zmul(u[q][7], w7);
+                }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
             const int j = threadIdx.x + q * nthr;
-            if (j < quarter) {
+            if (j < e) {
                 const int k = j & (ns - 1);
-                const int j0 = ((j - k) << 2) + k;
-                const double2 y0 = make_double2(v[q][0].x + v[q][2].x, v[q][0].y + v[q][2].y);
-                const double2 y1 = make_double2(v[q][0].x - v[q][2].x, v[q][0].y - v[q][2].y);
-                const double2 y2 = make_double2(v[q][1].x + v[q][3].x, v[q][1].y + v[q][3].y);
-                // -i (v1 - v3)
-                const double2 y3 = make_double2(v[q][1].y - v[q][3].y, -(v[q][1].x - v[q][3].x));
-                buf[j0] = make_double2(y0.x + y2.x, y0.y + y2.y);
-                buf[j0 + ns] = make_double2(y1.x + y3.x, y1.y + y3.y);
-                buf[j0 + 2 * ns] = make_double2(y0.x - y2.x, y0.y - y2.y);
-                buf[j0 + 3 * ns] = make_double2(y1.x - y3.x, y1.y - y3.y);
+                const int j0 = ((j - k) << 3) + k;
+                dft8(u[q]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) buf[j0 + i * ns] = u[q][i];
             }
         }
         __syncthreads();
@@ -146,6 +208,7 @@ struct DctArgs {
     // fused Poisson scaling (second forward pass; data is in the transposed layout: row = axis-1
     // frequency J, column = axis-0 frequency I): out /= 2 (cos(pi I / dimM) + cos(pi J / dimN) - 2)
     int fuse_scale, dimN, dimM;
+    const double *cos_col, *cos_row;   // cos(pi k / dimM), k < n ; cos(pi row / dimN), row < rows
     // fused <r, z> (last inverse pass): partial[row] = sum_c out[row][c] * dot_with[row][c]
     const double* dot_with;
     double* partial;
@@ -158,60 +221,89 @@ __device__ __forceinline__ double poisson_scale(int I, int J, int dimN, int dimM
     return 2.0 * (cospi((double)I / (double)dimM) + cospi((double)J / (double)dimN) - 2.0);
 }
 
-// forward DCT-II of every row:  y[k] = 2 sum_m x[m] cos(pi k (2m+1) / (2n))
+// Forward DCT-II of every row, y[k] = 2 sum_m x[m] cos(pi k (2m+1) / (2n)), by Makhoul's
+// permutation + one n-point complex FFT — of TWO rows at a time: rows 2b and 2b+1 ride in the real
+// and imaginary parts, Z = FFT(v_a + i v_b), V_a[k] = (Z[k] + conj Z[n-k]) / 2,
+// V_b[k] = (Z[k] - conj Z[n-k]) / 2i, y[k] = 2 Re(e^{-i pi k / 2n} V[k]).
 template <int MAXB>
-__global__ void __launch_bounds__(512, MAXB >= 4 ? 1 : 2) k_dct2_rows_pow2(const DctArgs a) {
+__global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_dct2_rows_pow2(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double2 cbuf[];
-    const int n = a.n, row = blockIdx.x;
-    const double* __restrict__ x = a.in + (size_t)row * n;
+    const int n = a.n, row = 2 * blockIdx.x;
+    const bool two = row + 1 < a.rows;
+    const double* __restrict__ xa = a.in + (size_t)row * n;
+    const double* __restrict__ xb = xa + n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double v = x[j];
         const int dst = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
-        cbuf[dst] = make_double2(v, 0.0);
+        cbuf[dst] = make_double2(xa[j], two ? xb[j] : 0.0);
     }
     __syncthreads();
     fft_pow2<MAXB>(cbuf, n, a.tw);
-    double* __restrict__ y = a.out + (size_t)row * n;
+    double* __restrict__ ya = a.out + (size_t)row * n;
+    double* __restrict__ yb = ya + n;
+    const double cra = a.fuse_scale ? a.cos_row[row] : 0.0;
+    const double crb = a.fuse_scale && two ? a.cos_row[row + 1] : 0.0;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double2 w = __ldg(a.mk + k), v = cbuf[k];
-        double r = 2.0 * (v.x * w.x - v.y * w.y);      // Re(e^{-i pi k/2n} V[k])
-        if (a.fuse_scale) r /= poisson_scale(k, row, a.dimN, a.dimM);
-        y[k] = r;
+        const double2 w = __ldg(a.mk + k), zk = cbuf[k], zn = cbuf[(n - k) & (n - 1)];
+        const double sx = zk.x + zn.x, sy = zk.y - zn.y;      // Z[k] + conj Z[n-k]
+        const double dx = zk.x - zn.x, dy = zk.y + zn.y;      // Z[k] - conj Z[n-k]
+        double ra = w.x * sx - w.y * sy;                      // Re(w (Z + conj Z'))
+        double rb = w.x * dy + w.y * dx;                      // Im(w (Z - conj Z'))
+        if (a.fuse_scale) {
+            // phase_unwrap.py:109: 2 (cos(pi I / M) + cos(pi J / N) - 2), [0,0] := 1  (I = k, J = row)
+            const double ck = a.cos_col[k];
+            ra /= (k == 0 && row == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
+            rb /= 2.0 * (ck + crb - 2.0);
+        }
+        ya[k] = ra;
+        if (two) yb[k] = rb;
     }
 }
 
-// inverse (scipy idct type 2, norm=None): x = dct2^{-1}(y)
+// inverse (scipy idct type 2, norm=None), two rows per FFT: with V[k] = e^{+i pi k/2n} (y[k] - i y[n-k]) / 2
+// the forward FFT of conj(V_a + i V_b) is n (v_a - i v_b)
 template <int MAXB>
-__global__ void __launch_bounds__(512, MAXB >= 4 ? 1 : 2) k_idct2_rows_pow2(const DctArgs a) {
+__global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double2 cbuf[];
     __shared__ double red[1024];
-    const int n = a.n, row = blockIdx.x;
-    const double* __restrict__ y = a.in + (size_t)row * n;
-    // V[k] = e^{+i pi k/2n} (y[k] - i y[n-k]) / 2 ; load conj(V) so the forward FFT yields conj(n v) (v is real)
+    const int n = a.n, row = 2 * blockIdx.x;
+    const bool two = row + 1 < a.rows;
+    const double* __restrict__ ya = a.in + (size_t)row * n;
+    const double* __restrict__ yb = ya + n;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double yk = y[k], ynk = k ? y[n - k] : 0.0;
         const double2 w = __ldg(a.mk + k);             // e^{-i pi k/2n} = (c, -s)
+        const double ak = ya[k], ank = k ? ya[n - k] : 0.0;
+        const double bk = two ? yb[k] : 0.0, bnk = (two && k) ? yb[n - k] : 0.0;
         // e^{+i t}(yk - i ynk) = (c yk + s ynk) + i (s yk - c ynk), with c = w.x, s = -w.y
-        const double re = 0.5 * (w.x * yk - w.y * ynk);
-        const double im = 0.5 * (-w.y * yk - w.x * ynk);
-        cbuf[k] = make_double2(re, -im);
+        const double re_a = 0.5 * (w.x * ak - w.y * ank), im_a = 0.5 * (-w.y * ak - w.x * ank);
+        const double re_b = 0.5 * (w.x * bk - w.y * bnk), im_b = 0.5 * (-w.y * bk - w.x * bnk);
+        cbuf[k] = make_double2(re_a - im_b, -im_a - re_b);   // conj(V_a) - i conj(V_b)
     }
     __syncthreads();
     fft_pow2<MAXB>(cbuf, n, a.tw);
-    double* __restrict__ x = a.out + (size_t)row * n;
+    double* __restrict__ xa = a.out + (size_t)row * n;
+    double* __restrict__ xb = xa + n;
     const double inv = 1.0 / (double)n;
-    double dot = 0.0;
+    double dot_a = 0.0, dot_b = 0.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const int src = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
-        const double v = cbuf[src].x * inv;
-        x[j] = v;
-        if (a.dot_with) dot = fma(v, a.dot_with[(size_t)row * n + j], dot);
+        const double2 f = cbuf[src];
+        const double va = f.x * inv, vb = -f.y * inv;
+        xa[j] = va;
+        if (two) xb[j] = vb;
+        if (a.dot_with) {
+            dot_a = fma(va, a.dot_with[(size_t)row * n + j], dot_a);
+            if (two) dot_b = fma(vb, a.dot_with[(size_t)(row + 1) * n + j], dot_b);
+        }
     }
     if (a.dot_with) {
-        const double s = block_sum(dot, red);
-        if (threadIdx.x == 0) a.partial[row] = s;
+        const double sa = block_sum(dot_a, red);
+        const double sb = block_sum(dot_b, red);
+        if (threadIdx.x == 0) {
+            a.partial[row] = sa;
+            if (two) a.partial[row + 1] = sb;
+        }
     }
 }
 
@@ -449,6 +541,7 @@ struct UwPlan {
     int N, M;
     double *r, *z, *t, *p, *q, *wwx, *wwy, *partial;
     AxisTables axN, axM;
+    double *cosI, *cosJ;      // cos(pi I / M), I < N ; cos(pi J / N), J < M   (phase_unwrap.py:109, swapped on purpose)
     UwScalars* sc;
     int npart;
 };
@@ -469,6 +562,8 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
         ax->mk = a.take<double2>(n);
         ax->ct = a.take<double>(ax->pow2 ? 1 : 4 * (size_t)n);
     }
+    u.cosI = a.take<double>(N);
+    u.cosJ = a.take<double>(M);
     u.sc = a.take<UwScalars>(1);
     return a.off;
 }
@@ -477,20 +572,19 @@ template <int INVERSE>
 static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
     a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n;
     if (ax.pow2) {
-        const int quarter = ax.n / 4 > 0 ? ax.n / 4 : 1;
-        // two radix-4 butterflies per thread where the row is long enough (ILP), at most 512 threads
-        int threads = quarter >= 128 ? quarter / 2 : quarter;
-        threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
-        const int per = (quarter + threads - 1) / threads;  // radix-4 butterflies per thread
+        const int eighth = ax.n / 8 > 0 ? ax.n / 8 : 1;
+        // one radix-8 butterfly per thread, two for the longest rows (at most 512 threads)
+        const int threads = eighth < 32 ? 32 : (eighth > 512 ? 512 : eighth);
+        const int per = (eighth + threads - 1) / threads;
         const size_t smem = (size_t)ax.n * sizeof(double2);
+        const int ctas = (a.rows + 1) / 2;           // two rows per FFT
         auto go = [&](auto kern) -> int {
             GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
-            kern<<<a.rows, threads, smem, st>>>(a);
+            kern<<<ctas, threads, smem, st>>>(a);
             return GPA_OK;
         };
         if (per <= 1) return INVERSE ? go(k_idct2_rows_pow2<1>) : go(k_dct2_rows_pow2<1>);
-        if (per <= 2) return INVERSE ? go(k_idct2_rows_pow2<2>) : go(k_dct2_rows_pow2<2>);
-        return INVERSE ? go(k_idct2_rows_pow2<4>) : go(k_dct2_rows_pow2<4>);
+        return INVERSE ? go(k_idct2_rows_pow2<2>) : go(k_dct2_rows_pow2<2>);
     }
     GPA_REQUIRE((size_t)ax.n * sizeof(double) <= 200 * 1024, "axis of length %d is too long for the direct DCT", ax.n);
     const size_t smem = (size_t)ax.n * sizeof(double);
@@ -516,6 +610,7 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
     if ((rc = launch_rows<0>(u.axM, a, st))) return rc;
     transpose(u.z, u.t, N, M, u.sc, st);                                   // t: (M, N)
     a.in = u.t; a.out = u.z; a.rows = M; a.fuse_scale = 1;                 // rows along axis 0, then / scale
+    a.cos_col = u.cosI; a.cos_row = u.cosJ;
     if ((rc = launch_rows<0>(u.axN, a, st))) return rc;
     a.fuse_scale = 0;
     a.in = u.z; a.out = u.t; a.rows = M;                                   // inverse along axis 0
@@ -556,6 +651,8 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
         const int cnt = ax->pow2 ? ax->n : 4 * ax->n;
         k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, ax->pow2);
     }
+    k_uw_cos_table<<<ceil_div(N, 256), 256, 0, st>>>(u.cosI, N, M);
+    k_uw_cos_table<<<ceil_div(M, 256), 256, 0, st>>>(u.cosJ, M, N);
     dim3 g2(ceil_div(M, 64), ceil_div(N, 4));
     const int n2 = g2.x * g2.y;
     GPA_REQUIRE(n2 <= u.npart && N <= u.npart, "frame too large for the reduction scratch");

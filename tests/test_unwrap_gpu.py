@@ -76,6 +76,17 @@ def test_oracle_parity_fixed_iteration_count(shape):
     assert np.abs(got.cpu().numpy() - ref).max() < 1e-9
 
 
+@pytest.mark.parametrize("shape", [(33, 64), (16, 1024), (8, 2048), (4, 8192), (2, 4), (512, 512), (64, 4096)])
+def test_fft_stage_plans_and_row_pairs(shape):
+    """Every FFT stage plan of the row kernels (leading radix-2 / radix-4 stage, 1-4 radix-8 stages, two
+    butterflies per thread at n = 8192), an odd number of rows (the last FFT carries one row) and tiny
+    axes, weighted, against the oracle after 3 iterations."""
+    psi, w = _case(shape, 3 + sum(shape), 0.05)
+    ref = oracle.phase_unwrap(psi, w, kmax=3)
+    got = PU.phase_unwrap(psi, w, kmax=3)
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("shape", [(128, 128), (96, 80)])
 def test_oracle_parity_to_convergence(shape):
     """Run to the 1e-9 stop.  CG iterates of two float64 implementations drift apart by rounding
