@@ -553,7 +553,9 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     u.r = a.take<double>(nm); u.z = a.take<double>(nm); u.t = a.take<double>(nm);
     u.p = a.take<double>(nm); u.q = a.take<double>(nm);
     u.wwx = a.take<double>(nm); u.wwy = a.take<double>(nm);
-    u.npart = 16384;
+    // per-CTA partial sums: the stencil kernels use one CTA per 4 x 64 pixels, the row kernels one value per row
+    const size_t tiles = (size_t)ceil_div(M, 64) * ceil_div(N, 4);
+    u.npart = (int)(tiles > 16384 ? tiles : 16384);
     u.partial = a.take<double>(u.npart);
     for (AxisTables* ax : {&u.axN, &u.axM}) {
         const int n = ax == &u.axN ? N : M;
@@ -655,7 +657,7 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     k_uw_cos_table<<<ceil_div(M, 256), 256, 0, st>>>(u.cosJ, M, N);
     dim3 g2(ceil_div(M, 64), ceil_div(N, 4));
     const int n2 = g2.x * g2.y;
-    GPA_REQUIRE(n2 <= u.npart && N <= u.npart, "frame too large for the reduction scratch");
+    GPA_REQUIRE(n2 <= u.npart && N <= u.npart && M <= u.npart, "frame too large for the reduction scratch");
     const int g1 = (int)((nm + 2047) / 2048 < 4096 ? (nm + 2047) / 2048 : 4096);
     {
         SetupArgs s;
