@@ -24,7 +24,10 @@ constexpr int kMaxFftLen = 8192;   // 16 B * 8192 = 128 KB of shared memory per 
 struct UwScalars {
     double rz, rz_prev, pqp, r0sq, rsq, alpha, beta;
     int done, k, kmax, pad;
+    unsigned ticket[4];      // "last CTA finishes the reduction" counters, one per reducing kernel
 };
+
+enum { kTicketInit = 0, kTicketBeta = 1, kTicketAlpha = 2, kTicketStop = 3 };
 
 __device__ __forceinline__ double wrap_pi_d(double v) {
     const double two_pi = 2.0 * kPi;
@@ -33,17 +36,45 @@ __device__ __forceinline__ double wrap_pi_d(double v) {
     return t * two_pi - kPi;
 }
 
+// sum over the CTA (any multiple of 32 threads up to 1024); sh needs 32 doubles
 __device__ __forceinline__ double block_sum(double v, double* sh) {
-    const int t = threadIdx.x;
-    sh[t] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
+    if (lane == 0) sh[warp] = v;
     __syncthreads();
-    for (int k = blockDim.x >> 1; k > 0; k >>= 1) {
-        if (t < k) sh[t] += sh[t + k];
-        __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) sh[0] = r;
     }
-    const double r = sh[0];
+    __syncthreads();
+    r = sh[0];
     __syncthreads();
     return r;
+}
+
+// Tail of every reducing kernel: each CTA has written its partial sums; the CTA that takes the last
+// ticket adds up all n partials (fixed order: the result does not depend on which CTA is last) and
+// applies the scalar update `fin(total)` — the PCG scalars never need a launch of their own.
+template <typename Fin>
+__device__ __forceinline__ void finish_reduction(unsigned* ticket, const double* part, int n, double* sh, Fin fin) {
+    __shared__ int s_last;
+    __threadfence();                       // this CTA's partials are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;   // ... before its ticket
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(part + i);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        fin(s);
+        *ticket = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -212,8 +243,16 @@ struct DctArgs {
     // fused <r, z> (last inverse pass): partial[row] = sum_c out[row][c] * dot_with[row][c]
     const double* dot_with;
     double* partial;
-    const UwScalars* sc;
+    UwScalars* sc;
 };
+
+// <r, z> is complete: k += 1, beta = rz / rz_prev (phase_unwrap.py:188-193)
+__device__ __forceinline__ void sc_beta(UwScalars* sc, double s) {
+    sc->k += 1;
+    sc->rz = s;
+    sc->beta = (sc->k == 1) ? 0.0 : s / sc->rz_prev;
+    sc->rz_prev = s;
+}
 
 __device__ __forceinline__ double poisson_scale(int I, int J, int dimN, int dimM) {
     // phase_unwrap.py:109: 2 (cos(pi I / M) + cos(pi J / N) - 2), [0,0] := 1
@@ -266,7 +305,7 @@ template <int MAXB>
 __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double2 cbuf[];
-    __shared__ double red[1024];
+    __shared__ double red[32];
     const int n = a.n, row = 2 * blockIdx.x;
     const bool two = row + 1 < a.rows;
     const double* __restrict__ ya = a.in + (size_t)row * n;
@@ -304,6 +343,8 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(cons
             a.partial[row] = sa;
             if (two) a.partial[row + 1] = sb;
         }
+        UwScalars* sc = a.sc;
+        finish_reduction(&sc->ticket[kTicketBeta], a.partial, a.rows, red, [sc](double s) { sc_beta(sc, s); });
     }
 }
 
@@ -312,7 +353,7 @@ template <int INVERSE>
 __global__ void k_dct2_rows_direct(const DctArgs a) {
     if (a.sc->done) return;
     extern __shared__ double rbuf[];
-    __shared__ double red[1024];
+    __shared__ double red[32];
     const int n = a.n, row = blockIdx.x, n4 = 4 * n;
     const double* __restrict__ in = a.in + (size_t)row * n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) rbuf[j] = in[j];
@@ -347,6 +388,8 @@ __global__ void k_dct2_rows_direct(const DctArgs a) {
     if (INVERSE && a.dot_with) {
         const double s = block_sum(dot, red);
         if (threadIdx.x == 0) a.partial[row] = s;
+        UwScalars* sc = a.sc;
+        finish_reduction(&sc->ticket[kTicketBeta], a.partial, a.rows, red, [sc](double t) { sc_beta(sc, t); });
     }
 }
 
@@ -372,7 +415,8 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
 struct SetupArgs {
     const double *psi, *dx, *dy, *weight;   // psi (N,M) or dx (N,M-1) & dy (N-1,M); weight (N,M) or null
     double *wwx, *wwy, *r, *phi, *partial;
-    int N, M;
+    UwScalars* sc;
+    int N, M, kmax;
 };
 
 __device__ __forceinline__ double edge_w(const double* w, size_t i, size_t j) {
@@ -382,96 +426,57 @@ __device__ __forceinline__ double edge_w(const double* w, size_t i, size_t j) {
 }
 
 // weighted right-hand side r = A^T W^T W b, edge weights, phi = 0        (phase_unwrap.py:154-176)
+constexpr int kUwRows = 32;     // rows per CTA of the stencil kernels (4 rows x 64 columns per step)
+
 __global__ void __launch_bounds__(256) k_uw_setup(const SetupArgs a) {
-    __shared__ double red[256];
+    __shared__ double red[32];
     const int N = a.N, M = a.M;
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     double rsq = 0.0;
-    if (r < N && c < M) {
-        const size_t i = (size_t)r * M + c;
-        auto bx = [&](int rr, int cc) -> double {      // wrapped difference along axis 1 at (rr, cc), cc < M-1
-            const double d = a.psi ? a.psi[(size_t)rr * M + cc + 1] - a.psi[(size_t)rr * M + cc]
-                                   : a.dx[(size_t)rr * (M - 1) + cc];
-            return wrap_pi_d(d);
-        };
-        auto by = [&](int rr, int cc) -> double {      // along axis 0 at (rr, cc), rr < N-1
-            const double d = a.psi ? a.psi[(size_t)(rr + 1) * M + cc] - a.psi[(size_t)rr * M + cc]
-                                   : a.dy[(size_t)rr * M + cc];
-            return wrap_pi_d(d);
-        };
-        double v = 0.0;
-        if (c < M - 1) {
-            const double w = edge_w(a.weight, i, i + 1);
-            a.wwx[(size_t)r * (M - 1) + c] = w;
-            v += w * bx(r, c);
+    auto bx = [&](int rr, int cc) -> double {      // wrapped difference along axis 1 at (rr, cc), cc < M-1
+        const double d = a.psi ? a.psi[(size_t)rr * M + cc + 1] - a.psi[(size_t)rr * M + cc]
+                               : a.dx[(size_t)rr * (M - 1) + cc];
+        return wrap_pi_d(d);
+    };
+    auto by = [&](int rr, int cc) -> double {      // along axis 0 at (rr, cc), rr < N-1
+        const double d = a.psi ? a.psi[(size_t)(rr + 1) * M + cc] - a.psi[(size_t)rr * M + cc]
+                               : a.dy[(size_t)rr * M + cc];
+        return wrap_pi_d(d);
+    };
+    for (int it = 0; it < kUwRows / 4; ++it) {
+        const int r = blockIdx.y * kUwRows + it * 4 + (threadIdx.x >> 6);
+        if (r < N && c < M) {
+            const size_t i = (size_t)r * M + c;
+            double v = 0.0;
+            if (c < M - 1) {
+                const double w = edge_w(a.weight, i, i + 1);
+                a.wwx[(size_t)r * (M - 1) + c] = w;
+                v += w * bx(r, c);
+            }
+            if (c > 0) v -= edge_w(a.weight, i - 1, i) * bx(r, c - 1);
+            if (r < N - 1) {
+                const double w = edge_w(a.weight, i, i + M);
+                a.wwy[i] = w;
+                v += w * by(r, c);
+            }
+            if (r > 0) v -= edge_w(a.weight, i - M, i) * by(r - 1, c);
+            a.r[i] = v;
+            a.phi[i] = 0.0;
+            rsq = fma(v, v, rsq);
         }
-        if (c > 0) v -= edge_w(a.weight, i - 1, i) * bx(r, c - 1);
-        if (r < N - 1) {
-            const double w = edge_w(a.weight, i, i + M);
-            a.wwy[i] = w;
-            v += w * by(r, c);
-        }
-        if (r > 0) v -= edge_w(a.weight, i - M, i) * by(r - 1, c);
-        a.r[i] = v;
-        a.phi[i] = 0.0;
-        rsq = v * v;
     }
     const double s = block_sum(rsq, red);
     if (threadIdx.x == 0) a.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
-}
-
-// single-CTA scalar updates ------------------------------------------------------------------
-__device__ __forceinline__ double sum_partials(const double* part, int n, double* sh) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
-    return block_sum(s, sh);
-}
-
-__global__ void k_sc_init(UwScalars* sc, const double* part, int n, int kmax) {
-    __shared__ double sh[1024];
-    const double s = sum_partials(part, n, sh);
-    if (threadIdx.x == 0) {
-        sc->r0sq = s;
-        sc->rsq = s;
+    UwScalars* sc = a.sc;
+    const int kmax = a.kmax;
+    finish_reduction(&sc->ticket[kTicketInit], a.partial, gridDim.x * gridDim.y, red, [sc, kmax](double t) {
+        sc->r0sq = t;
+        sc->rsq = t;
         sc->rz = sc->rz_prev = sc->pqp = sc->alpha = sc->beta = 0.0;
         sc->k = 0;
         sc->kmax = kmax;
-        sc->done = (s == 0.0);        // `while not all(rk == 0)`: nothing to do
-    }
-}
-
-__global__ void k_sc_beta(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[1024];
-    if (sc->done) return;
-    const double s = sum_partials(part, n, sh);
-    if (threadIdx.x == 0) {
-        sc->k += 1;
-        sc->rz = s;
-        sc->beta = (sc->k == 1) ? 0.0 : s / sc->rz_prev;      // phase_unwrap.py:189-193
-        sc->rz_prev = s;
-    }
-}
-
-__global__ void k_sc_alpha(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[1024];
-    if (sc->done) return;
-    const double s = sum_partials(part, n, sh);
-    if (threadIdx.x == 0) {
-        sc->pqp = s;
-        sc->alpha = sc->rz / s;                                 // :201
-    }
-}
-
-__global__ void k_sc_stop(UwScalars* sc, const double* part, int n) {
-    __shared__ double sh[1024];
-    if (sc->done) return;
-    const double s = sum_partials(part, n, sh);
-    if (threadIdx.x == 0) {
-        sc->rsq = s;
-        // :206  k >= kmax or |r| < 1e-9 |r0| ; and the loop condition `not all(r == 0)`
-        if (sc->k >= sc->kmax || sqrt(s) < 1e-9 * sqrt(sc->r0sq) || s == 0.0) sc->done = 1;
-    }
+        sc->done = (t == 0.0);        // `while not all(rk == 0)`: nothing to do
+    });
 }
 
 // p = z + beta p  (first iteration: p = z)
@@ -487,33 +492,39 @@ __global__ void __launch_bounds__(256) k_uw_update_p(const double* __restrict__ 
 // q = Q p = A^T W^T W A p (phase_unwrap.py:118-132) and partial sums of <p, q>
 __global__ void __launch_bounds__(256) k_uw_apply_q(const double* __restrict__ p, const double* __restrict__ wwx,
                                                     const double* __restrict__ wwy, double* __restrict__ q,
-                                                    double* __restrict__ partial, int N, int M, const UwScalars* sc) {
+                                                    double* __restrict__ partial, int N, int M, UwScalars* sc) {
     if (sc->done) return;
-    __shared__ double red[256];
+    __shared__ double red[32];
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     double pq = 0.0;
-    if (r < N && c < M) {
-        const size_t i = (size_t)r * M + c;
-        const double pc = p[i];
-        double v = 0.0;
-        if (c < M - 1) v += wwx[(size_t)r * (M - 1) + c] * (p[i + 1] - pc);
-        if (c > 0) v -= wwx[(size_t)r * (M - 1) + c - 1] * (pc - p[i - 1]);
-        if (r < N - 1) v += wwy[i] * (p[i + M] - pc);
-        if (r > 0) v -= wwy[i - M] * (pc - p[i - M]);
-        q[i] = v;
-        pq = pc * v;
+    for (int it = 0; it < kUwRows / 4; ++it) {
+        const int r = blockIdx.y * kUwRows + it * 4 + (threadIdx.x >> 6);
+        if (r < N && c < M) {
+            const size_t i = (size_t)r * M + c;
+            const double pc = p[i];
+            double v = 0.0;
+            if (c < M - 1) v += wwx[(size_t)r * (M - 1) + c] * (p[i + 1] - pc);
+            if (c > 0) v -= wwx[(size_t)r * (M - 1) + c - 1] * (pc - p[i - 1]);
+            if (r < N - 1) v += wwy[i] * (p[i + M] - pc);
+            if (r > 0) v -= wwy[i - M] * (pc - p[i - M]);
+            q[i] = v;
+            pq = fma(pc, v, pq);
+        }
     }
     const double s = block_sum(pq, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    finish_reduction(&sc->ticket[kTicketAlpha], partial, gridDim.x * gridDim.y, red, [sc](double t) {
+        sc->pqp = t;
+        sc->alpha = sc->rz / t;                                 // phase_unwrap.py:201
+    });
 }
 
 // phi += alpha p ; r -= alpha q ; partial sums of r^2
 __global__ void __launch_bounds__(256) k_uw_update_xr(double* __restrict__ phi, double* __restrict__ r,
                                                       const double* __restrict__ p, const double* __restrict__ q,
-                                                      double* __restrict__ partial, size_t n, const UwScalars* sc) {
+                                                      double* __restrict__ partial, size_t n, UwScalars* sc) {
     if (sc->done) return;
-    __shared__ double red[256];
+    __shared__ double red[32];
     const double alpha = sc->alpha;
     double rs = 0.0;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
@@ -524,6 +535,11 @@ __global__ void __launch_bounds__(256) k_uw_update_xr(double* __restrict__ phi, 
     }
     const double s = block_sum(rs, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    finish_reduction(&sc->ticket[kTicketStop], partial, gridDim.x, red, [sc](double t) {
+        sc->rsq = t;
+        // :206  k >= kmax or |r| < 1e-9 |r0| ; and the loop condition `not all(r == 0)`
+        if (sc->k >= sc->kmax || sqrt(t) < 1e-9 * sqrt(sc->r0sq) || t == 0.0) sc->done = 1;
+    });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,8 +569,8 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     u.r = a.take<double>(nm); u.z = a.take<double>(nm); u.t = a.take<double>(nm);
     u.p = a.take<double>(nm); u.q = a.take<double>(nm);
     u.wwx = a.take<double>(nm); u.wwy = a.take<double>(nm);
-    // per-CTA partial sums: the stencil kernels use one CTA per 4 x 64 pixels, the row kernels one value per row
-    const size_t tiles = (size_t)ceil_div(M, 64) * ceil_div(N, 4);
+    // per-CTA partial sums: the stencil kernels use one CTA per kUwRows x 64 pixels, the row kernels one value per row
+    const size_t tiles = (size_t)ceil_div(M, 64) * ceil_div(N, kUwRows);
     u.npart = (int)(tiles > 16384 ? tiles : 16384);
     u.partial = a.take<double>(u.npart);
     for (AxisTables* ax : {&u.axN, &u.axM}) {
@@ -655,7 +671,7 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     }
     k_uw_cos_table<<<ceil_div(N, 256), 256, 0, st>>>(u.cosI, N, M);
     k_uw_cos_table<<<ceil_div(M, 256), 256, 0, st>>>(u.cosJ, M, N);
-    dim3 g2(ceil_div(M, 64), ceil_div(N, 4));
+    dim3 g2(ceil_div(M, 64), ceil_div(N, kUwRows));
     const int n2 = g2.x * g2.y;
     GPA_REQUIRE(n2 <= u.npart && N <= u.npart && M <= u.npart, "frame too large for the reduction scratch");
     const int g1 = (int)((nm + 2047) / 2048 < 4096 ? (nm + 2047) / 2048 : 4096);
@@ -663,9 +679,10 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
         SetupArgs s;
         s.psi = psi; s.dx = dx; s.dy = dy; s.weight = weight;
         s.wwx = u.wwx; s.wwy = u.wwy; s.r = u.r; s.phi = phi; s.partial = u.partial; s.N = N; s.M = M;
+        s.sc = u.sc; s.kmax = kmax;
         KernelTimer timer("uw_setup", st);
+        GPA_CHECK_CUDA(cudaMemsetAsync(u.sc, 0, sizeof(UwScalars), st));     // done = 0, tickets = 0
         k_uw_setup<<<g2, 256, 0, st>>>(s);
-        k_sc_init<<<1, 1024, 0, st>>>(u.sc, u.partial, n2, kmax);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     // The reference always runs at least one iteration (k is tested after the update), so kmax <= 1
@@ -675,14 +692,11 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     for (int k = 0; k < iters; ++k) {
         int rc = poisson_solve(u, st);                       // t = z
         if (rc) return rc;
-        k_sc_beta<<<1, 1024, 0, st>>>(u.sc, u.partial, N);
         {
             KernelTimer timer("uw_vector_ops", st);
             k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
             k_uw_apply_q<<<g2, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
-            k_sc_alpha<<<1, 1024, 0, st>>>(u.sc, u.partial, n2);
             k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
-            k_sc_stop<<<1, 1024, 0, st>>>(u.sc, u.partial, g1);
         }
         GPA_CHECK_CUDA(cudaGetLastError());
         if ((k & 7) == 7 && k + 1 < iters) {                 // stop enqueueing once converged

@@ -42,7 +42,7 @@ def unwrap(psi=None, dx=None, dy=None, weight=None, kmax=100, return_iters=False
     iters = ctypes.c_int(0)
     _lib.check(lib.gpa_unwrap_pcg(_ptr(psi), _ptr(dx), _ptr(dy), _ptr(weight), n, m, int(kmax), _ptr(phi),
                                   ctypes.byref(iters) if return_iters else None, _ptr(ws), ws.numel(), _stream()))
-    _count(4 + 12 * max(1, int(kmax)))
+    _count(5 + 9 * max(1, int(kmax)))
     return (phi, iters.value) if return_iters else phi
 
 
