@@ -272,6 +272,33 @@ int gpa_props_from_jac(const double* jac, size_t npix, double refangle, double r
                        int add_identity, double* props, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6 — device pieces of the k-vector refinement loop (float64), SURVEY 8(f) row 2.
+ *
+ * Replaces, inside iterate_GPA (geometric_phase_analysis.py:116-154): np.angle / np.abs on the
+ * cropped lock-in (:134-139), sqrt(w / w.max()) (:141), and mathtools.fit_plane (mathtools.py:30-47,
+ * scipy.optimize.least_squares(loss='huber')) behind fit_delta_k (:92-94).
+ * ------------------------------------------------------------------------------------------ */
+
+/* phases = angle(lockin)[edge:N-edge, edge:M-edge], amp = abs(...) likewise (contiguous
+ * (N-2 edge, M-2 edge) arrays), *amp_max = max(amp) (device scalar, reset by the call). */
+int gpa_lockin_phase_amp(const void* lockin, int is_f64, int N, int M, int edge,
+                         double* phases, double* amp, double* amp_max /*device*/, void* stream);
+
+/* out = sqrt(amp / *amp_max): the unwrap weight of iterate_GPA. */
+int gpa_weight_sqrt_norm(const double* amp, const double* amp_max /*device*/, size_t n, double* out, void* stream);
+
+int gpa_fit_plane_workspace_bytes(size_t* bytes);
+
+/* Huber-loss plane fit img[x, y] ~ theta[0] x + theta[1] y + theta[2] (x, y array indices,
+ * f_scale = 1 in the reference) by iteratively reweighted least squares on the device: each step is
+ * one streaming reduction, the 3x3 solve runs in the kernel.  Stops when the plane moves by less than
+ * tol anywhere on the frame or after max_iter steps.  theta (3 doubles) and iterations are HOST
+ * outputs (the caller's k-vector update is host arithmetic); the call synchronises the stream. */
+int gpa_fit_plane_huber(const double* img, int n, int m, double f_scale, int max_iter, double tol,
+                        double* theta /*host*/, int* iterations /*host or NULL*/,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2 — weighted least-squares phase unwrapping (Ghiglia-Romero PCG, DCT Poisson preconditioner),
  * float64 throughout.
  *

@@ -67,6 +67,31 @@ def gen_props(gpa, pu):
         out_props_from_J=pe.props_from_J(J_iso, refangle=-1.5, refscale=0.7))
 
 
+def gen_iterate(gpa, pu):
+    """iterate_GPA (geometric_phase_analysis.py:116-154) and mathtools.fit_plane (mathtools.py:30-47):
+    a 96 x 80 lattice whose true k-vectors are 3 % off the ones handed to iterate_GPA."""
+    import pyGPA.mathtools as mt
+    shape = (96, 80)
+    ks_true = synth.primary_ks(0.1, 7.0, 3)
+    ks_guess = ks_true * 1.03
+    u = synth.gaussian_bump(shape) * 0.5
+    img = synth.lattice_image(shape, ks_true, u, noise=0.2, seed=21)
+    img = img - img.mean()
+    sigma = 6
+    prs, w, corr = gpa.iterate_GPA(img, ks_guess, sigma, edge=4, iters=2, kmax_iter=15, kmax=60)
+    prs0, w0, corr0 = gpa.iterate_GPA(img, ks_guess, sigma, edge=0, iters=1, kmax_iter=10, kmax=20)
+    rng = np.random.default_rng(4)
+    xx, yy = np.meshgrid(np.arange(70), np.arange(50), indexing='ij')
+    plane = 0.31 * xx - 0.17 * yy + 2.5 + 0.4 * rng.normal(size=xx.shape)
+    out = rng.uniform(size=xx.shape) < 0.08
+    plane[out] += 15 * rng.normal(size=out.sum())
+    np.savez_compressed(os.path.join(OUT, "iterate_96x80.npz"), in_image=img, in_ks=ks_guess, in_ks_true=ks_true,
+                        in_sigma=sigma, out_prs=prs, out_w=w, out_corr=corr,
+                        out_prs_edge0=prs0, out_w_edge0=w0, out_corr_edge0=corr0,
+                        in_plane=plane, out_plane_fit=mt.fit_plane(plane),
+                        out_delta_k=gpa.fit_delta_k(plane))
+
+
 def gen_base(gpa, pu):
     # ---- adaptive sweep: wfr2_grad_opt + optwfr2, non-square frame, 3 peaks -------------
     shape = (64, 48)
@@ -166,7 +191,7 @@ def gen_base(gpa, pu):
         out_undistorted=gpa.undistort_image(img_l, u_l))
 
 
-SECTIONS = {"base": gen_base, "wfr4": gen_wfr4, "props": gen_props}
+SECTIONS = {"base": gen_base, "wfr4": gen_wfr4, "props": gen_props, "iterate": gen_iterate}
 
 
 def main(argv=None):

@@ -15,7 +15,7 @@ TWO_PI = 2.0 * np.pi
 
 __all__ = [
     "wrap_to_pi", "gaussian_transfer", "lockin_fixed", "candidate_axes", "wfr_sweep",
-    "wfr_sweep_klist", "wfr4", "wfr4_allowed", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
+    "wfr_sweep_klist", "wfr4", "wfr4_allowed", "fit_plane", "iterate_GPA", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
     "reconstruct_u_inv", "reconstruct_u_inv_from_phases", "invert_u_overlap",
     "undistort_image", "extract_displacement_field", "fixed_reference_pipeline",
 ]
@@ -366,6 +366,35 @@ def extract_displacement_field(image, kvecs, sigma=None, kwscale=2.5, ksteps=3,
     weights = np.stack([np.abs(g['lockin']) for g in gs]) * (mask + 1e-6)
     u = reconstruct_u_inv_from_phases(kvecs, phases, weights)
     return (u, gs) if return_gs else u
+
+
+def fit_plane(image):
+    """mathtools.py:30-47: plane a[0] x + a[1] y + a[2] through `image`, Huber loss with scipy's
+    default f_scale = 1, minimised by scipy.optimize.least_squares from a zero start."""
+    import scipy.optimize as spo
+    image = np.asarray(image, dtype=np.float64)
+    xx, yy = np.meshgrid(np.arange(image.shape[0]), np.arange(image.shape[1]), indexing='ij')
+
+    def resid(x):
+        return (image - (x[0] * xx + x[1] * yy + x[2])).ravel()
+    return spo.least_squares(resid, np.zeros(3), loss='huber').x
+
+
+def iterate_GPA(image, kvecs, sigma, edge=5, iters=3, kmax_iter=25, kmax=200):
+    """geometric_phase_analysis.py:116-154."""
+    kvecs = np.asarray(kvecs, dtype=np.float64)
+    corr = np.zeros_like(kvecs)
+    sl = (slice(edge, -edge), slice(edge, -edge)) if edge > 0 else (slice(None), slice(None))
+    for i in range(iters + 1):
+        rs = [lockin_fixed(image, k, sigma) for k in kvecs + corr]
+        prs = [np.angle(r)[sl] for r in rs]
+        w = np.stack([np.abs(r)[sl] for r in rs])
+        if i < iters:
+            prs = [phase_unwrap(p, np.sqrt(we / we.max()), kmax=kmax_iter) for p, we in zip(prs, w)]
+            corr -= np.stack([fit_plane(p)[:2] / TWO_PI for p in prs])
+        else:
+            prs = np.stack([phase_unwrap(p, np.sqrt(we / we.max()), kmax=kmax) for p, we in zip(prs, w)])
+    return prs, w, corr
 
 
 def fixed_reference_pipeline(image, kvecs, sigma, kmax=100, weighted=True):

@@ -56,6 +56,11 @@ SIGNATURES = {
     "gpa_phasegradient_to_j": (c_int, [c_void_p, c_void_p, c_int, c_int, _pd, _pd, ctypes.POINTER(c_int), c_int, c_int,
                                        c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
     "gpa_props_from_jac": (c_int, [c_void_p, c_size_t, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "gpa_lockin_phase_amp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gpa_weight_sqrt_norm": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gpa_fit_plane_workspace_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
+    "gpa_fit_plane_huber": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double, _pd, ctypes.POINTER(c_int),
+                                    c_void_p, c_size_t, c_void_p]),
     "gpa_norm_axis0": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

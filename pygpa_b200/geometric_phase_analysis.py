@@ -13,10 +13,10 @@ import torch
 from . import cuGPA as _cu
 from . import engine, solvers
 from .cuGPA import _sweep, _to_host
-from .mathtools import wrapToPi  # noqa: F401  (re-exported like the reference does)
+from .mathtools import fit_plane, wrapToPi  # noqa: F401  (re-exported like the reference does)
 
 __all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_only_lockin_vec",
-           "wfr2_grad_opt", "wfr2_grad", "wfr2_grad_vec", "wfr3", "wfr4", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
+           "wfr2_grad_opt", "wfr2_grad", "wfr2_grad_vec", "wfr3", "wfr4", "fit_delta_k", "iterate_GPA", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
            "extract_displacement_field", "invert_u", "invert_u_overlap", "undistort_image"]
 
 
@@ -112,6 +112,44 @@ def wfr2_only_lockin_vec(image, sigma, kx, ky, kw, kstep):
 def wfr2_grad_vec(image, sigma, kx, ky, kw, kstep):
     """geometric_phase_analysis.py:816-836: dask-batched wfr2_grad_opt, same result."""
     return wfr2_grad_opt(image, sigma, kx, ky, kw, kstep)
+
+
+# ----------------------------------------------------------------------------------------------
+# k-vector refinement (K1 fixed lock-in + K2 + K6)
+# ----------------------------------------------------------------------------------------------
+def fit_delta_k(phases):
+    """geometric_phase_analysis.py:92-94: slope of the Huber plane through an unwrapped phase, in cycles."""
+    return fit_plane(phases)[:2] / (2 * np.pi)
+
+
+def iterate_GPA(image, kvecs, sigma, edge=5, iters=3, kmax_iter=25, kmax=200, verbose=False):
+    """Iterate the GPA procedure, moving the reference vectors to the extracted average
+    (geometric_phase_analysis.py:116-154).  Returns (prs, w, corr): the final unwrapped phases
+    (d, N-2 edge, M-2 edge), their weights |lock-in| and the correction with kvecs + corr the k-vectors
+    used last.  Everything per pixel stays on the device; only the three plane coefficients per
+    k-vector and iteration come back to update the k-vectors."""
+    dev = engine.require_cuda()
+    img = engine.image_to_device(image, dev)
+    kvecs = np.asarray(kvecs, dtype=np.float64)
+    corr = np.zeros_like(kvecs)
+    for i in range(iters + 1):
+        last = i == iters
+        prs, ws, deltas = [], [], []
+        for ks in kvecs + corr:
+            r = engine.lockin_fixed(img, ks, sigma)
+            ph, amp, amax = solvers.lockin_phase_amp(r, edge if edge > 0 else 0)
+            un = solvers.unwrap(psi=ph, weight=solvers.weight_sqrt_norm(amp, amax), kmax=kmax if last else kmax_iter)
+            if last:
+                prs.append(un)
+                ws.append(amp)
+            else:
+                deltas.append(solvers.fit_plane_huber(un)[:2] / (2 * np.pi))
+        if not last:
+            delta_ks = np.stack(deltas)
+            if verbose:
+                print(delta_ks)
+            corr -= delta_ks
+    return _host(torch.stack(prs)), _host(torch.stack(ws)), corr
 
 
 # ----------------------------------------------------------------------------------------------

@@ -111,6 +111,46 @@ def props_from_jac(jac, refangle=0.0, refscale=1.0, diff=False, add_identity=Fal
     return out
 
 
+def lockin_phase_amp(lockin, edge=0):
+    """(angle, abs, max abs) of a complex lock-in tensor cropped by `edge` on every side
+    (iterate_GPA, geometric_phase_analysis.py:134-139); the max stays on the device."""
+    lib = _lib.load()
+    n, m = int(lockin.shape[0]), int(lockin.shape[1])
+    shape = (n - 2 * edge, m - 2 * edge)
+    ph = torch.empty(shape, dtype=torch.float64, device=lockin.device)
+    amp = torch.empty(shape, dtype=torch.float64, device=lockin.device)
+    amax = torch.empty(1, dtype=torch.float64, device=lockin.device)
+    _lib.check(lib.gpa_lockin_phase_amp(_ptr(lockin), int(lockin.dtype == torch.complex128), n, m, int(edge),
+                                        _ptr(ph), _ptr(amp), _ptr(amax), _stream()))
+    _count(1)
+    return ph, amp, amax
+
+
+def weight_sqrt_norm(amp, amax):
+    """sqrt(amp / max amp) (geometric_phase_analysis.py:141)."""
+    lib = _lib.load()
+    out = torch.empty_like(amp)
+    _lib.check(lib.gpa_weight_sqrt_norm(_ptr(amp), _ptr(amax), amp.numel(), _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
+def fit_plane_huber(img, f_scale=1.0, max_iter=500, tol=1e-11, return_iters=False):
+    """Huber plane fit of a float64 CUDA image: host array [a_x, a_y, b] with img ~ a_x x + a_y y + b
+    (mathtools.py:30-47)."""
+    lib = _lib.load()
+    n, m = int(img.shape[0]), int(img.shape[1])
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.gpa_fit_plane_workspace_bytes(ctypes.byref(nbytes)))
+    ws = workspace(nbytes.value, img.device)
+    theta = np.zeros(3)
+    iters = ctypes.c_int(0)
+    _lib.check(lib.gpa_fit_plane_huber(_ptr(img), n, m, float(f_scale), int(max_iter), float(tol), _lib.as_pd(theta),
+                                       ctypes.byref(iters), _ptr(ws), ws.numel(), _stream()))
+    _count(iters.value)
+    return (theta, iters.value) if return_iters else theta
+
+
 def norm_axis0(w):
     lib = _lib.load()
     out = torch.empty(w.shape[1:], dtype=torch.float64, device=w.device)

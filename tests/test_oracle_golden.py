@@ -49,6 +49,27 @@ def test_wfr4_matches_reference_fixture():
     assert a.shape == (49, 49) and a.diagonal().all() and np.array_equal(a, a.T)
 
 
+def test_iterate_gpa_and_plane_fit_match_reference_fixture():
+    g = load_golden("iterate_96x80.npz")
+    assert np.allclose(oracle.fit_plane(g["in_plane"]), g["out_plane_fit"], rtol=1e-9, atol=1e-10)
+    prs, w, corr = oracle.iterate_GPA(g["in_image"], g["in_ks"], int(g["in_sigma"]), edge=4, iters=2, kmax_iter=15, kmax=60)
+    assert np.allclose(prs, g["out_prs"], rtol=1e-8, atol=1e-8)
+    assert np.allclose(w, g["out_w"], **TIGHT) and np.allclose(corr, g["out_corr"], rtol=1e-8, atol=1e-11)
+
+
+def test_props_oracle_matches_reference_fixture():
+    g = load_golden("props_64x48.npz")
+    ks, grads, w, nm = g["in_ks_ani"], g["in_grads"], g["in_weights"], float(g["in_nmperpixel"])
+    tol = dict(rtol=1e-9, atol=1e-12)
+    assert np.allclose(oracle.phasegradient2J(ks, grads, w, nm), g["out_J_iso"], **tol)
+    assert np.allclose(oracle.phasegradient2J(ks, grads, w, nm, iso_ref=False), g["out_J_plain"], **tol)
+    assert np.allclose(oracle.phasegradient2J(ks, grads, w, nm, sort=-1), g["out_J_sorted_neg"], **tol)
+    assert np.allclose(oracle.phasegradient2J(ks, grads, g["in_weights_rankdef"], nm), g["out_J_rankdef"], **tol)
+    assert np.allclose(oracle.phasegradient2Jac(ks, grads, w, nm), g["out_Jac"], **tol)
+    assert np.array_equal(oracle.props_from_Jac(g["out_Jac"]), g["out_props"])
+    assert np.array_equal(oracle.props_from_J(g["out_J_iso"], refangle=-1.5, refscale=0.7), g["out_props_from_J"])
+
+
 def test_tail_matches_reference_fixture():
     g = load_golden("tail_64x48.npz")
     ks, ph, w = g["in_ks"], g["in_phases"], g["in_weights"]
