@@ -339,6 +339,29 @@ int gpa_resample_image(const double* img, int N, int M, const double* u_inv, dou
 int gpa_undistort_image(const double* img, const double* u, int N, int M, int iters, double* out,
                         void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K7 — unit-cell averaging (float64), SURVEY 8(f) row 4.
+ *
+ * Replaces unit_cell_average (unit_cell_averaging.py:132-205, numba loop with add_to_position
+ * :208-217) and expand_unitcell (:234-249, scipy map_coordinates).  The host passes what
+ * calc_ucell_parameters (:45-53) derives from the two k-vectors: ks (2,2) row-major, its inverse,
+ * the lower cell corner rmin and the zoomed cell array size (rs0, rs1).
+ * ------------------------------------------------------------------------------------------ */
+int gpa_uc_workspace_bytes(int rs0, int rs1, size_t* bytes);
+
+/* out (rs0, rs1) = drizzle average of img (N, M) [displaced by u (2, N, M), may be NULL] over the unit
+ * cell, zoom z; NaN pixels of img are skipped, cells nothing landed on are NaN (0 / 0). */
+int gpa_uc_average(const double* img, const double* u, int N, int M,
+                   const double* ks /*host*/, const double* kinv /*host*/, const double* rmin /*host*/,
+                   double z, int rs0, int rs1, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* out (H, W) = cubic-spline (order 3, mode 'constant', cval 0) samples of the NaN-cleared cell image
+ * ucell (n, m) at the folded coordinates of r / z2 + u (u (2, H, W), or NULL with the scalar u_const). */
+int gpa_uc_expand(const double* ucell, int n, int m, int H, int W, const double* u, double u_const,
+                  double z2, const double* ks /*host*/, const double* kinv /*host*/,
+                  const double* rmin /*host*/, double z, double* out,
+                  void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

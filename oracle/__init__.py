@@ -15,3 +15,4 @@ reference checkout is present, against the live reference in
 """
 from .ref_numpy import *  # noqa: F401,F403
 from .props_numpy import *  # noqa: F401,F403
+from .ucell_numpy import *  # noqa: F401,F403

@@ -92,6 +92,34 @@ def gen_iterate(gpa, pu):
                         out_delta_k=gpa.fit_delta_k(plane))
 
 
+def gen_ucell(gpa, pu):
+    """unit_cell_average / expand_unitcell (unit_cell_averaging.py:132-249), the constructions of the
+    reference's tests/test_unit_cell_averaging.py at reduced size (r_k = 0.05, 96 x 80, z = 2 and 3)."""
+    import pyGPA.unit_cell_averaging as uc
+    shape = (96, 80)
+    ks3 = synth.primary_ks(0.05, 7.0, 3)
+    ks = ks3[:2]
+    u = synth.gaussian_bump(shape) * 0.8
+    img = synth.lattice_image(shape, ks3, None, second_order=0.3)
+    img = img / img.max()
+    img_d = synth.lattice_image(shape, ks3, u, second_order=0.3)
+    img_d = img_d / img_d.max()
+    img_nan = img.copy()
+    img_nan[10:30, 20:50] = np.nan
+    out = {}
+    for z in (2, 3):
+        cell = uc.unit_cell_average(img, ks, z=z)
+        out[f"out_cell_z{z}"] = cell
+        out[f"out_expand_z{z}"] = uc.expand_unitcell(cell, ks, shape, z=z)
+        cell_d = uc.unit_cell_average(img_d, ks, z=z, u=u)
+        out[f"out_cell_def_z{z}"] = cell_d
+        out[f"out_expand_def_z{z}"] = uc.expand_unitcell(cell_d, ks, shape, z=z, u=u)
+    out["out_cell_nan"] = uc.unit_cell_average(img_nan, ks, z=2)
+    out["out_expand_z2_zoom"] = uc.expand_unitcell(out["out_cell_z2"], ks, (120, 100), z=2, z2=1.5)
+    np.savez_compressed(os.path.join(OUT, "ucell_96x80.npz"), in_image=img, in_image_def=img_d, in_image_nan=img_nan,
+                        in_ks=ks, in_u=u, **out)
+
+
 def gen_base(gpa, pu):
     # ---- adaptive sweep: wfr2_grad_opt + optwfr2, non-square frame, 3 peaks -------------
     shape = (64, 48)
@@ -191,7 +219,7 @@ def gen_base(gpa, pu):
         out_undistorted=gpa.undistort_image(img_l, u_l))
 
 
-SECTIONS = {"base": gen_base, "wfr4": gen_wfr4, "props": gen_props, "iterate": gen_iterate}
+SECTIONS = {"base": gen_base, "wfr4": gen_wfr4, "props": gen_props, "iterate": gen_iterate, "ucell": gen_ucell}
 
 
 def main(argv=None):

@@ -61,6 +61,11 @@ SIGNATURES = {
     "gpa_fit_plane_workspace_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
     "gpa_fit_plane_huber": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double, _pd, ctypes.POINTER(c_int),
                                     c_void_p, c_size_t, c_void_p]),
+    "gpa_uc_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "gpa_uc_average": (c_int, [c_void_p, c_void_p, c_int, c_int, _pd, _pd, _pd, c_double, c_int, c_int, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "gpa_uc_expand": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_double, c_double, _pd, _pd, _pd,
+                              c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_norm_axis0": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

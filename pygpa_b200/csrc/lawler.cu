@@ -356,3 +356,174 @@ extern "C" int gpa_undistort_image(const double* img, const double* u, int N, in
     if (rc) return rc;
     return gpa_resample_image(img, N, M, u_inv, out, rest, ws_bytes - used, stream);
 }
+
+// ==============================================================================================
+// K7 — unit-cell averaging: pyGPA/unit_cell_averaging.py:132-249
+// ==============================================================================================
+// unit_cell_average: every pixel r (+ u(r)) is folded into the unit cell spanned by the two
+// k-vectors ks — fractional coordinates f = (r + u) ks^T mod 1, cartesian R = z (f ks^-T - rmin) — and
+// dropped "drizzle like" onto the 2 x 2 cluster of cells around R (:208-217).  A scatter-add: fp64
+// atomics into the (small, L2-resident) cell array; the order of the additions is not fixed, so
+// results agree with the reference to rounding (1e-13 relative), not bit for bit.
+// expand_unitcell (:234-249) is the gather back: the K4 cubic-spline evaluation (mode='constant')
+// of the NaN-cleared cell at the folded coordinate of every output pixel.
+namespace gpa {
+
+struct UcGeom {
+    double ks[2][2], kinv[2][2], rmin[2], z;
+};
+
+__device__ __forceinline__ void fold_into_cell(const UcGeom& g, double x, double y, double& R0, double& R1) {
+    double f0 = x * g.ks[0][0] + y * g.ks[0][1];         // forward_transform: vecs @ ks.T
+    double f1 = x * g.ks[1][0] + y * g.ks[1][1];
+    f0 -= floor(f0);                                     // % 1.
+    f1 -= floor(f1);
+    R0 = (f0 * g.kinv[0][0] + f1 * g.kinv[0][1] - g.rmin[0]) * g.z;   // backward_transform, - rmin, * z
+    R1 = (f0 * g.kinv[1][0] + f1 * g.kinv[1][1] - g.rmin[1]) * g.z;
+}
+
+__global__ void __launch_bounds__(256) k_uc_scatter(const double* __restrict__ img, const double* __restrict__ u, int N, int M,
+                                                    const UcGeom g, int rs0, int rs1, double* __restrict__ res,
+                                                    double* __restrict__ weights) {
+    const size_t total = (size_t)N * M;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const double v = img[i];
+        if (isnan(v)) continue;                          // NaN masks a pixel (:194)
+        const int r = (int)(i / M), c = (int)(i % M);
+        double x = (double)r, y = (double)c;
+        if (u) {
+            x += u[i];
+            y += u[total + i];
+        }
+        double R0, R1;
+        fold_into_cell(g, x, y, R0, R1);
+        const double fl0 = floor(R0), fl1 = floor(R1);
+        const double f0 = R0 - fl0, f1 = R1 - fl1;
+        const int i0 = (int)fl0, i1 = (int)fl1;
+        // float_overlap (:37-42) as written: overlap[li][lj] = (lj ? f0 : 1 - f0) * (li ? f1 : 1 - f1)
+#pragma unroll
+        for (int li = 0; li < 2; ++li)
+#pragma unroll
+            for (int lj = 0; lj < 2; ++lj) {
+                const int a = i0 + li, b = i1 + lj;
+                if (a < 0 || a >= rs0 || b < 0 || b >= rs1) continue;    // the reference would write out of bounds
+                const double w = (lj ? f0 : 1.0 - f0) * (li ? f1 : 1.0 - f1);
+                atomicAdd(res + (size_t)a * rs1 + b, v * w);
+                atomicAdd(weights + (size_t)a * rs1 + b, w);
+            }
+    }
+}
+
+// res / weights (NaN where nothing landed), or with clear_nan the NaN-cleared copy expand_unitcell filters
+__global__ void k_uc_divide(const double* __restrict__ res, const double* __restrict__ weights, size_t n, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = res[i] / weights[i];
+}
+
+__global__ void k_nan_to_num(const double* __restrict__ in, size_t n, double* __restrict__ out) {
+    const double big = 1.7976931348623157e308;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = in[i];
+        out[i] = isnan(v) ? 0.0 : (isinf(v) ? copysign(big, v) : v);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_uc_expand(const double* __restrict__ coef, int n, int m, int H, int W,
+                                                   const double* __restrict__ u, double u_const, double z2, const UcGeom g,
+                                                   double* __restrict__ out) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (r >= H || c >= W) return;
+    const size_t i = (size_t)r * W + c;
+    double x = (double)r / z2, y = (double)c / z2;              // np.mgrid / z2
+    if (u) {
+        x += u[i];
+        y += u[(size_t)H * W + i];
+    } else {
+        x += u_const;
+        y += u_const;
+    }
+    double R0, R1;
+    fold_into_cell(g, x, y, R0, R1);
+    double v = 0.0;
+    if (R0 >= 0.0 && R0 <= (double)(n - 1) && R1 >= 0.0 && R1 <= (double)(m - 1)) v = spline_eval<kConstant>(coef, n, m, R0, R1);
+    out[i] = v;
+}
+
+static void fill_geom(UcGeom& g, const double* ks, const double* kinv, const double* rmin, double z) {
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            g.ks[i][j] = ks[2 * i + j];
+            g.kinv[i][j] = kinv[2 * i + j];
+        }
+    g.rmin[0] = rmin[0]; g.rmin[1] = rmin[1]; g.z = z;
+}
+
+}  // namespace gpa
+
+extern "C" int gpa_uc_workspace_bytes(int rs0, int rs1, size_t* bytes) {
+    GPA_REQUIRE(bytes && rs0 >= 1 && rs1 >= 1, "bad argument");
+    *bytes = 4 * ((size_t)rs0 * rs1 * sizeof(double) + 256) + 1024;
+    return GPA_OK;
+}
+
+extern "C" int gpa_uc_average(const double* img, const double* u /*(2,N,M) or null*/, int N, int M,
+                              const double* ks /*host 4*/, const double* kinv /*host 4*/, const double* rmin /*host 2*/,
+                              double z, int rs0, int rs1, double* out /*(rs0, rs1)*/, void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(img && ks && kinv && rmin && out && ws, "null pointer argument");
+    GPA_REQUIRE(N >= 1 && M >= 1 && rs0 >= 1 && rs1 >= 1, "bad shape");
+    size_t need = 0;
+    gpa_uc_workspace_bytes(rs0, rs1, &need);
+    if (ws_bytes < need) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)rs0 * rs1;
+    Arena a(ws, ws_bytes);
+    double* res = a.take<double>(n);
+    double* wts = a.take<double>(n);
+    GPA_CHECK_CUDA(cudaMemsetAsync(res, 0, n * sizeof(double), st));
+    GPA_CHECK_CUDA(cudaMemsetAsync(wts, 0, n * sizeof(double), st));
+    UcGeom g;
+    fill_geom(g, ks, kinv, rmin, z);
+    size_t blocks = ((size_t)N * M + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    {
+        KernelTimer t("k_uc_scatter", st);
+        k_uc_scatter<<<(unsigned)blocks, 256, 0, st>>>(img, u, N, M, g, rs0, rs1, res, wts);
+    }
+    k_uc_divide<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(res, wts, n, out);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_uc_expand(const double* ucell /*(n, m)*/, int n, int m, int H, int W, const double* u /*(2,H,W) or null*/,
+                             double u_const, double z2, const double* ks, const double* kinv, const double* rmin, double z,
+                             double* out /*(H, W)*/, void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(ucell && ks && kinv && rmin && out && ws, "null pointer argument");
+    GPA_REQUIRE(n >= 2 && m >= 2 && H >= 1 && W >= 1 && z2 != 0.0, "bad argument");
+    size_t need = 0;
+    gpa_uc_workspace_bytes(n, m, &need);
+    if (ws_bytes < need) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t cnt = (size_t)n * m;
+    Arena a(ws, ws_bytes);
+    double* clean = a.take<double>(cnt);
+    double* coef = a.take<double>(cnt);
+    double* t0 = a.take<double>(cnt);
+    double* t1 = a.take<double>(cnt);
+    k_nan_to_num<<<(unsigned)((cnt + 255) / 256 < 1184 ? (cnt + 255) / 256 : 1184), 256, 0, st>>>(ucell, cnt, clean);   // np.nan_to_num (:246)
+    int rc = prefilter_2d(clean, n, m, 1.0, kConstant, coef, 1, 0, t0, t1, st);
+    if (rc) return rc;
+    UcGeom g;
+    fill_geom(g, ks, kinv, rmin, z);
+    KernelTimer t("k_uc_expand", st);
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8));
+    k_uc_expand<<<grid, 256, 0, st>>>(coef, n, m, H, W, u, u_const, z2, g, out);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}

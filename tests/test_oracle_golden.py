@@ -70,6 +70,23 @@ def test_props_oracle_matches_reference_fixture():
     assert np.array_equal(oracle.props_from_J(g["out_J_iso"], refangle=-1.5, refscale=0.7), g["out_props_from_J"])
 
 
+def test_unit_cell_oracle_matches_reference_fixture():
+    g = load_golden("ucell_96x80.npz")
+    ks, u, shape = g["in_ks"], g["in_u"], g["in_image"].shape
+    for z in (2, 3):
+        c = oracle.unit_cell_average(g["in_image"], ks, z=z)
+        assert np.array_equal(np.isnan(c), np.isnan(g[f"out_cell_z{z}"]))
+        assert np.allclose(c, g[f"out_cell_z{z}"], rtol=1e-12, atol=1e-13, equal_nan=True)
+        assert np.allclose(oracle.expand_unitcell(g[f"out_cell_z{z}"], ks, shape, z=z), g[f"out_expand_z{z}"], **TIGHT)
+        c = oracle.unit_cell_average(g["in_image_def"], ks, u=u, z=z)
+        assert np.allclose(c, g[f"out_cell_def_z{z}"], rtol=1e-12, atol=1e-13, equal_nan=True)
+        assert np.allclose(oracle.expand_unitcell(g[f"out_cell_def_z{z}"], ks, shape, z=z, u=u),
+                           g[f"out_expand_def_z{z}"], **TIGHT)
+    assert np.allclose(oracle.unit_cell_average(g["in_image_nan"], ks, z=2), g["out_cell_nan"], rtol=1e-12, atol=1e-13,
+                       equal_nan=True)
+    assert np.allclose(oracle.expand_unitcell(g["out_cell_z2"], ks, (120, 100), z=2, z2=1.5), g["out_expand_z2_zoom"], **TIGHT)
+
+
 def test_tail_matches_reference_fixture():
     g = load_golden("tail_64x48.npz")
     ks, ph, w = g["in_ks"], g["in_phases"], g["in_weights"]
