@@ -362,6 +362,18 @@ int gpa_uc_expand(const double* ucell, int n, int m, int H, int W, const double*
                   const double* rmin /*host*/, double z, double* out,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8 — gaussian_deconvolve (float64), SURVEY 8(f) row 3.
+ *
+ * Replaces gaussian_deconvolve (geometric_phase_analysis.py:892-904): every (N, M) plane of `data` is
+ * reflect-padded by 2 dr, filtered with skimage's Wiener filter for the Gaussian PSF of std sigma
+ * (W = H / (H^2 + balance L^2) on the DFT grid of the padded frame) and cropped back.  The padded
+ * axes (N + 4 dr, M + 4 dr) may have any length up to 4096 (Bluestein transforms in shared memory).
+ * ------------------------------------------------------------------------------------------ */
+int gpa_deconvolve_workspace_bytes(int N, int M, int dr, size_t* bytes);
+int gpa_gaussian_deconvolve(const double* data, int planes, int N, int M, double sigma, int dr,
+                            double balance, double* out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ check the CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 product package ``pygpa_b200`` never does (tests/test_no_oracle_in_product.py
 enforces that).
 
-Parity status: PINNED.  ``tests/golden/*.npz`` were produced by the unmodified
+Parity status: PINNED (except oracle/wiener_numpy.py, whose third-party arithmetic — scikit-image's
+Wiener filter — is absent here: that module says "parity unpinned" in its header).  ``tests/golden/*.npz`` were produced by the unmodified
 reference functions (``oracle/gen_golden.py`` imports ``/root/reference``); the
 oracle is asserted against them in ``tests/test_oracle_golden.py`` and, when the
 reference checkout is present, against the live reference in
@@ -16,3 +17,4 @@ reference checkout is present, against the live reference in
 from .ref_numpy import *  # noqa: F401,F403
 from .props_numpy import *  # noqa: F401,F403
 from .ucell_numpy import *  # noqa: F401,F403
+from .wiener_numpy import *  # noqa: F401,F403

@@ -66,6 +66,9 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "gpa_uc_expand": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_double, c_double, _pd, _pd, _pd,
                               c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_deconvolve_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "gpa_gaussian_deconvolve": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_double, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
     "gpa_norm_axis0": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

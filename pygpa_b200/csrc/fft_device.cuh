@@ -1,0 +1,135 @@
+// Shared-memory FFT used by K2 (DCT rows, unwrap.cu) and the Wiener deconvolution (wiener.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gpa {
+
+// ------------------------------------------------------------------------------------------
+// in-place Stockham FFT of buf[0..n) (forward, e^{-2 pi i jk/n}); all threads of the CTA.
+// Radix-8 stages (a third of the shared-memory round trips of radix 2), preceded by one radix-2 or
+// radix-4 stage when log2(n) is not a multiple of 3.  Every stage reads all its inputs into
+// registers, synchronises, and writes in autosort order: no second buffer.  MAXB = radix-8
+// butterflies per thread (blockDim.x * MAXB >= n / 8); tw[t] = e^{-2 pi i t/n}, t < n.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 zmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 zmul_mi(double2 a) { return make_double2(a.y, -a.x); }     // -i a
+
+// x <- DFT_4(x), natural order
+__device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
+    const double2 t0 = zadd(x0, x2), t1 = zsub(x0, x2), t2 = zadd(x1, x3), t3 = zmul_mi(zsub(x1, x3));
+    x0 = zadd(t0, t2);
+    x1 = zadd(t1, t3);
+    x2 = zsub(t0, t2);
+    x3 = zsub(t1, t3);
+}
+
+// u <- DFT_8(u), natural order
+__device__ __forceinline__ void dft8(double2 (&u)[8]) {
+    const double r = 0.70710678118654752440084436210485;
+    double2 a0 = zadd(u[0], u[4]), a1 = zadd(u[1], u[5]), a2 = zadd(u[2], u[6]), a3 = zadd(u[3], u[7]);
+    double2 b0 = zsub(u[0], u[4]), b1 = zsub(u[1], u[5]), b2 = zsub(u[2], u[6]), b3 = zsub(u[3], u[7]);
+    b1 = make_double2(r * (b1.x + b1.y), r * (b1.y - b1.x));       // * e^{-i pi/4}
+    b2 = zmul_mi(b2);                                              // * e^{-i pi/2}
+    b3 = make_double2(r * (b3.y - b3.x), -r * (b3.x + b3.y));      // * e^{-3 i pi/4}
+    dft4(a0, a1, a2, a3);
+    dft4(b0, b1, b2, b3);
+    u[0] = a0; u[1] = b0; u[2] = a1; u[3] = b1; u[4] = a2; u[5] = b2; u[6] = a3; u[7] = b3;
+}
+
+template <int MAXB>
+__device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __restrict__ tw) {
+    const int nthr = blockDim.x;
+    const int lg = 31 - __clz(n);
+    int ns = 1;
+    if (lg % 3 == 1) {                               // one radix-2 stage (ns = 1: twiddles are 1)
+        const int half = n >> 1;
+        double2 a[4 * MAXB], b[4 * MAXB];
+#pragma unroll
+        for (int q = 0; q < 4 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                a[q] = buf[j];
+                b[q] = buf[j + half];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < half) {
+                buf[2 * j] = zadd(a[q], b[q]);
+                buf[2 * j + 1] = zsub(a[q], b[q]);
+            }
+        }
+        __syncthreads();
+        ns = 2;
+    } else if (lg % 3 == 2) {                        // one radix-4 stage
+        const int quarter = n >> 2;
+        double2 v[2 * MAXB][4];
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < quarter) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[q][i] = buf[j + i * quarter];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2 * MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < quarter) {
+                dft4(v[q][0], v[q][1], v[q][2], v[q][3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) buf[4 * j + i] = v[q][i];
+            }
+        }
+        __syncthreads();
+        ns = 4;
+    }
+    const int e = n >> 3;
+    for (; ns < n; ns <<= 3) {
+        double2 u[MAXB][8];
+        const int tstep = e / ns;                    // e^{-2 pi i q k/(8 ns)} = tw[q k n/(8 ns)]
+#pragma unroll
+        for (int q = 0; q < MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < e) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[q][i] = buf[j + i * e];
+                if (ns > 1) {
+                    const int k = j & (ns - 1);
+                    const double2 w1 = __ldg(tw + k * tstep), w2 = __ldg(tw + 2 * k * tstep), w4 = __ldg(tw + 4 * k * tstep);
+                    const double2 w3 = zmul(w1, w2), w5 = zmul(w1, w4), w6 = zmul(w2, w4);
+                    const double2 w7 = zmul(w3, w4);
+                    u[q][1] = zmul(u[q][1], w1);
+                    u[q][2] = zmul(u[q][2], w2);
+                    u[q][3] = zmul(u[q][3], w3);
+                    u[q][4] = zmul(u[q][4], w4);
+                    u[q][5] = zmul(u[q][5], w5);
+                    u[q][6] = zmul(u[q][6], w6);
+                    u[q][7] = zmul(u[q][7], w7);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < MAXB; ++q) {
+            const int j = threadIdx.x + q * nthr;
+            if (j < e) {
+                const int k = j & (ns - 1);
+                const int j0 = ((j - k) << 3) + k;
+                dft8(u[q]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) buf[j0 + i * ns] = u[q][i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gpa

@@ -17,7 +17,7 @@ from .mathtools import fit_plane, wrapToPi  # noqa: F401  (re-exported like the 
 
 __all__ = ["GPA", "optGPA", "vecGPA", "wfr", "wfr2", "optwfr2", "wfr2_only_lockin", "wfr2_only_lockin_vec",
            "wfr2_grad_opt", "wfr2_grad", "wfr2_grad_vec", "wfr3", "wfr4", "fit_delta_k", "iterate_GPA", "myweighed_lstsq", "reconstruct_u_inv", "reconstruct_u_inv_from_phases",
-           "extract_displacement_field", "invert_u", "invert_u_overlap", "undistort_image"]
+           "extract_displacement_field", "invert_u", "invert_u_overlap", "undistort_image", "gaussian_deconvolve"]
 
 
 def optGPA(image, kvec, sigma=22):
@@ -236,6 +236,14 @@ def undistort_image(deformed, u):
     return _host(solvers.undistort(solvers.to_device_f64(deformed, dev), solvers.to_device_f64(u, dev)))
 
 
+def gaussian_deconvolve(data, sigma, dr=20, balance=5000):
+    """Deconvolve a stack of images `data` (..., N, M) with a Gaussian kernel of std sigma: reflect padding
+    by 2 dr, Wiener filter (scikit-image's, with its Laplacian regulariser), crop
+    (geometric_phase_analysis.py:892-904)."""
+    dev = engine.require_cuda()
+    return _host(solvers.gaussian_deconvolve(solvers.to_device_f64(data, dev), sigma, dr, balance))
+
+
 _DEVICE_SWEEPS = {}
 
 
@@ -246,10 +254,8 @@ def extract_displacement_field(image, kvecs, sigma=None, kwscale=2.5, ksteps=3, 
     With one of this package's sweeps as ``wfr_func`` (the default) the whole chain — sweep per
     k-vector, phases and masked weights, per-pixel least squares, PCG integration — stays on the
     GPU and only u comes back.  Any other callable is invoked exactly like the reference does and
-    its NumPy results are uploaded for the tail.  deconvolve=True needs scikit-image's Wiener
-    filter, which is outside this package: NotImplementedError."""
-    if deconvolve:
-        raise NotImplementedError("deconvolve=True (skimage Wiener deconvolution) is not part of the B200 hot path")
+    its NumPy results are uploaded for the tail.  deconvolve=True applies gaussian_deconvolve to u
+    (on the device as well)."""
     dev = engine.require_cuda()
     image = np.asarray(image, dtype=np.float64)
     kvecs = np.asarray(kvecs, dtype=np.float64)
@@ -272,6 +278,8 @@ def extract_displacement_field(image, kvecs, sigma=None, kwscale=2.5, ksteps=3, 
             phs.append(ph)
             wts.append(wt)
         u = solvers.displacement_from_phases(kvecs, torch.stack(phs), torch.stack(wts))
+        if deconvolve:
+            u = solvers.gaussian_deconvolve(u, sigma, dr)
         return _host(u)
     gs = [wfr_func(centred, sigma, pk[0], pk[1], kw=kw, kstep=kstep) for pk in kvecs]
     phases = np.stack([np.angle(g['lockin']) for g in gs])
@@ -279,6 +287,8 @@ def extract_displacement_field(image, kvecs, sigma=None, kwscale=2.5, ksteps=3, 
     mask[dr:-dr, dr:-dr] = 1.
     weights = np.stack([np.abs(g['lockin']) for g in gs]) * (mask + 1e-6)
     u = reconstruct_u_inv_from_phases(kvecs, phases, weights)
+    if deconvolve:
+        u = gaussian_deconvolve(u, sigma, dr)
     if return_gs:
         return u, gs
     return u

@@ -151,6 +151,23 @@ def fit_plane_huber(img, f_scale=1.0, max_iter=500, tol=1e-11, return_iters=Fals
     return (theta, iters.value) if return_iters else theta
 
 
+def gaussian_deconvolve(data, sigma, dr=20, balance=5000.0):
+    """Wiener deconvolution of every trailing (N, M) plane of a float64 CUDA tensor with the Gaussian of
+    std sigma (geometric_phase_analysis.py:892-904), on the device."""
+    lib = _lib.load()
+    n, m = int(data.shape[-2]), int(data.shape[-1])
+    planes = int(data.numel() // (n * m))
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.gpa_deconvolve_workspace_bytes(n, m, int(dr), ctypes.byref(nbytes)))
+    ws = workspace(nbytes.value, data.device)
+    data = data.contiguous()
+    out = torch.empty_like(data)
+    _lib.check(lib.gpa_gaussian_deconvolve(_ptr(data), planes, n, m, float(sigma), int(dr), float(balance), _ptr(out),
+                                           _ptr(ws), ws.numel(), _stream()))
+    _count(4 + 7 * planes)
+    return out
+
+
 def norm_axis0(w):
     lib = _lib.load()
     out = torch.empty(w.shape[1:], dtype=torch.float64, device=w.device)

@@ -70,8 +70,10 @@ def test_extract_displacement_field_golden():
         assert np.abs(u - g["out_u_edf"]).max() < DISP_TOL
     u_cu = GPA.extract_displacement_field(img, ks, sigma=sigma, wfr_func=cuGPA.wfr2_grad_opt)
     assert np.abs(u_cu - g["out_u_edf"]).max() < DISP_TOL
-    with pytest.raises(NotImplementedError):
-        GPA.extract_displacement_field(img, ks, deconvolve=True)
+    # deconvolve=True (geometric_phase_analysis.py:928-929): the Wiener step applied to the reference's u
+    u_dec = GPA.extract_displacement_field(img, ks, sigma=sigma, deconvolve=True)
+    ref_dec = oracle.gaussian_deconvolve(g["out_u_edf"], sigma, 2 * sigma)
+    assert np.abs(u_dec - ref_dec).max() < DISP_TOL
 
 
 def test_displacement_field_accuracy_like_reference_test():
