@@ -41,4 +41,4 @@ def test_constant_field_is_preserved_and_oversize_is_refused():
     with pytest.raises(GpaError):
         GPA.gaussian_deconvolve(np.zeros((4100, 64)), 4, 8)
     with pytest.raises(GpaError):
-        GPA.gaussian_deconvolve(np.zeros((20, 64)), 4, 8)                          # reflect padding wider than the frame
+        GPA.gaussian_deconvolve(np.zeros((12, 64)), 4, 8)                          # reflect padding wider than the frame
