@@ -359,6 +359,21 @@ constexpr int kMrTX = 64;     // k_mr_interp tile: rows
 constexpr int kMrTY = 128;    //                   columns
 constexpr int kPmB = 8;       // bound blocks for the pruning: kPmB x kPmB coarse cells
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct MrPass1Params {
     const float* img;
     const float2* phy;
@@ -392,9 +407,10 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
         for (int j = lane; j < n_samp; j += 32) {
             int c = cbase + j;
             if (c >= M) c %= M;
-            tile[j * SP + rr] = __ldg(row + c);
+            cp_async4(tile + j * SP + rr, row + c);       // transposing fill, every copy in flight at once
         }
     }
+    cp_async_commit();
     const int pl0 = blockIdx.z * prm.planes_per_cta;
     const int pl1 = min(pl0 + prm.planes_per_cta, prm.count);
     auto stage_carrier = [&](int pl, int slot) {
@@ -407,6 +423,7 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
         }
     };
     stage_carrier(pl0, 0);
+    cp_async_wait_all();
     __syncthreads();
     const float* col = tile + (S * warp * kP) * SP + lane;
     const int r = r0 + lane;
@@ -466,9 +483,14 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     const int plane = prm.plane0 + pl * prm.pstep;
     const int J = prm.J;
     const int n_samp = S * (WARPS * kP + J + kAhead + 1);
-    {
-        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
-        for (int j = threadIdx.x >> 5; j < n_samp; j += GROUPS * WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
+    {   // plane tile: rows of 32 float2 = 256 B, all copies in flight at once (cp.async, 16 B each: with a
+        // load + store per row the fill was one DRAM round trip per row and warp, ~15 % of the CTA's life)
+        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0;
+        for (int i = threadIdx.x; i < n_samp * (kLanes / 2); i += GROUPS * WARPS * 32) {
+            const int j = i / (kLanes / 2), c = 2 * (i % (kLanes / 2));
+            cp_async16(smem + j * kLanes + c, src + (size_t)j * prm.pitch_d + c);
+        }
+        cp_async_commit();
     }
     const float2* col = smem + (S * warp * kP) * kLanes + lane;
     const int my = my0 + lane;
@@ -478,10 +500,12 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     auto stage_carrier = [&](int c, int slot) {
         const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * mx0;
         float2* dst = sph + slot * n_samp;
-        for (int j = tig; j < n_samp; j += GT) dst[j] = __ldg(ph + j);
+        for (int j = tig; j < n_samp; j += GT) cp_async8(dst + j, ph + j);
+        cp_async_commit();
     };
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory"); };
     if (group < prm.n_cand) stage_carrier(group, 0);
+    cp_async_wait_all();
     __syncthreads();
     int slot = 0;
     for (int c = group; c < prm.n_cand; c += GROUPS, slot ^= 1) {
@@ -518,6 +542,7 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
                 prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
                          (my0 + lane) / kPmB] = a2max[hb];
         }
+        cp_async_wait_all();
         group_sync();     // this group's next carrier is complete; the current one is no longer read
     }
 }
@@ -538,9 +563,14 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     const int pl = blockIdx.z;
     const int plane = prm.plane0 + pl * prm.pstep;
     constexpr int n_samp = S * (WARPS * kP + JT);
-    {
-        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0 + lane;
-        for (int j = threadIdx.x >> 5; j < n_samp; j += GROUPS * WARPS) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch_d);
+    {   // plane tile: rows of 32 float2 = 256 B, all copies in flight at once (cp.async, 16 B each: with a
+        // load + store per row the fill was one DRAM round trip per row and warp, ~15 % of the CTA's life)
+        const float2* __restrict__ src = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)(S * mx0) * prm.pitch_d + my0;
+        for (int i = threadIdx.x; i < n_samp * (kLanes / 2); i += GROUPS * WARPS * 32) {
+            const int j = i / (kLanes / 2), c = 2 * (i % (kLanes / 2));
+            cp_async16(smem + j * kLanes + c, src + (size_t)j * prm.pitch_d + c);
+        }
+        cp_async_commit();
     }
     const float2* col = smem + (S * warp * kP) * kLanes + lane;
     const int my = my0 + lane;
@@ -548,10 +578,12 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
     auto stage_carrier = [&](int c, int slot) {
         const float2* __restrict__ ph = prm.phx + (size_t)(c * prm.row_c + plane * prm.row_p) * prm.n_alloc + S * mx0;
         float2* dst = sph + slot * n_samp;
-        for (int j = tig; j < n_samp; j += GT) dst[j] = __ldg(ph + j);
+        for (int j = tig; j < n_samp; j += GT) cp_async8(dst + j, ph + j);
+        cp_async_commit();
     };
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory"); };
     if (group < prm.n_cand) stage_carrier(group, 0);
+    cp_async_wait_all();
     __syncthreads();
     int slot = 0;
     for (int c = group; c < prm.n_cand; c += GROUPS, slot ^= 1) {
@@ -597,6 +629,7 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
                 prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
                          (my0 + lane) / kPmB] = a2max[hb];
         }
+        cp_async_wait_all();
         group_sync();
     }
 }
@@ -674,12 +707,6 @@ __global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax
     }
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // CTA = kMrTX x kMrTY fine pixels of one plane; all candidate rows of the plane stream through:
 //   coarse tile -> smem (cp.async, double buffered), interpolate along x into smem (transposed),
