@@ -742,46 +742,44 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     constexpr int SBX = kMrTX / S / kPmB, SBY = kMrTY / S / kPmB;   // bound blocks inside the tile (2 x 4 at S = 4)
     static_assert(SBX >= 1 && SBY >= 1 && kMrTX / S % kPmB == 0 && kMrTY / S % kPmB == 0, "tile must hold whole bound blocks");
     static_assert(kMrHL <= kPmB, "the interpolation halo must stay within one neighbouring bound block");
-    __shared__ float s_thr[2][8];
+    __shared__ int s_blk[SBX][SBY];       // smallest recorded winner (float bits, >= 0) per bound block of the tile
     __shared__ int s_cnt;
     __shared__ unsigned short s_list[kMaxPruneCand];
     int n_live = prm.n_cand;
     const bool prune = prm.prune != 0;
     if (prune) {
-        // smallest recorded winner per (row half h, warp column block): thread = (x = lane + 32 h, 16 columns of `warp`)
+        constexpr int BPX = kPmB * S;             // pixels per bound-block edge
+        if (threadIdx.x < SBX * SBY) s_blk[threadIdx.x / SBY][threadIdx.x % SBY] = 0x7f7fffff;   // FLT_MAX
+        __syncthreads();
+        // row-major (coalesced) sweep over the tile's keys: thread = (column, row parity)
+        const int col = threadIdx.x % kMrTY, r0 = threadIdx.x / kMrTY;
+        constexpr int RSTEP = 256 / kMrTY;
+        static_assert(256 % kMrTY == 0 && BPX % RSTEP == 0, "a thread's rows must not straddle bound blocks");
+        float tmin[SBX];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float tmin = 3.4e38f;
-            const int x = x0 + lane + 32 * h;
+        for (int i = 0; i < SBX; ++i) tmin[i] = 3.4028234e38f;
+        const int y = y0 + col;
 #pragma unroll
-            for (int p = 0; p < kP; ++p) {
-                const int y = y0 + warp * kP + p;
-                if (x < prm.N && y < prm.M) tmin = fminf(tmin, __uint_as_float((unsigned)(prm.key[(size_t)x * prm.M + y] >> 32)));
-            }
+        for (int e = 0; e < kMrTX / RSTEP; ++e) {
+            const int x = x0 + r0 + RSTEP * e;
+            if (x < prm.N && y < prm.M)
+                tmin[(RSTEP * e) / BPX] = fminf(tmin[(RSTEP * e) / BPX],
+                                               __uint_as_float((unsigned)(prm.key[(size_t)x * prm.M + y] >> 32)));   // only grows: any value read is a valid bound
+        }
+        constexpr int SPAN = BPX < 32 ? BPX : 32;     // lanes of a warp that share a bound-block column
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-            if (lane == 0) s_thr[h][warp] = tmin;
+        for (int i = 0; i < SBX; ++i) {
+#pragma unroll
+            for (int o = SPAN / 2; o > 0; o >>= 1) tmin[i] = fminf(tmin[i], __shfl_xor_sync(0xffffffffu, tmin[i], o));
+            if (lane % SPAN == 0) atomicMin(&s_blk[i][col / BPX], __float_as_int(tmin[i]));
         }
         __syncthreads();
         if (warp == 0) {
-            // thresholds per bound block of the tile (pixels 32 h .. 32 h + 31  <->  kPmB coarse rows when S = 4, ...)
             float thr[SBX][SBY];
 #pragma unroll
             for (int i = 0; i < SBX; ++i)
 #pragma unroll
-                for (int j = 0; j < SBY; ++j) {
-                    float t = 3.4e38f;
-                    // pixel rows of block i: [i kPmB S, (i+1) kPmB S) -> halves h; pixel columns -> warps of 16 columns
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int w = 0; w < 8; ++w) {
-                            const bool rows = (32 * h) / (kPmB * S) <= i && i <= (32 * h + 31) / (kPmB * S);
-                            const bool cols = (16 * w) / (kPmB * S) <= j && j <= (16 * w + 15) / (kPmB * S);
-                            if (rows && cols) t = fminf(t, s_thr[h][w]);
-                        }
-                    thr[i][j] = t;
-                }
+                for (int j = 0; j < SBY; ++j) thr[i][j] = __int_as_float(s_blk[i][j]);
             const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;      // window: one block around the tile's blocks
             int cnt = 0;
             for (int base = 0; base < prm.n_cand; base += 32) {
