@@ -4,7 +4,7 @@ This package is a NumPy/SciPy restatement of the algorithms in the reference
 ``pyGPA`` (geometric_phase_analysis.py / phase_unwrap.py / cuGPA.py).  It exists to
 check the CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
-product package ``pygpa_b200`` never does (tests/test_no_oracle_in_product.py
+product package ``pygpa_b200`` never does (tests/test_host_logic.py::test_product_never_imports_the_oracle
 enforces that).
 
 Parity status: PINNED (except oracle/wiener_numpy.py, whose third-party arithmetic — scikit-image's
