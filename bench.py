@@ -319,6 +319,24 @@ def run_ours(args, cfg):
         t1e.record()
         torch.cuda.synchronize()
         lf_ms = t0e.elapsed_time(t1e)
+        # ---- consumers of the sweep: timed once each after a warm-up call ----
+        from pygpa_b200 import property_extract as pe_b200, unit_cell_averaging as uc_b200
+        grads64 = torch.stack([o["grad"] for o in outs]).double()
+        img64 = img.double()
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            t0e.record()
+            r = fn()
+            t1e.record()
+            torch.cuda.synchronize()
+            return r, t0e.elapsed_time(t1e)
+        jac, j_ms = timed(lambda: pe_b200.phasegradient2J_device(ks, grads64, weights, 1.0, add_identity=True))
+        _props, p_ms = timed(lambda: solvers.props_from_jac(jac))
+        _dec, d_ms2 = timed(lambda: solvers.gaussian_deconvolve(u, cfg["sigma"], dr))
+        _cell, c_ms = timed(lambda: uc_b200.unit_cell_average_device(img64, ks[:2], u, z=2))
+        _fit, f_ms = timed(lambda: solvers.fit_plane_huber(u[0]))
         # transparency: the same sweep with the (exact) branch-and-bound pruning switched off
         engine.set_pruning(False)
         step()
@@ -354,6 +372,13 @@ def run_ours(args, cfg):
             "lstsq": {"ms": prof["k_lstsq"][0], "bound": "hbm", "achieved_gbs": ls_gbs, "peak_gbs": hbm, "frac": ls_gbs / hbm,
                       "basis": "64 B/pixel (SURVEY 8d) x 2 solves"},
             "kernels_ms": {k_: v[0] for k_, v in prof.items()},
+            "consumers_ms": {
+                "what": "SURVEY 8f rows on the C3 frame, device resident, one call each (float64, HBM-bound streaming kernels)",
+                "phasegradient2Jac": j_ms, "phasegradient2Jac_gbs": 104.0 * SIZE * SIZE / (j_ms / 1e3) / 1e9,
+                "props_from_Jac": p_ms, "props_from_Jac_gbs": 64.0 * SIZE * SIZE / (p_ms / 1e3) / 1e9,
+                "gaussian_deconvolve_2_planes": d_ms2, "unit_cell_average_z2": c_ms, "fit_plane_huber": f_ms,
+                "basis": "104 B/pixel (3 x (2 gradients + 1 weight) in, 4 out) and 64 B/pixel (4 in, 4 out) against hbm_gbs of MEASURED_PEAKS.json",
+            },
         }
         # reference cuGPA on this GPU: the CuPy module itself if importable, else its torch transcription
         try:
