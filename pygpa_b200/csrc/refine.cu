@@ -66,14 +66,42 @@ __global__ void __launch_bounds__(256) k_sqrt_norm(const double* __restrict__ am
 }
 
 struct PlaneFitState {
-    double theta[3];      // plane in scaled, centred coordinates: z ~ theta0 xs + theta1 ys + theta2
+    double theta[3];      // point the next launch evaluates, in scaled, centred coordinates: z ~ t0 xs + t1 ys + t2
+    double accepted[3];   // last accepted point and its objective
+    double f_accepted;
+    double irls[3];       // IRLS step from the last accepted point (the safe fallback)
     double delta;         // largest change of the plane over the frame in the last step
-    int done, iter, max_iter, pad;
+    int done, iter, max_iter, was_newton;
     unsigned ticket;
 };
 
-constexpr int kPlaneSums = 9;
+constexpr int kPlaneSums = 19;   // IRLS normal equations 9, inlier Hessian 6, gradient 3, objective 1
 
+// 3x3 solve by Gaussian elimination with partial pivoting; false when singular
+__device__ bool solve3(double A[3][4], double (&x)[3]) {
+    for (int col = 0; col < 3; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 3; ++r)
+            if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
+        if (!(fabs(A[piv][col]) > 0.0)) return false;
+        for (int k = 0; k < 4; ++k) { const double t = A[col][k]; A[col][k] = A[piv][k]; A[piv][k] = t; }
+        for (int r = col + 1; r < 3; ++r) {
+            const double f = A[r][col] / A[col][col];
+            for (int k = col; k < 4; ++k) A[r][k] -= f * A[col][k];
+        }
+    }
+    x[2] = A[2][3] / A[2][2];
+    x[1] = (A[1][3] - A[1][2] * x[2]) / A[1][1];
+    x[0] = (A[0][3] - A[0][1] * x[1] - A[0][2] * x[2]) / A[0][0];
+    return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]);
+}
+
+// One step of the Huber plane fit.  The objective sum rho(r_i) is convex and piecewise quadratic, so
+// Newton's method on the current inlier set (|r| <= f_scale) lands on the minimiser in a handful of
+// steps once the inlier set settles; the IRLS step (weights min(1, f_scale/|r|), a majorise-minimise
+// step that can never increase the objective) is computed in the same sweep and taken instead whenever
+// the Newton step is unavailable (singular inlier Hessian) or made the objective worse.  Launch k
+// evaluates everything at state->theta; the CTA that finishes last decides the next point.
 __global__ void __launch_bounds__(256) k_plane_irls(const double* __restrict__ img, int n, int m, PlaneFitState* st,
                                                     double* __restrict__ partial, double f_scale, double tol) {
     if (st->done) return;
@@ -89,15 +117,20 @@ __global__ void __launch_bounds__(256) k_plane_irls(const double* __restrict__ i
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const int r = (int)(i / m), c = (int)(i % m);
         const double x = ((double)r - xc) * sx, y = ((double)c - yc) * sy, z = img[i];
-        double w = 1.0;
-        if (!first) {
-            const double res = fabs(z - (t0 * x + t1 * y + t2));
-            w = res > f_scale ? f_scale / res : 1.0;          // Huber: psi(r) / r
-        }
+        const double res = z - (t0 * x + t1 * y + t2), ares = fabs(res);
+        const bool in = first || ares <= f_scale;           // the first step is ordinary least squares
+        const double w = in ? 1.0 : f_scale / ares;          // Huber: psi(r) / r
         const double wx = w * x, wy = w * y;
         acc[0] += wx * x; acc[1] += wx * y; acc[2] += wy * y;
         acc[3] += wx;     acc[4] += wy;     acc[5] += w;
         acc[6] += wx * z; acc[7] += wy * z; acc[8] += w * z;
+        if (in) {
+            acc[9] += x * x; acc[10] += x * y; acc[11] += y * y;
+            acc[12] += x;    acc[13] += y;     acc[14] += 1.0;
+        }
+        const double psi = w * res;                           // clip(res, -f_scale, f_scale)
+        acc[15] += psi * x; acc[16] += psi * y; acc[17] += psi;
+        acc[18] += in ? 0.5 * res * res : f_scale * ares - 0.5 * f_scale * f_scale;
     }
     const int nblk = gridDim.x;
 #pragma unroll
@@ -117,37 +150,51 @@ __global__ void __launch_bounds__(256) k_plane_irls(const double* __restrict__ i
         for (int i = threadIdx.x; i < nblk; i += 256) s += __ldcg(partial + (size_t)k * nblk + i);
         S[k] = block_sum32(s, sh);
     }
-    if (threadIdx.x == 0) {
-        // normal equations [[xx, xy, x], [xy, yy, y], [x, y, 1]] theta = [xz, yz, z], Gaussian elimination
-        double A[3][4] = {{S[0], S[1], S[3], S[6]}, {S[1], S[2], S[4], S[7]}, {S[3], S[4], S[5], S[8]}};
-        bool ok = true;
-        for (int col = 0; col < 3 && ok; ++col) {
-            int piv = col;
-            for (int r = col + 1; r < 3; ++r)
-                if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
-            if (A[piv][col] == 0.0) { ok = false; break; }
-            for (int k = 0; k < 4; ++k) { const double t = A[col][k]; A[col][k] = A[piv][k]; A[piv][k] = t; }
-            for (int r = col + 1; r < 3; ++r) {
-                const double f = A[r][col] / A[col][col];
-                for (int k = col; k < 4; ++k) A[r][k] -= f * A[col][k];
-            }
+    if (threadIdx.x != 0) return;
+    st->ticket = 0u;
+    st->iter += 1;
+    const double F = S[18];
+    if (!first && st->was_newton && !(F <= st->f_accepted)) {
+        // the Newton step overshot: go back and take the IRLS step from the last accepted point
+        st->theta[0] = st->irls[0]; st->theta[1] = st->irls[1]; st->theta[2] = st->irls[2];
+        st->was_newton = 0;
+        if (st->iter >= st->max_iter) {
+            st->theta[0] = st->accepted[0]; st->theta[1] = st->accepted[1]; st->theta[2] = st->accepted[2];
+            st->done = 1;
         }
-        if (ok) {
-            double th[3];
-            th[2] = A[2][3] / A[2][2];
-            th[1] = (A[1][3] - A[1][2] * th[2]) / A[1][1];
-            th[0] = (A[0][3] - A[0][1] * th[1] - A[0][2] * th[2]) / A[0][0];
-            // change of the fitted plane anywhere on the frame (scaled coordinates span [-1/2, 1/2])
-            const double d = 0.5 * fabs(th[0] - t0) + 0.5 * fabs(th[1] - t1) + fabs(th[2] - t2);
-            st->theta[0] = th[0]; st->theta[1] = th[1]; st->theta[2] = th[2];
-            st->delta = d;
-            st->iter += 1;
-            if ((!first && d < tol) || st->iter >= st->max_iter) st->done = 1;
-        } else {
-            st->done = 1;       // degenerate frame (all weights zero): keep the last plane
-        }
-        st->ticket = 0u;
+        return;
     }
+    st->accepted[0] = t0; st->accepted[1] = t1; st->accepted[2] = t2;
+    st->f_accepted = F;
+    double next[3] = {t0, t1, t2};
+    bool newton = false, have = false;
+    {
+        double A[3][4] = {{S[0], S[1], S[3], S[6]}, {S[1], S[2], S[4], S[7]}, {S[3], S[4], S[5], S[8]}};
+        double th[3];
+        if (solve3(A, th)) {
+            st->irls[0] = th[0]; st->irls[1] = th[1]; st->irls[2] = th[2];
+            next[0] = th[0]; next[1] = th[1]; next[2] = th[2];
+            have = true;
+        }
+    }
+    if (!first && S[14] >= 3.0) {
+        double H[3][4] = {{S[9], S[10], S[12], S[15]}, {S[10], S[11], S[13], S[16]}, {S[12], S[13], S[14], S[17]}};
+        double d[3];
+        if (solve3(H, d)) {
+            next[0] = t0 + d[0]; next[1] = t1 + d[1]; next[2] = t2 + d[2];
+            newton = have = true;
+        }
+    }
+    if (!have) {                 // degenerate frame (all weights zero): keep the current plane
+        st->done = 1;
+        return;
+    }
+    // change of the fitted plane anywhere on the frame (scaled coordinates span [-1/2, 1/2])
+    const double d = 0.5 * fabs(next[0] - t0) + 0.5 * fabs(next[1] - t1) + fabs(next[2] - t2);
+    st->delta = d;
+    st->was_newton = newton ? 1 : 0;
+    st->theta[0] = next[0]; st->theta[1] = next[1]; st->theta[2] = next[2];
+    if ((!first && d < tol) || st->iter >= st->max_iter) st->done = 1;
 }
 
 }  // namespace gpa
