@@ -132,4 +132,82 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Bluestein (chirp-z) DFT of ANY length P inside shared memory, built on fft_pow2:
+//   X[k] = c[k] sum_n (x[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / P)
+// i.e. a circular convolution of length L >= 2P - 1 (a power of two) = two FFT_L.
+// ------------------------------------------------------------------------------------------
+struct AxisPlan {
+    int P, L;
+    double2* chirp;     // [P]  exp(-i pi n^2 / P)
+    double2* bhat;      // [L]  FFT_L of the wrapped conjugate chirp
+    double2* tw;        // [L]  exp(-2 pi i t / L)
+};
+
+static __global__ void k_bs_tables(double2* chirp, double2* tw, int P, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) {
+        const long long q = ((long long)i * i) % (2LL * P);        // n^2 mod 2P: exact range reduction
+        double s, c;
+        sincospi(-(double)q / (double)P, &s, &c);
+        chirp[i] = make_double2(c, s);
+    }
+    if (i < L) {
+        double s, c;
+        sincospi(-2.0 * (double)i / (double)L, &s, &c);
+        tw[i] = make_double2(c, s);
+    }
+}
+
+// bhat = FFT_L(b),  b[m mod L] = conj(chirp[|m|]), |m| < P        (one CTA)
+template <int MAXB>
+static __global__ void __launch_bounds__(512, 1) k_bs_prep(const AxisPlan ax) {
+    extern __shared__ double2 bs_buf[];
+    for (int i = threadIdx.x; i < ax.L; i += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (i < ax.P) v = ax.chirp[i];
+        else if (ax.L - i < ax.P) v = ax.chirp[ax.L - i];
+        bs_buf[i] = make_double2(v.x, -v.y);
+    }
+    __syncthreads();
+    fft_pow2<MAXB>(bs_buf, ax.L, ax.tw);
+    for (int i = threadIdx.x; i < ax.L; i += blockDim.x) ax.bhat[i] = bs_buf[i];
+}
+
+// buf[0..P) <- DFT_P(buf[0..P)); buf holds L entries (the rest is scratch); all threads of the CTA,
+// which must have synchronised after writing buf.  On return buf[0..P) is visible to every thread.
+template <int MAXB>
+__device__ __forceinline__ void bluestein_dft(double2* buf, const AxisPlan& ax) {
+    const int P = ax.P, L = ax.L;
+    for (int n = threadIdx.x; n < L; n += blockDim.x)
+        buf[n] = n < P ? zmul(buf[n], __ldg(ax.chirp + n)) : make_double2(0.0, 0.0);
+    __syncthreads();
+    fft_pow2<MAXB>(buf, L, ax.tw);
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        const double2 y = zmul(buf[k], __ldg(ax.bhat + k));
+        buf[k] = make_double2(y.x, -y.y);                 // conj: the second forward FFT then inverts
+    }
+    __syncthreads();
+    fft_pow2<MAXB>(buf, L, ax.tw);
+    const double inv_l = 1.0 / (double)L;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        const double2 v = zmul(make_double2(buf[k].x, -buf[k].y), __ldg(ax.chirp + k));
+        buf[k] = make_double2(v.x * inv_l, v.y * inv_l);
+    }
+    __syncthreads();
+}
+
+static inline int bs_pow2_at_least(int v) {
+    int l = 1;
+    while (l < v) l <<= 1;
+    return l;
+}
+
+// launch geometry of the shared-memory FFT of length L: threads, and whether a thread carries two butterflies
+static inline void fft_launch_shape(int L, int& threads, int& per) {
+    const int eighth = L / 8 > 0 ? L / 8 : 1;
+    threads = eighth < 32 ? 32 : (eighth > 512 ? 512 : eighth);
+    per = (eighth + threads - 1) / threads;
+}
+
 }  // namespace gpa

@@ -9,9 +9,10 @@
 // enqueues (it polls the flag every few iterations to stop enqueueing early).
 //
 // DCT-II / DCT-III (scipy.fft.dctn / idctn, unnormalised): one row per CTA in shared memory.
-// Power-of-two lengths use Makhoul's permutation and ONE n-point complex FFT per PAIR of rows
-// (radix-8 Stockham in place, twiddles from a table); other lengths use the O(n^2) cosine-table
-// sum (any n, slower).  The 2-D
+// Makhoul's permutation turns each DCT into ONE n-point complex DFT per PAIR of rows: a radix-8
+// Stockham FFT in shared memory for power-of-two n, a Bluestein chirp-z transform (two FFTs of
+// length L >= 2n - 1) for any other n up to 4096 — iterate_GPA crops the frame by `edge`, so odd
+// sizes are the norm there — and the O(n^2) cosine-table sum beyond that.  The 2-D
 // transform is row pass -> transpose -> row pass; the 1/scale of the Poisson solve is fused into
 // the second forward pass and <r, z> into the last inverse pass.
 #include "common.cuh"
@@ -88,13 +89,16 @@ __global__ void k_uw_cos_table(double* cs, int n, int denom) {
     if (i < n) cs[i] = cospi((double)i / (double)denom);
 }
 
-__global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int pow2) {
+// mode 2: power-of-two FFT (tw, mk), 1: Bluestein FFT (mk only; the chirp tables come from k_bs_tables), 0: direct (ct)
+__global__ void k_uw_tables(double2* tw, double2* mk, double* ct, int n, int mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pow2) {
+    if (mode) {
         if (i < n) {
             double s, c;
-            sincospi(-2.0 * (double)i / (double)n, &s, &c);
-            tw[i] = make_double2(c, s);
+            if (mode == 2) {
+                sincospi(-2.0 * (double)i / (double)n, &s, &c);
+                tw[i] = make_double2(c, s);
+            }
             sincospi(-(double)i / (2.0 * (double)n), &s, &c);
             mk[i] = make_double2(c, s);
         }
@@ -107,7 +111,8 @@ struct DctArgs {
     const double* in;
     double* out;
     int rows, n;               // rows of length n, contiguous
-    const double2 *tw, *mk;    // pow2 tables
+    const double2 *tw, *mk;    // FFT tables
+    AxisPlan bs;               // Bluestein plan of this axis (bs.L == 0: n is a power of two)
     const double* ct;          // direct table
     // fused Poisson scaling (second forward pass; data is in the transposed layout: row = axis-1
     // frequency J, column = axis-0 frequency I): out /= 2 (cos(pi I / dimM) + cos(pi J / dimN) - 2)
@@ -150,13 +155,14 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_dct2_rows_pow2(const
         cbuf[dst] = make_double2(xa[j], two ? xb[j] : 0.0);
     }
     __syncthreads();
-    fft_pow2<MAXB>(cbuf, n, a.tw);
+    if (a.bs.L) bluestein_dft<MAXB>(cbuf, a.bs);
+    else fft_pow2<MAXB>(cbuf, n, a.tw);
     double* __restrict__ ya = a.out + (size_t)row * n;
     double* __restrict__ yb = ya + n;
     const double cra = a.fuse_scale ? a.cos_row[row] : 0.0;
     const double crb = a.fuse_scale && two ? a.cos_row[row + 1] : 0.0;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double2 w = __ldg(a.mk + k), zk = cbuf[k], zn = cbuf[(n - k) & (n - 1)];
+        const double2 w = __ldg(a.mk + k), zk = cbuf[k], zn = cbuf[k ? n - k : 0];
         const double sx = zk.x + zn.x, sy = zk.y - zn.y;      // Z[k] + conj Z[n-k]
         const double dx = zk.x - zn.x, dy = zk.y + zn.y;      // Z[k] - conj Z[n-k]
         double ra = w.x * sx - w.y * sy;                      // Re(w (Z + conj Z'))
@@ -193,7 +199,8 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(cons
         cbuf[k] = make_double2(re_a - im_b, -im_a - re_b);   // conj(V_a) - i conj(V_b)
     }
     __syncthreads();
-    fft_pow2<MAXB>(cbuf, n, a.tw);
+    if (a.bs.L) bluestein_dft<MAXB>(cbuf, a.bs);
+    else fft_pow2<MAXB>(cbuf, n, a.tw);
     double* __restrict__ xa = a.out + (size_t)row * n;
     double* __restrict__ xb = xa + n;
     const double inv = 1.0 / (double)n;
@@ -423,8 +430,11 @@ static bool is_pow2(int n) { return n >= 2 && (n & (n - 1)) == 0; }
 struct AxisTables {
     double2 *tw, *mk;
     double* ct;
+    AxisPlan bs;          // bs.L != 0: any-length axis handled by the Bluestein transform
     int n, pow2;
 };
+
+constexpr int kMaxBluesteinAxis = kMaxFftLen / 2;    // L = pow2 >= 2n - 1 must fit shared memory
 
 struct UwPlan {
     int N, M;
@@ -451,7 +461,14 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
         ax->n = n; ax->pow2 = is_pow2(n) && n <= kMaxFftLen;
         ax->tw = a.take<double2>(n + 1);
         ax->mk = a.take<double2>(n);
-        ax->ct = a.take<double>(ax->pow2 ? 1 : 4 * (size_t)n);
+        ax->bs.P = n; ax->bs.L = 0; ax->bs.chirp = ax->bs.bhat = ax->bs.tw = nullptr;
+        if (!ax->pow2 && n <= kMaxBluesteinAxis) {
+            ax->bs.L = bs_pow2_at_least(2 * n - 1);
+            ax->bs.chirp = a.take<double2>(n);
+            ax->bs.bhat = a.take<double2>(ax->bs.L);
+            ax->bs.tw = a.take<double2>(ax->bs.L);
+        }
+        ax->ct = a.take<double>(ax->pow2 || ax->bs.L ? 1 : 4 * (size_t)n);
     }
     u.cosI = a.take<double>(N);
     u.cosJ = a.take<double>(M);
@@ -461,13 +478,13 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
 
 template <int INVERSE>
 static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
-    a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n;
-    if (ax.pow2) {
-        const int eighth = ax.n / 8 > 0 ? ax.n / 8 : 1;
-        // one radix-8 butterfly per thread, two for the longest rows (at most 512 threads)
-        const int threads = eighth < 32 ? 32 : (eighth > 512 ? 512 : eighth);
-        const int per = (eighth + threads - 1) / threads;
-        const size_t smem = (size_t)ax.n * sizeof(double2);
+    a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n; a.bs = ax.bs;
+    if (ax.pow2 || ax.bs.L) {
+        // one radix-8 butterfly per thread, two for the longest transforms (at most 512 threads)
+        const int len = ax.bs.L ? ax.bs.L : ax.n;
+        int threads, per;
+        fft_launch_shape(len, threads, per);
+        const size_t smem = (size_t)len * sizeof(double2);
         const int ctas = (a.rows + 1) / 2;           // two rows per FFT
         auto go = [&](auto kern) -> int {
             GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
@@ -539,8 +556,22 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t nm = (size_t)N * M;
     for (const AxisTables* ax : {&u.axN, &u.axM}) {
-        const int cnt = ax->pow2 ? ax->n : 4 * ax->n;
-        k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, ax->pow2);
+        const int mode = ax->pow2 ? 2 : (ax->bs.L ? 1 : 0);
+        const int cnt = mode ? ax->n : 4 * ax->n;
+        k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, mode);
+        if (ax->bs.L) {       // chirp, FFT_L twiddles and the transformed chirp of the Bluestein convolution
+            k_bs_tables<<<ceil_div(ax->bs.L, 256), 256, 0, st>>>(ax->bs.chirp, ax->bs.tw, ax->bs.P, ax->bs.L);
+            int threads, per;
+            fft_launch_shape(ax->bs.L, threads, per);
+            const size_t smem = (size_t)ax->bs.L * sizeof(double2);
+            if (per <= 1) {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+                k_bs_prep<1><<<1, threads, smem, st>>>(ax->bs);
+            } else {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+                k_bs_prep<2><<<1, threads, smem, st>>>(ax->bs);
+            }
+        }
     }
     k_uw_cos_table<<<ceil_div(N, 256), 256, 0, st>>>(u.cosI, N, M);
     k_uw_cos_table<<<ceil_div(M, 256), 256, 0, st>>>(u.cosJ, M, N);

@@ -20,43 +20,6 @@ namespace gpa {
 
 constexpr int kMaxBluesteinL = 8192;       // 128 KB of shared memory per row
 
-struct AxisPlan {
-    int P, L;
-    double2 *chirp;     // [P]  exp(-i pi n^2 / P)
-    double2 *bhat;      // [L]  FFT_L of the wrapped conjugate chirp
-    double2 *tw;        // [L]  exp(-2 pi i t / L)
-};
-
-__global__ void k_bs_tables(double2* chirp, double2* tw, int P, int L) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) {
-        const long long q = ((long long)i * i) % (2LL * P);        // n^2 mod 2P: exact range reduction
-        double s, c;
-        sincospi(-(double)q / (double)P, &s, &c);
-        chirp[i] = make_double2(c, s);
-    }
-    if (i < L) {
-        double s, c;
-        sincospi(-2.0 * (double)i / (double)L, &s, &c);
-        tw[i] = make_double2(c, s);
-    }
-}
-
-// bhat = FFT_L(b),  b[m mod L] = conj(chirp[|m|]), |m| < P
-template <int MAXB>
-__global__ void __launch_bounds__(512, 1) k_bs_prep(const AxisPlan ax) {
-    extern __shared__ double2 buf[];
-    for (int i = threadIdx.x; i < ax.L; i += blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        if (i < ax.P) v = ax.chirp[i];
-        else if (ax.L - i < ax.P) v = ax.chirp[ax.L - i];
-        buf[i] = make_double2(v.x, -v.y);
-    }
-    __syncthreads();
-    fft_pow2<MAXB>(buf, ax.L, ax.tw);
-    for (int i = threadIdx.x; i < ax.L; i += blockDim.x) ax.bhat[i] = buf[i];
-}
-
 struct BsArgs {
     const double2* in;       // rows of length P (stride in_stride elements)
     double2* out;            // rows of length P
@@ -152,12 +115,6 @@ __global__ void k_transpose_z(const double2* __restrict__ in, double2* __restric
     }
 }
 
-static int pow2_at_least(int v) {
-    int l = 1;
-    while (l < v) l <<= 1;
-    return l;
-}
-
 static size_t carve_wiener(AxisPlan (&ax)[2], double2*& A, double2*& B, void* ws, size_t ws_bytes, int P0, int P1) {
     Arena a(ws, ws_bytes);
     A = a.take<double2>((size_t)P0 * P1);
@@ -165,7 +122,7 @@ static size_t carve_wiener(AxisPlan (&ax)[2], double2*& A, double2*& B, void* ws
     const int Ps[2] = {P0, P1};
     for (int i = 0; i < 2; ++i) {
         ax[i].P = Ps[i];
-        ax[i].L = pow2_at_least(2 * Ps[i] - 1);
+        ax[i].L = bs_pow2_at_least(2 * Ps[i] - 1);
         ax[i].chirp = a.take<double2>(Ps[i]);
         ax[i].bhat = a.take<double2>(ax[i].L);
         ax[i].tw = a.take<double2>(ax[i].L);
@@ -204,7 +161,7 @@ extern "C" int gpa_deconvolve_workspace_bytes(int N, int M, int dr, size_t* byte
     GPA_REQUIRE(bytes && N >= 2 && M >= 2 && dr >= 0, "bad argument");
     const int P0 = N + 4 * dr, P1 = M + 4 * dr;
     GPA_REQUIRE(2 * dr <= N - 1 && 2 * dr <= M - 1, "reflect padding of %d does not fit a %d x %d frame", 2 * dr, N, M);
-    GPA_REQUIRE(pow2_at_least(2 * P0 - 1) <= kMaxBluesteinL && pow2_at_least(2 * P1 - 1) <= kMaxBluesteinL,
+    GPA_REQUIRE(bs_pow2_at_least(2 * P0 - 1) <= kMaxBluesteinL && bs_pow2_at_least(2 * P1 - 1) <= kMaxBluesteinL,
                 "padded frame %d x %d exceeds the in-shared-memory transform (at most %d samples per axis)", P0, P1,
                 kMaxBluesteinL / 2);
     AxisPlan ax[2];

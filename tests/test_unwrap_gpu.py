@@ -77,11 +77,14 @@ def test_oracle_parity_fixed_iteration_count(shape):
 
 
 @pytest.mark.parametrize("shape,kmax", [((2, 2), 3), ((4, 4), 3), ((8, 8), 3), ((16, 16), 3), ((33, 64), 3), ((512, 1024), 3),
-                                        ((1024, 1024), 3), ((2048, 2048), 2), ((4096, 4096), 1), ((8192, 8192), 1)])
+                                        ((1024, 1024), 3), ((2048, 2048), 2), ((4096, 4096), 1), ((8192, 8192), 1),
+                                        ((1014, 1014), 3), ((1000, 601), 3), ((3, 5), 2), ((4100, 2056), 1)])
 def test_fft_stage_plans_and_row_pairs(shape, kmax):
     """Every FFT stage plan of the row kernels — leading radix-2 / radix-4 stage, 0 to 4 radix-8 stages,
     two butterflies per thread at the maximum length 8192 — plus an odd number of rows (the last FFT
-    carries a single row), weighted, against the oracle.  (Frames with M >= 2N or N >= 2M are avoided:
+    carries a single row), the Bluestein transform of non-power-of-two axes (1014 = iterate_GPA's default
+    crop of a 1024 frame, even / odd / tiny lengths) and the direct cosine sums beyond 4096 (4100),
+    weighted, against the oracle.  (Frames with M >= 2N or N >= 2M are avoided:
     the reference's swapped Poisson scale makes those NaN, see test_reference_nan_quirk_*.)"""
     psi, w = _case(shape, 3 + sum(shape), 0.05)
     ref = oracle.phase_unwrap(psi, w, kmax=kmax)
