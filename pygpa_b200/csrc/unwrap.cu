@@ -150,9 +150,21 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_dct2_rows_pow2(const
     const bool two = row + 1 < a.rows;
     const double* __restrict__ xa = a.in + (size_t)row * n;
     const double* __restrict__ xb = xa + n;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int dst = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
-        cbuf[dst] = make_double2(xa[j], two ? xb[j] : 0.0);
+    // fixed trip count (blockDim.x * 8 MAXB >= n): every global load of the thread is issued before the
+    // first shared-memory store waits on one (a runtime-bound loop serialised them: 24 % of the kernel)
+    {
+        double va[8 * MAXB], vb[8 * MAXB];
+#pragma unroll
+        for (int q = 0; q < 8 * MAXB; ++q) {
+            const int j = threadIdx.x + q * blockDim.x;
+            va[q] = j < n ? xa[j] : 0.0;
+            vb[q] = (j < n && two) ? xb[j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8 * MAXB; ++q) {
+            const int j = threadIdx.x + q * blockDim.x;
+            if (j < n) cbuf[(j & 1) ? n - 1 - (j >> 1) : (j >> 1)] = make_double2(va[q], vb[q]);
+        }
     }
     __syncthreads();
     if (a.bs.L) bluestein_dft<MAXB>(cbuf, a.bs);
@@ -189,14 +201,28 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(cons
     const bool two = row + 1 < a.rows;
     const double* __restrict__ ya = a.in + (size_t)row * n;
     const double* __restrict__ yb = ya + n;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double2 w = __ldg(a.mk + k);             // e^{-i pi k/2n} = (c, -s)
-        const double ak = ya[k], ank = k ? ya[n - k] : 0.0;
-        const double bk = two ? yb[k] : 0.0, bnk = (two && k) ? yb[n - k] : 0.0;
-        // e^{+i t}(yk - i ynk) = (c yk + s ynk) + i (s yk - c ynk), with c = w.x, s = -w.y
-        const double re_a = 0.5 * (w.x * ak - w.y * ank), im_a = 0.5 * (-w.y * ak - w.x * ank);
-        const double re_b = 0.5 * (w.x * bk - w.y * bnk), im_b = 0.5 * (-w.y * bk - w.x * bnk);
-        cbuf[k] = make_double2(re_a - im_b, -im_a - re_b);   // conj(V_a) - i conj(V_b)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {             // two batches of 4 MAXB elements: 16 MAXB loads in flight
+        double ak[4 * MAXB], ank[4 * MAXB], bk[4 * MAXB], bnk[4 * MAXB];
+#pragma unroll
+        for (int q = 0; q < 4 * MAXB; ++q) {           // fixed trip count: the loads are issued back to back
+            const int k = threadIdx.x + (half * 4 * MAXB + q) * blockDim.x;
+            const bool in = k < n;
+            ak[q] = in ? ya[k] : 0.0;
+            ank[q] = (in && k) ? ya[n - k] : 0.0;
+            bk[q] = (in && two) ? yb[k] : 0.0;
+            bnk[q] = (in && two && k) ? yb[n - k] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4 * MAXB; ++q) {
+            const int k = threadIdx.x + (half * 4 * MAXB + q) * blockDim.x;
+            if (k >= n) continue;
+            const double2 w = __ldg(a.mk + k);             // e^{-i pi k/2n} = (c, -s)
+            // e^{+i t}(yk - i ynk) = (c yk + s ynk) + i (s yk - c ynk), with c = w.x, s = -w.y
+            const double re_a = 0.5 * (w.x * ak[q] - w.y * ank[q]), im_a = 0.5 * (-w.y * ak[q] - w.x * ank[q]);
+            const double re_b = 0.5 * (w.x * bk[q] - w.y * bnk[q]), im_b = 0.5 * (-w.y * bk[q] - w.x * bnk[q]);
+            cbuf[k] = make_double2(re_a - im_b, -im_a - re_b);   // conj(V_a) - i conj(V_b)
+        }
     }
     __syncthreads();
     if (a.bs.L) bluestein_dft<MAXB>(cbuf, a.bs);
