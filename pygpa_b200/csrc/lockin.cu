@@ -53,6 +53,24 @@ __global__ void k_build_phasors(float2* __restrict__ table, double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// asynchronous global -> shared copies (LDGSTS): tile fills with every row in flight at once
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // register-blocked FIR core
 // ---------------------------------------------------------------------------------------------
 // acc[p] = sum_{d<T} g[d] * sample(p + d),  p < P.   `load(j)` returns sample j.  Taps and samples
@@ -202,10 +220,14 @@ k_pass2(const Pass2Params prm, const __grid_constant__ TapTable taps) {
     const int T = prm.T;
     const int n_samp = kTile + T + kAhead;
 
-    {   // tile fill: rows are 256 B, fully coalesced; pitch/n_alloc padding keeps it in bounds
-        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride +
-                                         (size_t)x0 * prm.pitch + y0 + lane;
-        for (int j = warp; j < n_samp; j += kWarps) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch);
+    {   // tile fill: rows are 256 B (16 copies of 16 B), all in flight; pitch/n_alloc padding keeps it in bounds
+        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride + (size_t)x0 * prm.pitch + y0;
+        for (int i = threadIdx.x; i < n_samp * (kLanes / 2); i += kWarps * 32) {
+            const int j = i / (kLanes / 2), c = 2 * (i % (kLanes / 2));
+            cp_async16(smem + j * kLanes + c, src + (size_t)j * prm.pitch + c);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
     }
     __syncthreads();
 
@@ -312,8 +334,13 @@ k_pass2_seq(const SeqParams prm, const __grid_constant__ TapTable taps) {
     const float2* col = smem + (warp * kP) * kLanes + lane;
     for (int pl = 0; pl < prm.count; ++pl) {
         __syncthreads();      // the previous plane's tile is no longer read
-        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride + (size_t)x0 * prm.pitch + y0 + lane;
-        for (int j = warp; j < n_samp; j += kWarps) smem[j * kLanes + lane] = __ldg(src + (size_t)j * prm.pitch);
+        const float2* __restrict__ src = prm.planes + (size_t)pl * prm.plane_stride + (size_t)x0 * prm.pitch + y0;
+        for (int i = threadIdx.x; i < n_samp * (kLanes / 2); i += kWarps * 32) {
+            const int j = i / (kLanes / 2), c = 2 * (i % (kLanes / 2));
+            cp_async16(smem + j * kLanes + c, src + (size_t)j * prm.pitch + c);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
         __syncthreads();
         const int cand = prm.plane0 + pl;
         const float2* __restrict__ ph = prm.phx + (size_t)cand * prm.n_alloc + x0 + warp * kP;
@@ -358,21 +385,6 @@ constexpr int kMrHL = 5;      // coarse samples to the left of an output's own c
 constexpr int kMrTX = 64;     // k_mr_interp tile: rows
 constexpr int kMrTY = 128;    //                   columns
 constexpr int kPmB = 8;       // bound blocks for the pruning: kPmB x kPmB coarse cells
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct MrPass1Params {
     const float* img;
