@@ -276,8 +276,9 @@ def run_ours(args, cfg):
                 torch.cuda.current_stream().synchronize()
                 return host
             return None
-        for _ in range(2):
-            e2e_step()
+        host = None
+        for _ in range(3):
+            host = e2e_step()       # keep the previous result alive like the timed loop does: both pinned buffer sets get cached
         barrier()
         n_e2e = max(3, min(args.steps, 5))
         t0 = time.perf_counter()
