@@ -1117,43 +1117,12 @@ struct MrFinalizeParams {
     int Nd, Md, n_cand, S, pstep;
 };
 
+// winner of pixel (x, y), known to belong to one of this call's planes
 template <int S, typename T2>
-__global__ void __launch_bounds__(256)
-k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
+__device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, const TapTable& taps, int x, int y, unsigned idx,
+                                                  int plane, int row, int cand) {
     const FinalizeParams& prm = mp.f;
-    using R = typename real_of<T2>::type;
-    const int y = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int x = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= prm.N || y >= prm.M) return;
     const size_t pix = (size_t)x * prm.M + y;
-    const size_t npix = (size_t)prm.N * prm.M;
-    const unsigned long long k = prm.key[pix];
-    if ((k >> 32) == 0ull) {
-        T2 z;
-        z.x = 0;
-        z.y = 0;
-        static_cast<T2*>(prm.lockin)[pix] = z;
-        if (prm.grad) {
-            static_cast<R*>(prm.grad)[2 * pix] = 0;
-            static_cast<R*>(prm.grad)[2 * pix + 1] = 0;
-        }
-        if (prm.w) {
-            static_cast<R*>(prm.w)[pix] = (R)prm.w0x;
-            static_cast<R*>(prm.w)[npix + pix] = (R)prm.w0y;
-        }
-        if (prm.kidx) prm.kidx[pix] = -1;
-        return;
-    }
-    const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
-    int plane, row, cand;
-    if (prm.list_mode) {
-        plane = (int)idx; row = plane; cand = 0;
-    } else {
-        plane = (int)(idx % (unsigned)prm.n_planes);
-        row = (int)(idx / (unsigned)prm.n_planes);
-        cand = row;
-    }
-    if (plane < prm.plane_begin || plane >= prm.plane_end || (plane - prm.plane_begin) % mp.pstep != 0) return;
     const int Nd = mp.Nd, Md = mp.Md;
     const float2* __restrict__ P = mp.p2 + ((size_t)((plane - prm.plane0) / mp.pstep) * mp.n_cand + cand) * Nd * Md;
     // Fine positions x-1, x, x+1 and y-1, y, y+1 in UNWRAPPED coordinates (the coarse grid is circular
@@ -1215,6 +1184,74 @@ k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) 
         s_yp.x = fmaf(gx[1], rv[2].x, s_yp.x); s_yp.y = fmaf(gx[1], rv[2].y, s_yp.y);
     }
     finalize_store<T2>(prm, pix, x, y, idx, row, plane, s_0, s_xm, s_xp, s_ym, s_yp);
+}
+
+// A warp owns 128 consecutive pixels of one frame row.  When the planes are sharded over GPUs only a
+// fraction of them has its winner in this call's planes, finely interleaved (neighbouring pixels win in
+// neighbouring planes, which belong to different ranks), so the warp first compacts the pixels it has to
+// work on (ballot + prefix) and then processes them 32 at a time: the per-rank finalize time scales
+// with the rank's share instead of staying that of the whole frame.  All pixels of a warp share x, so
+// the x taps stay warp-uniform.
+constexpr int kFinSpan = 128;
+
+template <int S, typename T2>
+__global__ void __launch_bounds__(256)
+k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
+    const FinalizeParams& prm = mp.f;
+    using R = typename real_of<T2>::type;
+    __shared__ unsigned char s_list[8][kFinSpan];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.y * 8 + warp;
+    const int yb = blockIdx.x * kFinSpan;
+    if (x >= prm.N) return;
+    const size_t npix = (size_t)prm.N * prm.M;
+    int count = 0;
+#pragma unroll
+    for (int j = 0; j < kFinSpan / 32; ++j) {
+        const int y = yb + 32 * j + lane;
+        bool own = false;
+        if (y < prm.M) {
+            const size_t pix = (size_t)x * prm.M + y;
+            const unsigned long long k = prm.key[pix];
+            if ((k >> 32) == 0ull) {      // nothing ever exceeded |0|: geometric_phase_analysis.py:806 keeps the zeros
+                T2 z;
+                z.x = 0;
+                z.y = 0;
+                static_cast<T2*>(prm.lockin)[pix] = z;
+                if (prm.grad) {
+                    static_cast<R*>(prm.grad)[2 * pix] = 0;
+                    static_cast<R*>(prm.grad)[2 * pix + 1] = 0;
+                }
+                if (prm.w) {
+                    static_cast<R*>(prm.w)[pix] = (R)prm.w0x;
+                    static_cast<R*>(prm.w)[npix + pix] = (R)prm.w0y;
+                }
+                if (prm.kidx) prm.kidx[pix] = -1;
+            } else {
+                const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+                const int plane = prm.list_mode ? (int)idx : (int)(idx % (unsigned)prm.n_planes);
+                own = plane >= prm.plane_begin && plane < prm.plane_end && (plane - prm.plane_begin) % mp.pstep == 0;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, own);
+        if (own) s_list[warp][count + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)(32 * j + lane);
+        count += __popc(mask);
+    }
+    __syncwarp();
+    for (int t = lane; t < count; t += 32) {
+        const int y = yb + s_list[warp][t];
+        const unsigned long long k = prm.key[(size_t)x * prm.M + y];
+        const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+        int plane, row, cand;
+        if (prm.list_mode) {
+            plane = (int)idx; row = plane; cand = 0;
+        } else {
+            plane = (int)(idx % (unsigned)prm.n_planes);
+            row = (int)(idx / (unsigned)prm.n_planes);
+            cand = row;
+        }
+        mr_finalize_pixel<S, T2>(mp, taps, x, y, idx, plane, row, cand);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1628,7 +1665,7 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
     f.plane0 = plane_begin; f.plane_begin = plane_begin; f.plane_end = plane_end;
     f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
     mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S; mp.pstep = plane_step;
-    dim3 grid(ceil_div(M, 32), ceil_div(N, 8));
+    dim3 grid(ceil_div(M, kFinSpan), ceil_div(N, 8));
     KernelTimer timer("k_mr_finalize", st);
 #define GPA_MRFIN(SS)                                                              \
     if (out_f64) k_mr_finalize<SS, double2><<<grid, 256, 0, st>>>(mp, tb);         \
