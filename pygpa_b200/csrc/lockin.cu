@@ -1191,10 +1191,9 @@ __device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, co
 // neighbouring planes, which belong to different ranks), so the warp first compacts the pixels it has to
 // work on (ballot + prefix) and then processes them 32 at a time: the per-rank finalize time scales
 // with the rank's share instead of staying that of the whole frame.  All pixels of a warp share x, so
-// the x taps stay warp-uniform.
-constexpr int kFinSpan = 128;
-
-template <int S, typename T2>
+// the x taps stay warp-uniform.  SPAN = pixels per warp: 32 when every plane is this call's (nothing to
+// compact; the small patch keeps the gathers of a CTA in L1), 64 / 128 for half / smaller shares.
+template <int S, typename T2, int kFinSpan>
 __global__ void __launch_bounds__(256)
 k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
     const FinalizeParams& prm = mp.f;
@@ -1665,12 +1664,22 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
     f.plane0 = plane_begin; f.plane_begin = plane_begin; f.plane_end = plane_end;
     f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
     mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S; mp.pstep = plane_step;
-    dim3 grid(ceil_div(M, kFinSpan), ceil_div(N, 8));
+    // pixels per warp: no compaction needed when every plane is ours, wider spans for smaller shares
+    const bool all_planes = plane_begin == 0 && plane_end == n_planes && plane_step == 1;
+    const int span = all_planes ? 32 : (plane_step == 2 ? 64 : 128);
+    dim3 grid(ceil_div(M, span), ceil_div(N, 8));
     KernelTimer timer("k_mr_finalize", st);
-#define GPA_MRFIN(SS)                                                              \
-    if (out_f64) k_mr_finalize<SS, double2><<<grid, 256, 0, st>>>(mp, tb);         \
-    else k_mr_finalize<SS, float2><<<grid, 256, 0, st>>>(mp, tb)
+#define GPA_MRFIN2(SS, TT)                                                                  \
+    do {                                                                                    \
+        if (span == 32) k_mr_finalize<SS, TT, 32><<<grid, 256, 0, st>>>(mp, tb);            \
+        else if (span == 64) k_mr_finalize<SS, TT, 64><<<grid, 256, 0, st>>>(mp, tb);       \
+        else k_mr_finalize<SS, TT, 128><<<grid, 256, 0, st>>>(mp, tb);                      \
+    } while (0)
+#define GPA_MRFIN(SS)                          \
+    if (out_f64) GPA_MRFIN2(SS, double2);      \
+    else GPA_MRFIN2(SS, float2)
     if (S == 2) { GPA_MRFIN(2); } else if (S == 4) { GPA_MRFIN(4); } else { GPA_MRFIN(8); }
+#undef GPA_MRFIN2
 #undef GPA_MRFIN
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
