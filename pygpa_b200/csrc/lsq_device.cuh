@@ -18,14 +18,17 @@ namespace gpa {
 
 constexpr int kMaxD = 8;
 
-template <int NRHS>
-GPA_HD inline void lsq_solve2(const double (&a0)[kMaxD], const double (&a1)[kMaxD],
-                                           const double (&y)[NRHS][kMaxD], int d, double (&x)[NRHS][2]) {
+// DM = compile-time capacity of the row arrays (d <= DM): the kernels instantiate DM = 3 — the
+// three primary k-vectors of every pipeline in the reference — next to the general DM = kMaxD, which
+// halves their register footprint.
+template <int NRHS, int DM>
+GPA_HD inline void lsq_solve2(const double (&a0)[DM], const double (&a1)[DM],
+                                           const double (&y)[NRHS][DM], int d, double (&x)[NRHS][2]) {
 #pragma unroll
     for (int k = 0; k < NRHS; ++k) x[k][0] = x[k][1] = 0.0;
     double n0 = 0.0, n1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) {
+    for (int i = 0; i < DM; ++i) {
         if (i < d) {
             n0 = fma(a0[i], a0[i], n0);
             n1 = fma(a1[i], a1[i], n1);
@@ -36,12 +39,12 @@ GPA_HD inline void lsq_solve2(const double (&a0)[kMaxD], const double (&a1)[kMax
     if (!(f2 > 0.0)) return;
     const double f = sqrt(f2);
     const double inv_f = 1.0 / f;
-    double q[kMaxD];
+    double q[DM];
     double g = 0.0, z1[NRHS];
 #pragma unroll
     for (int k = 0; k < NRHS; ++k) z1[k] = 0.0;
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) {
+    for (int i = 0; i < DM; ++i) {
         if (i < d) {
             q[i] = (swap ? a1[i] : a0[i]) * inv_f;
             g = fma(q[i], swap ? a0[i] : a1[i], g);
@@ -53,7 +56,7 @@ GPA_HD inline void lsq_solve2(const double (&a0)[kMaxD], const double (&a1)[kMax
 #pragma unroll
     for (int k = 0; k < NRHS; ++k) z2h[k] = 0.0;
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) {
+    for (int i = 0; i < DM; ++i) {
         if (i < d) {
             const double e = (swap ? a0[i] : a1[i]) - g * q[i];
             h2 = fma(e, e, h2);

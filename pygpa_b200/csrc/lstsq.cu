@@ -24,14 +24,15 @@ struct LsqParams {
     int use_matrix;
 };
 
+template <int DM>
 __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= p.n || c >= p.m) return;
-    double b[kMaxD];
+    double b[DM];
     const long long o = p.base + (long long)r * p.rs + (long long)c * p.cs;
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) {
+    for (int i = 0; i < DM; ++i) {
         if (i < p.d) {
             double v = p.src[o + i * p.ps];
             if (p.doff) v = p.src[o + i * p.ps + p.doff] - v;
@@ -43,16 +44,16 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
     double x0 = 0.0, x1 = 0.0;
     if (p.use_matrix) {
 #pragma unroll
-        for (int i = 0; i < kMaxD; ++i) {
+        for (int i = 0; i < DM; ++i) {
             if (i < p.d) {
                 x0 = fma(p.P[0][i], b[i], x0);
                 x1 = fma(p.P[1][i], b[i], x1);
             }
         }
     } else {
-        double a0[kMaxD], a1[kMaxD], y[1][kMaxD], x[1][2];
+        double a0[DM], a1[DM], y[1][DM], x[1][2];
 #pragma unroll
-        for (int i = 0; i < kMaxD; ++i) {
+        for (int i = 0; i < DM; ++i) {
             if (i < p.d) {
                 const double w = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
                 a0[i] = w * p.K[i][0];
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
                 y[0][i] = w * b[i];
             }
         }
-        lsq_solve2<1>(a0, a1, y, p.d, x);
+        lsq_solve2<1, DM>(a0, a1, y, p.d, x);
         x0 = x[0][0];
         x1 = x[0][1];
     }
@@ -181,7 +182,8 @@ extern "C" int gpa_lstsq_u(const double* src, int src_kind, const double* w, int
     {
         KernelTimer t("k_lstsq", st);
         dim3 grid(ceil_div(p.m, 64), ceil_div(p.n, 4));
-        k_lstsq<<<grid, 256, 0, st>>>(p);
+        if (d <= 3) k_lstsq<3><<<grid, 256, 0, st>>>(p);
+        else k_lstsq<kMaxD><<<grid, 256, 0, st>>>(p);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;

@@ -29,15 +29,16 @@ struct Grad2JParams {
     double nmperpixel;
 };
 
+template <int DM>
 __global__ void __launch_bounds__(256) k_grad2J(const Grad2JParams p) {
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= p.N || c >= p.M) return;
     const size_t pix = (size_t)r * p.M + c;
     const size_t npix = (size_t)p.N * p.M;
-    double a0[kMaxD], a1[kMaxD], y[2][kMaxD], x[2][2];
+    double a0[DM], a1[DM], y[2][DM], x[2][2];
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) {
+    for (int i = 0; i < DM; ++i) {
         if (i < p.d) {
             const double w = p.w[(size_t)i * p.wn * p.wm + (size_t)r * p.wm + c];
             const double2 g = *reinterpret_cast<const double2*>(p.grads + ((size_t)p.order[i] * npix + pix) * 2);
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) k_grad2J(const Grad2JParams p) {
             y[1][i] = w * b1;
         }
     }
-    lsq_solve2<2>(a0, a1, y, p.d, x);
+    lsq_solve2<2, DM>(a0, a1, y, p.d, x);
     // J[i][j] = d u_i / d x_j: right-hand side j (gradient along axis j) gives column j
     const double id = p.add_identity ? 1.0 : 0.0;
     double2* out = reinterpret_cast<double2*>(p.J + pix * 4);
@@ -106,7 +107,8 @@ extern "C" int gpa_phasegradient_to_j(const double* grads, const double* weights
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KernelTimer t("k_grad2J", st);
     dim3 grid(ceil_div(M, 64), ceil_div(N, 4));
-    k_grad2J<<<grid, 256, 0, st>>>(p);
+    if (d <= 3) k_grad2J<3><<<grid, 256, 0, st>>>(p);
+    else k_grad2J<kMaxD><<<grid, 256, 0, st>>>(p);
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }

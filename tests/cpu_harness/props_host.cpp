@@ -42,7 +42,7 @@ void host_lsq2(const double* a, const double* y, long n, int d, double* x) {
             yy[0][i] = y[(p * 2 + 0) * d + i];
             yy[1][i] = y[(p * 2 + 1) * d + i];
         }
-        gpa::lsq_solve2<2>(a0, a1, yy, d, xx);
+        gpa::lsq_solve2<2, gpa::kMaxD>(a0, a1, yy, d, xx);
         for (int k = 0; k < 4; ++k) x[4 * p + k] = xx[k / 2][k % 2];
     }
 }

@@ -415,3 +415,61 @@ def test_full_size_properties_config3():
     m = far[0][:, None] & far[1][None, :]
     assert m.mean() > 0.6
     assert (c["kidx"].cpu().numpy() == rolled)[m].mean() > 0.999
+
+
+def test_config5_size_8192_spot_check():
+    """BASELINE config 5 size (8192^2, 41x41 candidates), one peak.  The frame is synthesised on the
+    device (torch, float64: test plumbing only) because the NumPy generator needs ~40 s at this size; an
+    independent float64 Gabor sum on patches copied back checks phase, amplitude and that no
+    neighbouring candidate beats the winner.  fp32 carriers would lose 5e-4 rad at x ~ 8192: the
+    kernels build them in fp64 with range reduction, which this test would catch."""
+    dev = engine.require_cuda()
+    n, sigma, ng = 8192, 10, 41
+    ks = synth.primary_ks(0.05, 7.0, 3)
+    kw, kstep = synth.sweep_params(ks, ng)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.arange(n, dtype=torch.float64, device=dev)[:, None]
+    y = torch.arange(n, dtype=torch.float64, device=dev)[None, :]
+    ux = 6.0 * torch.sin(2 * np.pi * (1.3 * x + 0.4 * y) / n) * torch.cos(2 * np.pi * 0.9 * y / n)
+    uy = 5.0 * torch.cos(2 * np.pi * (0.7 * x - 1.1 * y) / n)
+    img64 = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for k in ks:
+        img64 += torch.cos(2 * np.pi * (k[0] * (x + ux) + k[1] * (y + uy)))
+    img64 += 0.3 * torch.randn((n, n), dtype=torch.float64, device=dev, generator=g)
+    img64 -= img64.mean()
+    del ux, uy
+    img = img64.float()
+    k = ks[0]
+    wxs, wys = engine.grid_axes(k[0], k[1], kw, kstep)
+    assert len(wxs) == ng and len(wys) == ng
+    plan = engine.SweepPlan((n, n), wxs, wys, sigma, device=dev)
+    assert plan.mr is not None
+    a = plan.run(img, k)
+    kidx = a["kidx"]
+    assert kidx.min().item() >= 0 and kidx.max().item() < ng * ng
+    # the winners follow the local lattice: a smooth map, not the grid centre everywhere
+    assert torch.unique(kidx).numel() > 50
+    r = 6 * sigma
+    d = np.arange(-r, r + 1)
+    gw = np.exp(-d ** 2 / (2.0 * sigma ** 2)) / (sigma * np.sqrt(2 * np.pi))
+    rng = np.random.default_rng(1)
+    pts = [(5, 8190), (8191, 3), (4096, 4096)] + [tuple(rng.integers(0, n, size=2)) for _ in range(9)]
+    for px, py in pts:
+        xs, ys = (px + d) % n, (py + d) % n
+        patch = img64[torch.as_tensor(xs, device=dev)][:, torch.as_tensor(ys, device=dev)].cpu().numpy()
+
+        def gabor(wx, wy):
+            return (gw[:, None] * gw[None, :] * patch * np.exp(2j * np.pi * (wx * xs[:, None] + wy * ys[None, :]))).sum()
+        ix, iy = divmod(int(kidx[px, py].item()), ng)
+        s = gabor(wxs[ix], wys[iy])
+        rot = np.exp(-2j * np.pi * ((wxs[ix] - k[0]) * px + (wys[iy] - k[1]) * py))
+        lock = complex(a["lockin"][px, py].item())
+        assert abs(np.angle(lock * np.conj(s * rot))) < 1e-3
+        assert abs(abs(lock) - abs(s)) < 1e-4 * abs(s) + 1e-6
+        for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            jx, jy = ix + dx, iy + dy
+            if 0 <= jx < ng and 0 <= jy < ng:
+                assert abs(gabor(wxs[jx], wys[jy])) <= abs(s) * (1 + NEAR_TIE)
+    del a, plan
+    engine.release_workspaces()
+    torch.cuda.empty_cache()
