@@ -41,3 +41,29 @@ def test_version_and_error_string():
     assert planes <= nbytes.value < planes * 1.05
     with pytest.raises(_lib.GpaError):
         _lib.check(-1)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the 8(f) entry points run before any CUDA call: invalid input -> GPA_ERR_INVALID
+    (-1) and a message, never a crash."""
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    null = ctypes.c_void_p(0)
+    assert lib.gpa_props_from_jac(null, 10, 0.0, 1.0, 0, 0, null, null) == -1
+    assert b"null" in lib.gpa_last_error()
+    k = (ctypes.c_double * 6)(*([0.1] * 6))
+    assert lib.gpa_phasegradient_to_j(null, null, 4, 4, k, None, None, 0, 3, 4, 4, 1.0, 0, null, null) == -1
+    assert lib.gpa_deconvolve_workspace_bytes(4100, 64, 8, ctypes.byref(nbytes)) == -1      # 4132 > 4096 samples
+    assert b"exceeds" in lib.gpa_last_error()
+    assert lib.gpa_deconvolve_workspace_bytes(12, 64, 8, ctypes.byref(nbytes)) == -1        # reflect padding too wide
+    assert lib.gpa_deconvolve_workspace_bytes(2048, 2048, 20, ctypes.byref(nbytes)) == 0
+    assert nbytes.value >= 2 * 2128 * 2128 * 16
+    assert lib.gpa_uc_workspace_bytes(0, 5, ctypes.byref(nbytes)) == -1
+    assert lib.gpa_uc_workspace_bytes(100, 120, ctypes.byref(nbytes)) == 0 and nbytes.value >= 4 * 100 * 120 * 8
+    assert lib.gpa_fit_plane_workspace_bytes(ctypes.byref(nbytes)) == 0 and nbytes.value > 19 * 1184 * 8
+    th = (ctypes.c_double * 3)()
+    assert lib.gpa_fit_plane_huber(null, 8, 8, 1.0, 10, 1e-9, th, None, null, 0, null) == -1
+    assert lib.gpa_wfr4_sweep(null, 64, 64, k, k, 3, null, None, 2, None, 2, 0.0, 0.0, 1, null, null, null, null,
+                              null, 0, null) == -1
+    assert lib.gpa_unwrap_workspace_bytes(1014, 1014, ctypes.byref(nbytes)) == 0             # Bluestein tables included
+    assert nbytes.value > 7 * 1014 * 1014 * 8 + 2 * 2048 * 16
