@@ -99,23 +99,49 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
         ranges = shard_units_interleaved(n_peaks, plans[0].wy.size, world, rank)
     else:
         ranges = [(lo, hi, 1) for lo, hi in shard_units(n_peaks, plans[0].wy.size, world, rank)]
+    # The peaks are independent until the collectives.  With private workspaces their kernels go to one
+    # stream per peak: a rank's share of one peak is only a few planes (5 of 41 on 8 GPUs = 320 pass-2
+    # CTAs = 2.2 waves of the 148 SMs, which run as 3), so the tail of one peak is filled by the next.
+    side = _peak_streams(dev, n_peaks) if dev.type == "cuda" and all(p._private for p in plans) else None
     keys = torch.zeros((n_peaks, n, m), dtype=torch.int64, device=dev)
-    for p, (plan, (lo, hi, step)) in enumerate(zip(plans, ranges)):
+
+    def per_peak(fn):
+        if side is None:
+            for p in range(n_peaks):
+                fn(p)
+            return
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        for p in range(n_peaks):
+            side[p].wait_event(start)
+            with torch.cuda.stream(side[p]):
+                fn(p)
+            done = torch.cuda.Event()
+            done.record(side[p])
+            main.wait_event(done)
+
+    def argmax_peak(p):
+        lo, hi, step = ranges[p]
         if hi > lo:
-            plan.argmax(img_dev, keys[p], lo, hi, step)
+            plans[p].argmax(img_dev, keys[p], lo, hi, step)
+    per_peak(argmax_peak)
     dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
     want_grad = grad_mode != 2
     # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)] float32, zero where this rank owns nothing
     payload = torch.zeros((2 if want_grad else 1, n_peaks, n, m, 2), dtype=torch.float32, device=dev)
     lockin = torch.view_as_complex(payload[0])
-    outs = []
-    for p, (plan, kref, (lo, hi, step)) in enumerate(zip(plans, krefs, ranges)):
-        out = {"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None}
+    outs = [{"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None}
+            for p in range(n_peaks)]
+
+    def finalize_peak(p):
+        lo, hi, step = ranges[p]
         if hi > lo:
-            plan.finalize(img_dev, keys[p], kref, grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
-                          planes_valid=plan._private, out=out, plane_step=step)
-        out["key"] = keys[p]
-        outs.append(out)
+            plans[p].finalize(img_dev, keys[p], krefs[p], grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
+                              planes_valid=plans[p]._private, out=outs[p], plane_step=step)
+    per_peak(finalize_peak)
+    for p in range(n_peaks):
+        outs[p]["key"] = keys[p]
     if dst is None:
         dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
     else:
@@ -129,3 +155,14 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     for p, o in enumerate(outs):
         o["kidx"] = kidx[p]
     return outs
+
+
+_side_streams = {}
+
+
+def _peak_streams(dev, n):
+    """One side stream per peak and device, created once."""
+    pool = _side_streams.setdefault(str(dev), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
