@@ -196,7 +196,7 @@ def run_ours(args, cfg):
     for k in ks:
         wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
         assert len(wxs) == NGRID and len(wys) == NGRID
-        plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=world > 1))
+        plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=True))
     taps = 2 * plans[0].rx + 1
 
     def step():

@@ -77,7 +77,8 @@ def merge_payload(tensors, group=None):
 def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     """All peaks of one frame, k-grid sharded over the ranks of `group`.
     plans: one engine.SweepPlan per peak (identical on every rank; give them private workspaces so
-    the finalize reuses what the arg-max left and stays bit-identical to one GPU).
+    the finalize reuses what the arg-max left and stays bit-identical to one GPU).  A single rank with
+    private multirate plans takes the same route (no collectives): its peaks overlap on their streams.
     Returns [dict(lockin, grad, kidx, key)] per peak — on every rank, or with dst=<rank> the payload
     (lockin, grad) is only reduced to that rank.
 
@@ -89,9 +90,10 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     frame on 2 GPUs, against 0.75 ms for the two collectives issued at the end)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if world == 1:
-        return [plan.run(img_dev, kref, grad_mode) for plan, kref in zip(plans, krefs)]
     n_peaks, n, m, dev = len(plans), plans[0].n, plans[0].m, img_dev.device
+    private = all(p._private and p.mr is not None and p.mr_in_flight == p.wy.size for p in plans)
+    if world == 1 and not (private and dev.type == "cuda"):
+        return [plan.run(img_dev, kref, grad_mode) for plan, kref in zip(plans, krefs)]
     # multirate plans with their own workspace take an interleaved share (good pruning thresholds on
     # every rank); otherwise contiguous plane ranges
     interleave = all(p.mr is not None and p._private and p.mr_in_flight >= -(-p.wy.size // world) for p in plans)
@@ -126,7 +128,8 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
         if hi > lo:
             plans[p].argmax(img_dev, keys[p], lo, hi, step)
     per_peak(argmax_peak)
-    dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    if world > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
     want_grad = grad_mode != 2
     # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)] float32, zero where this rank owns nothing
     payload = torch.zeros((2 if want_grad else 1, n_peaks, n, m, 2), dtype=torch.float32, device=dev)
@@ -142,7 +145,9 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
     per_peak(finalize_peak)
     for p in range(n_peaks):
         outs[p]["key"] = keys[p]
-    if dst is None:
+    if world == 1:
+        pass
+    elif dst is None:
         dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
     else:
         dist.reduce(payload, dst=dst, op=dist.ReduceOp.SUM, group=group)
