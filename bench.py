@@ -340,6 +340,18 @@ def run_ours(args, cfg):
         _dec, d_ms2 = timed(lambda: solvers.gaussian_deconvolve(u, cfg["sigma"], dr))
         _cell, c_ms = timed(lambda: uc_b200.unit_cell_average_device(img64, ks[:2], u, z=2))
         _fit, f_ms = timed(lambda: solvers.fit_plane_huber(u[0]))
+        # BASELINE config 3 names "+ weighted phase_unwrap": per peak, weights sqrt(|lockin| / max) as iterate_GPA
+        # uses them (geometric_phase_analysis.py:141), kmax = 100
+        def unwrap_peaks():
+            its = []
+            for o in outs:
+                ph, amp, amax = solvers.lockin_phase_amp(o["lockin"], 0)
+                _phi, it = solvers.unwrap(psi=ph, weight=solvers.weight_sqrt_norm(amp, amax), kmax=100, return_iters=True)
+                its.append(it)
+            return its
+        lib.gpa_profile_enable(0)            # keep these solves out of the uw_* event timers of the tail above
+        uw_iters, uw3_ms = timed(unwrap_peaks)
+        lib.gpa_profile_enable(1)
         # transparency: the same sweep with the (exact) branch-and-bound pruning switched off
         engine.set_pruning(False)
         step()
@@ -375,6 +387,8 @@ def run_ours(args, cfg):
             "lstsq": {"ms": prof["k_lstsq"][0], "bound": "hbm", "achieved_gbs": ls_gbs, "peak_gbs": hbm, "frac": ls_gbs / hbm,
                       "basis": "64 B/pixel (SURVEY 8d) x 2 solves"},
             "kernels_ms": {k_: v[0] for k_, v in prof.items()},
+            "weighted_phase_unwrap_3_peaks": {"ms": uw3_ms, "pcg_iterations": uw_iters, "kmax": 100,
+                                              "what": "phase_unwrap(angle(lockin), sqrt(|lockin| / max)) per peak, device resident"},
             "consumers_ms": {
                 "what": "SURVEY 8f rows on the C3 frame, device resident, one call each (float64, HBM-bound streaming kernels)",
                 "phasegradient2Jac": j_ms, "phasegradient2Jac_gbs": 104.0 * SIZE * SIZE / (j_ms / 1e3) / 1e9,
