@@ -234,7 +234,8 @@ def run_ours(args, cfg):
     gpu_launches = engine.launch_count - launches0
     tot, n = ctypes.c_double(0), ctypes.c_int(0)
     kernels = {}
-    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_interp", "k_mr_finalize", "k_pass1", "k_pass2_argmax", "k_finalize")
+    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize",
+             "k_pass1", "k_pass2_argmax", "k_finalize")
     for name in names:
         _lib.check(lib.gpa_profile_read(name.encode(), ctypes.byref(tot), ctypes.byref(n), 0))
         kernels[name] = (tot.value, n.value)
@@ -442,6 +443,12 @@ def run_ours(args, cfg):
             w_eff = (11 + 10 * (S - 1)) / S
             flop_per_unit = 4 * w_eff * (1 + 1.0 / S) + 3
             basis = f"multirate form, stride {S}: 4*{w_eff:.2f}*(1+1/{S})+3 = {flop_per_unit:.1f} flop per pixel*kvec (tile halos not counted)"
+        elif dom == "k_mr_pass2b":
+            # split pass 2, coarse-rate stage: per COARSE output and candidate (2H+1) real-tap x complex-sample
+            # MACs (4 flop) + one demodulation and one de-rotation (6 flop each); a unit is S^2 coarse outputs
+            S, jb = mr["S"], 2 * plans[0].split["H"] + 1
+            flop_per_unit = (4 * jb + 12) / (S * S)
+            basis = f"split pass 2, coarse stage, stride {S}: (4*{jb} + 12)/S^2 = {flop_per_unit:.2f} flop per pixel*kvec"
         elif dom == "k_mr_pass2":
             S = mr["S"]
             flop_per_unit = (4 * (2 * mr["Ra_x"] + 1) + 8 * S) / (S * S)
@@ -485,7 +492,7 @@ def run_ours(args, cfg):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "working set per step (3 x 1.44 GB of first-pass planes) exceeds L2; no flush needed",
                        "parallelism": f"k-grid sharded over {world} GPU(s)", "filter": f"{taps} taps (4.5 sigma)",
-                       "argmax_form": (f"multirate, stride {mr['S']}" if mr else "direct"),
+                       "argmax_form": (f"multirate, stride {mr['S']}" + (f", split pass 2 ({2 * plans[0].split['H'] + 1} coarse taps per candidate)" if plans[0].split else "") if mr else "direct"),
                        "pruning": "exact per-tile branch and bound on (results bit-identical to off; pipeline.sweep_ms_per_step_without_pruning gives the off time)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
             "pipeline": pipeline, "cugpa_equivalent": cugpa,

@@ -145,14 +145,25 @@ int gpa_sweep_argmax(const float* img, int N, int M,
  * bit-identical with it on or off; it only changes how much work is done).  On by default. */
 int gpa_set_pruning(int on);
 
+/* Split pass 2 (R1x > 0; candidate grids only).  All candidates of a plane share their full-rate
+ * filtering: G_a = G_1 * G_2 (sigma_a^2 = sigma_1^2 + sigma_2^2), the plane is demodulated by the
+ * ANCHOR wx0 = wx_rows[n_rows / 2] and filtered by G_1 once (decimating), and every candidate
+ * wx = wx0 + dw then costs a (2 H2x + 1)-tap filter at the COARSE rate: demodulate the coarse samples by
+ * delta = dw sigma_a^2 / sigma_2^2, apply G_2, scale by exp(2 pi^2 dw^2 sigma_a^2 sigma_1^2 / sigma_2^2) and
+ * rotate back — exactly G_a centred on wx, because G_1(f) G_2(f + delta) is that Gaussian.  The rows that
+ * wrapped around the frame edge (whose carrier phase jumps by dw N, as the reference's does) are carried
+ * separately through the anchor stage.  taps_1x: G_1 (2 R1x + 1 fine taps); taps_2x: S G_2(S m), |m| <= H2x.
+ * R1x = 0 selects the single-stage pass 2 (taps_1x, taps_2x, sigma_a, sigma_1 ignored). */
 int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int stride,
-                                 int Rax, int Ray, int Rb, int planes_in_flight, size_t* bytes);
+                                 int Rax, int Ray, int Rb, int R1x, int H2x, int planes_in_flight, size_t* bytes);
 int gpa_sweep_argmax_mr(const float* img, int N, int M,
                         const double* wx_rows /*host*/, int n_rows,
                         const double* wy_planes /*host*/, int n_planes, int cand_mode,
                         int plane_begin, int plane_end, int plane_step, int stride,
                         const float* taps_ax /*host*/, int Rax, const float* taps_ay /*host*/, int Ray,
                         const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
+                        const float* taps_1x /*host*/, int R1x, const float* taps_2x /*host*/, int H2x,
+                        double sigma_a, double sigma_1,
                         unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
 
 /* gpa_sweep_finalize computed from the coarse grids gpa_sweep_argmax_mr left in ws (same ws, same
@@ -163,6 +174,7 @@ int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows /*host*/, int n_ro
                           const double* wy_planes /*host*/, int n_planes, int cand_mode,
                           int plane_begin, int plane_end, int plane_step, int stride, int Rax, int Ray,
                           const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
+                          int R1x, int H2x,
                           const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
                           int out_f64, void* lockin, void* grad, void* w, int* kidx,
                           void* ws, size_t ws_bytes, void* stream);

@@ -74,3 +74,70 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
                     taps_ax=_kernel_taps(n, sigma_a, ra), taps_ay=_kernel_taps(m, sigma_a, ra),
                     taps_bx=_kernel_taps(n, sigma_b, rb), taps_by=_kernel_taps(m, sigma_b, rb))
     return None
+
+
+# ---- split pass 2: G_a = G_1 * G_2, anchor stage shared by the candidates of a plane ---------------
+SPLIT_TOL = 1.3e-6       # worst-case transfer-function error; the 4.5 sigma truncation of G_a alone is 1.3e-6
+SPLIT_TRUNC1 = 6.0       # stage A runs once per plane: its truncation is free
+
+
+def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
+    """max over input frequency f (cycles / fine pixel, relative to the anchor) of
+    |c G_1t(f) h_t(S (f + delta)) - G_a(f + dw)|: the split pipeline's response to e^{2 pi i f x}
+    against the ideal candidate-centred Gaussian, truncation and coarse-rate aliasing included."""
+    sigma_2 = np.sqrt(sigma_a ** 2 - sigma_1 ** 2)
+    f = (np.arange(nf) - nf // 2) / nf
+    d = np.arange(-r1, r1 + 1)
+    g1 = np.exp(-d ** 2 / (2 * sigma_1 ** 2)) / (sigma_1 * np.sqrt(2 * np.pi))
+    G1 = np.exp(-2j * np.pi * np.outer(f, d)) @ g1
+    m = np.arange(-h, h + 1)
+    h2 = s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))
+    delta = dw * sigma_a ** 2 / sigma_2 ** 2
+    c = np.exp(2 * np.pi ** 2 * dw ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)
+    H2 = np.exp(-2j * np.pi * np.outer(s * (f + delta), m)) @ h2
+    return float(np.abs(c * G1 * H2 - np.exp(-2 * np.pi ** 2 * sigma_a ** 2 * (f + dw) ** 2)).max())
+
+
+@functools.lru_cache(maxsize=64)
+def _split_plan(n, s, sigma_a, dw_max):
+    for h in (6, 7, 8, 9, 10, 11):                       # 13 ... 23 coarse taps per candidate
+        best = None
+        for s2c in np.arange(1.35, min(h / 4.4, 2.4) + 1e-9, 0.05):      # coarse-rate sigma of G_2
+            sigma_2 = float(s2c * s)
+            if sigma_2 >= 0.98 * sigma_a:
+                break
+            sigma_1 = float(np.sqrt(sigma_a ** 2 - sigma_2 ** 2))
+            r1 = int(np.ceil(SPLIT_TRUNC1 * sigma_1))
+            j1 = -(-(2 * r1 + 1) // s)
+            j1 = max(18, j1 + (j1 & 1))                 # even, >= 18: the statically scheduled stage-A kernels
+            r1 = (s * j1 - 1) // 2
+            if r1 + s * (h + 1) > n or n // s <= 2 * (-(-r1 // s) + 1) or s * j1 + 2 > MAX_TAPS:
+                continue
+            err = max(_split_error(s, sigma_a, sigma_1, r1, h, dw) for dw in (dw_max, 0.5 * dw_max))
+            if best is None or err < best[0]:
+                best = (err, sigma_1, sigma_2, r1)
+        if best is not None and best[0] <= SPLIT_TOL:
+            err, sigma_1, sigma_2, r1 = best
+            d = np.arange(-r1, r1 + 1)
+            t1 = (np.exp(-d ** 2 / (2 * sigma_1 ** 2)) / (sigma_1 * np.sqrt(2 * np.pi))).astype(np.float32)
+            m = np.arange(-h, h + 1)
+            t2 = (s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))).astype(np.float32)
+            t1.setflags(write=False)
+            t2.setflags(write=False)
+            return dict(R1=r1, H=h, sigma_1=sigma_1, sigma_2=sigma_2, taps_1=t1, taps_2=t2, err=err,
+                        c_max=float(np.exp(2 * np.pi ** 2 * dw_max ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)))
+    return None
+
+
+def split_taps(n, mr, wx_rows):
+    """Parameters of the split pass 2 (csrc/lockin.cu, k_mr_pass2b) for an axis of length n, the
+    multirate plan ``mr`` and the candidate axis ``wx_rows``, or None when no factorisation
+    G_a = G_1 * G_2 meets SPLIT_TOL with at most 23 coarse taps (wide grids: the candidates then
+    keep their own full-rate pass 2).  The anchor is wx_rows[len // 2]."""
+    wx = np.asarray(wx_rows, dtype=np.float64)
+    if wx.size < 8:
+        return None
+    dw_max = float(np.abs(wx - wx[wx.size // 2]).max())
+    # quantise dw_max upwards so that plans of neighbouring peaks share the cached search
+    q = 2.0 ** (np.floor(np.log2(max(dw_max, 1e-12))) - 4)
+    return _split_plan(int(n), int(mr["S"]), float(mr["sigma_a"]), float(np.ceil(dw_max / q) * q))

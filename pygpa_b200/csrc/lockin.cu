@@ -550,7 +550,7 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
         for (int hb = 0; hb < kP / kPmB; ++hb) {
 #pragma unroll
             for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
-            if ((lane & (kPmB - 1)) == 0)
+            if ((lane & (kPmB - 1)) == 0 && prm.pmax != nullptr)
                 prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
                          (my0 + lane) / kPmB] = a2max[hb];
         }
@@ -637,12 +637,202 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
         for (int hb = 0; hb < kP / kPmB; ++hb) {
 #pragma unroll
             for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
-            if ((lane & (kPmB - 1)) == 0)
+            if ((lane & (kPmB - 1)) == 0 && prm.pmax != nullptr)
                 prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
                          (my0 + lane) / kPmB] = a2max[hb];
         }
         cp_async_wait_all();
         group_sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split pass 2: one shared anchor stage per plane + a coarse-rate stage per candidate
+// ---------------------------------------------------------------------------------------------
+// The candidates of one plane differ only in the axis-0 carrier, wx = wx0 + dw with |dw| far below
+// the decimated band, so the full-rate part of the decimating filter can be shared.  Factorise
+// G_a = G_1 * G_2 (sigma_a^2 = sigma_1^2 + sigma_2^2) and demodulate by the ANCHOR wx0 only:
+//   stage A (per plane, k_mr_pass2 / k_mr_pass2s with a two-row carrier table)
+//       A(e) = sum_x' G_1(S (e - H) - x') P1(t(x')) e^{2 pi i wx0 t(x')},   e in [0, Nd + 2H)
+//   stage B (per candidate, k_mr_pass2b, coarse rate)
+//       P2(mx) = c e^{2 pi i (dw - delta) S mx} sum_j h[j] e^{2 pi i delta S (mx + j - H)} A(mx + j)
+//       h[j] = S G_2(S (j - H)),  delta = dw sigma_a^2 / sigma_2^2,  c = exp(2 pi^2 dw^2 sigma_a^2 sigma_1^2 / sigma_2^2)
+// In the frequency domain G_1(f) G_2(f + delta) c = G_a(f + dw): the product of the anchor-centred
+// G_1 and the shifted G_2 IS the candidate-centred G_a, so P2 equals the single-stage result up to
+// the truncation of the factors and the aliasing of the coarse-rate G_2 (both below the existing
+// 4.5 sigma truncation error for the parameters the host picks, pygpa_b200/_taps.py).
+// Frame border: the reference demodulates by the carrier of the WRAPPED index t, which differs from the
+// linear-phase ramp e^{2 pi i dw x'} by the constant J = e^{+-2 pi i dw N} on the rows that wrapped.
+// Stage A therefore keeps the wrapped rows' contribution apart (A_edge; non-zero only within
+// ceil(R_1/S) coarse rows of the frame edge) and stage B adds it back multiplied by J.
+struct SplitTabParams {
+    float2* phx1;      // [2][n_alloc]: anchor carrier masked to the frame body / to the wrapped halo rows
+    float2* carB;      // [n_cand][NdE]
+    float2* derotB;    // [n_cand][Nd]
+    float2* jB;        // [n_cand][2]
+    const double* wx_d;
+    double wx0, ratio /* sigma_a^2 / sigma_2^2 */, cexp /* 2 pi^2 sigma_a^2 sigma_1^2 / sigma_2^2 */;
+    int n_cand, N, S, H, Nd, NdE, n_alloc, Rtot;
+};
+
+__global__ void k_build_split_tables(const SplitTabParams p) {
+    const int c = blockIdx.y;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, tstep = gridDim.x * blockDim.x;
+    if (c == p.n_cand) {
+        for (int r = t0; r < p.n_alloc; r += tstep) {
+            const int xu = r - p.Rtot;
+            int t = xu % p.N;
+            if (t < 0) t += p.N;
+            const float2 ph = phasor_turns(p.wx0 * (double)t);
+            const bool body = xu >= 0 && xu < p.N;
+            const float2 zero = make_float2(0.f, 0.f);
+            p.phx1[r] = body ? ph : zero;
+            p.phx1[p.n_alloc + r] = body ? zero : ph;
+        }
+        return;
+    }
+    const double dw = p.wx_d[c] - p.wx0;
+    const double delta = dw * p.ratio;
+    const float cs = (float)exp(p.cexp * dw * dw);
+    for (int e = t0; e < p.NdE; e += tstep) p.carB[(size_t)c * p.NdE + e] = phasor_turns(delta * (double)(p.S * (e - p.H)));
+    for (int mx = t0; mx < p.Nd; mx += tstep) {
+        const float2 d = phasor_turns((dw - delta) * (double)(p.S * mx));
+        p.derotB[(size_t)c * p.Nd + mx] = make_float2(cs * d.x, cs * d.y);
+    }
+    if (t0 == 0) {
+        p.jB[2 * c] = phasor_turns(dw * (double)p.N);
+        p.jB[2 * c + 1] = phasor_turns(-dw * (double)p.N);
+    }
+}
+
+struct MrPass2bParams {
+    const float2* A;        // [chunk][2][NdE][Md]: body / edge parts of the anchor stage
+    const float2* carB;
+    const float2* derotB;
+    const float2* jB;
+    float2* p2;             // [chunk][n_cand][Nd][Md]
+    float* pmax;            // [chunk][n_cand][nbx][nby]
+    int Nd, Md, NdE, H, EB /* coarse rows next to the frame edge that A_edge reaches */, n_cand, nbx, nby;
+};
+
+// CTA: kWarps * kP coarse output rows x 32 coarse columns (lane = column) of one plane; the A tile is
+// staged once and every candidate of the plane streams through: per-candidate carrier / de-rotation
+// rows by cp.async (double buffered, one barrier per candidate), JB-tap FIR along the rows with the
+// taps in registers and compile-time tap / accumulator indices (as k_mr_pass2s).
+template <int JB>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
+    constexpr int TO = kWarps * kP;            // output rows per CTA
+    constexpr int TR = TO + JB - 1;            // A rows per CTA
+    constexpr int NT = kWarps * 32;
+    extern __shared__ float2 smem[];
+    float2* const tB = smem;                   // [TR][32]
+    float2* const tE = tB + TR * kLanes;       // [TR][32]
+    float2* const scar = tE + TR * kLanes;     // [2][TR]
+    float2* const sder = scar + 2 * TR;        // [2][TO]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int my0 = blockIdx.x * kLanes;
+    const int mx0 = blockIdx.y * TO;
+    const int pl = blockIdx.z;
+    const int Nd = prm.Nd, Md = prm.Md, NdE = prm.NdE;
+    const float2 zero = make_float2(0.f, 0.f);
+    const int lo_end = prm.H + prm.EB, hi_begin = Nd + prm.H - prm.EB;     // A_edge is zero on rows [lo_end, hi_begin)
+    {
+        const float2* __restrict__ Ab = prm.A + (size_t)pl * 2 * NdE * Md;
+        const float2* __restrict__ Ae = Ab + (size_t)NdE * Md;
+        const bool cta_edge = mx0 < lo_end || mx0 + TR > hi_begin;
+        for (int i = threadIdx.x; i < TR * kLanes; i += NT) {
+            const int e = mx0 + i / kLanes, col = my0 + i % kLanes;
+            if (e < NdE && col < Md) {
+                cp_async8(tB + i, Ab + (size_t)e * Md + col);
+                if (cta_edge) cp_async8(tE + i, Ae + (size_t)e * Md + col);
+            } else {
+                tB[i] = zero;
+                if (cta_edge) tE[i] = zero;
+            }
+        }
+        cp_async_commit();
+    }
+    auto stage = [&](int c, int slot) {
+        for (int j = threadIdx.x; j < TR + TO; j += NT) {
+            if (j < TR) {
+                const int e = mx0 + j;
+                if (e < NdE) cp_async8(scar + slot * TR + j, prm.carB + (size_t)c * NdE + e);
+                else scar[slot * TR + j] = zero;
+            } else {
+                const int mx = mx0 + j - TR;
+                if (mx < Nd) cp_async8(sder + slot * TO + j - TR, prm.derotB + (size_t)c * Nd + mx);
+                else sder[slot * TO + j - TR] = zero;
+            }
+        }
+        cp_async_commit();
+    };
+    stage(0, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    const int e0 = mx0 + warp * kP;                          // first A row of this warp
+    const bool edge = e0 < lo_end || e0 + kP + JB - 1 > hi_begin;   // warp-uniform
+    const int e_mid = prm.H + Nd / 2;                        // rows below wrapped downwards (J_lo), the others upwards (J_hi)
+    const float2* colB = tB + (warp * kP) * kLanes + lane;
+    const float2* colE = tE + (warp * kP) * kLanes + lane;
+    const int my = my0 + lane;
+    float2 g[JB];
+#pragma unroll
+    for (int j = 0; j < JB; ++j) g[j] = taps.g[j];
+    for (int c = 0; c < prm.n_cand; ++c) {
+        const int slot = c & 1;
+        if (c + 1 < prm.n_cand) stage(c + 1, slot ^ 1);
+        const float2* car = scar + slot * TR + warp * kP;
+        float2 acc[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) acc[p] = zero;
+        if (!edge) {
+#pragma unroll
+            for (int k = 0; k < kP + JB - 1; ++k) {
+                const float2 smp = cmul(colB[k * kLanes], car[k]);
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+                    if (k - p >= 0 && k - p < JB) acc[p] = __ffma2_rn(g[k - p], smp, acc[p]);
+            }
+        } else {
+            const float2 jlo = __ldg(prm.jB + 2 * c), jhi = __ldg(prm.jB + 2 * c + 1);
+#pragma unroll
+            for (int k = 0; k < kP + JB - 1; ++k) {
+                const float2 jj = (e0 + k < e_mid) ? jlo : jhi;
+                const float2 ed = cmul(colE[k * kLanes], jj);
+                const float2 bd = colB[k * kLanes];
+                const float2 smp = cmul(make_float2(bd.x + ed.x, bd.y + ed.y), car[k]);
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+                    if (k - p >= 0 && k - p < JB) acc[p] = __ffma2_rn(g[k - p], smp, acc[p]);
+            }
+        }
+        const float2* der = sder + slot * TO + warp * kP;
+        float2* out = prm.p2 + ((size_t)pl * prm.n_cand + c) * Nd * Md;
+        float a2max[kP / kPmB];
+#pragma unroll
+        for (int hb = 0; hb < kP / kPmB; ++hb) a2max[hb] = 0.f;
+        if (my < Md) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int mx = mx0 + warp * kP + p;
+                if (mx < Nd) {
+                    const float2 v = cmul(acc[p], der[p]);
+                    out[(size_t)mx * Md + my] = v;
+                    a2max[p / kPmB] = fmaxf(a2max[p / kPmB], fmaf(v.x, v.x, v.y * v.y));
+                }
+            }
+        }
+#pragma unroll
+        for (int hb = 0; hb < kP / kPmB; ++hb) {
+#pragma unroll
+            for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
+            if ((lane & (kPmB - 1)) == 0)
+                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
+                         (my0 + lane) / kPmB] = a2max[hb];
+        }
+        cp_async_wait_all();
+        __syncthreads();      // the next candidate's rows are complete; this one's are no longer read
     }
 }
 
@@ -1392,15 +1582,19 @@ static int g_prune_enabled = 1;
 struct MrGeometry {
     int N, M, S, Nd, Md, pitch_d, n_rows, n_planes, Rax, Ray, Rb, Jx, Jy, txd, warps2, n_alloc, n_rows_filled, n_cand;
     int nbx_alloc, nby_alloc, can_prune;
-    size_t plane_stride, p2_stride, pm_stride;   // elements per plane
+    // split pass 2 (R1 > 0): stage-A radius / taps per phase, stage-B coarse radius, extended coarse rows, row shift of P1
+    int R1, J1, H, NdE, row_shift;
+    size_t plane_stride, p2_stride, pm_stride, a_stride;   // elements per plane
     double *wx_d, *wy_d;
     float2 *phx, *phy, *p1, *p2;
+    float2 *a_st, *phx1, *carB, *derotB, *jB;    // split pass 2: stage-A output and the carrier tables
     float* pmax;
     unsigned short* perm;
     int chunk;
 };
 
-static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax, int Ray, int Rb) {
+static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax, int Ray, int Rb,
+                   int R1 = 0, int H = 0) {
     GPA_REQUIRE(S == 2 || S == 4 || S == 8, "multirate stride must be 2, 4 or 8 (got %d)", S);
     GPA_REQUIRE(N % S == 0 && M % S == 0, "frame (%d x %d) is not divisible by the stride %d", N, M, S);
     GPA_REQUIRE(n_rows >= 1 && n_planes >= 1, "empty candidate set");
@@ -1417,10 +1611,26 @@ static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int ca
     g.pitch_d = (int)align_up((size_t)g.Md, 32);
     g.n_alloc = S * (ceil_div(g.Nd, g.txd) * g.txd + g.Jx + kAhead + 1);
     g.n_rows_filled = N + S * g.Jx;
-    g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
+    g.row_shift = Rax;
     g.n_cand = cand_mode == GPA_CAND_GRID ? n_rows : 1;
+    g.R1 = R1; g.H = H; g.J1 = 0; g.NdE = 0; g.a_stride = 0;
+    if (R1 > 0) {
+        // split pass 2: P1 carries a halo of R1 + S H rows each side; stage A produces Nd + 2H coarse rows
+        GPA_REQUIRE(cand_mode == GPA_CAND_GRID, "the split pass 2 needs a candidate grid");
+        GPA_REQUIRE(H >= 1 && 2 * H + 1 <= 23, "split pass 2: coarse radius %d out of range", H);
+        GPA_REQUIRE(g.Nd >= 2 * (ceil_div(R1, S) + 1) && R1 + S * (H + 1) <= N,
+                    "split pass 2: stage-A radius %d does not fit the frame", R1);
+        g.J1 = ceil_div(2 * R1 + 1, S);
+        GPA_REQUIRE(S * g.J1 + kAhead <= kMaxTaps, "split pass 2: stage-A filter too long");
+        g.NdE = g.Nd + 2 * H;
+        g.row_shift = R1 + S * H;
+        g.n_alloc = S * (ceil_div(g.NdE, g.txd) * g.txd + g.J1 + kAhead + 1);
+        g.n_rows_filled = S * g.NdE + S * g.J1;
+        g.a_stride = (size_t)2 * g.NdE * g.Md;
+    }
+    g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
     g.p2_stride = (size_t)g.n_cand * g.Nd * g.Md;
-    g.nbx_alloc = ceil_div(g.Nd, g.txd) * (g.txd / kPmB);
+    g.nbx_alloc = ceil_div(g.Nd, kWarps * kP) * (kWarps * kP / kPmB);
     g.nby_alloc = g.pitch_d / kPmB;
     g.pm_stride = (size_t)g.n_cand * g.nbx_alloc * g.nby_alloc;
     g.can_prune = g.Nd % kPmB == 0 && g.Md % kPmB == 0 && g.n_cand <= kMaxPruneCand && g.n_planes <= 256;
@@ -1437,13 +1647,20 @@ static size_t carve_mr(MrGeometry& g, void* ws, size_t ws_bytes, int chunk) {
     g.p2 = a.take<float2>((size_t)chunk * g.p2_stride);
     g.pmax = a.take<float>((size_t)chunk * g.pm_stride);
     g.perm = a.take<unsigned short>((size_t)chunk * ceil_div(g.N, kMrTX) * ceil_div(g.M, kMrTY));
+    if (g.R1 > 0) {
+        g.a_st = a.take<float2>((size_t)chunk * g.a_stride);
+        g.phx1 = a.take<float2>((size_t)2 * g.n_alloc);
+        g.carB = a.take<float2>((size_t)g.n_cand * g.NdE);
+        g.derotB = a.take<float2>((size_t)g.n_cand * g.Nd);
+        g.jB = a.take<float2>((size_t)2 * g.n_cand);
+    }
     g.chunk = chunk;
     return a.off;
 }
 
 static int fit_chunk_mr(MrGeometry& g, void* ws, size_t ws_bytes, int want) {
     const size_t fixed = carve_mr(g, nullptr, 0, 0);
-    const size_t per_plane = (g.plane_stride + g.p2_stride) * sizeof(float2) + g.pm_stride * sizeof(float) +
+    const size_t per_plane = (g.plane_stride + g.p2_stride + g.a_stride) * sizeof(float2) + g.pm_stride * sizeof(float) +
                              (size_t)ceil_div(g.N, kMrTX) * ceil_div(g.M, kMrTY) * sizeof(unsigned short) + 1024;
     if (ws_bytes < fixed + per_plane + 512) return 0;
     size_t c = (ws_bytes - fixed - 512) / per_plane;
@@ -1484,12 +1701,13 @@ static int fill_interp(TapTable& t, const float* bx, const float* by, int Rb, in
 
 template <int S>
 static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, const TapTable& tx, const TapTable& tb,
-                     int plane0, int pstep, int count, int cand_mode, unsigned long long* key, cudaStream_t st) {
+                     const TapTable& t2, int plane0, int pstep, int count, int cand_mode, unsigned long long* key,
+                     cudaStream_t st) {
     {   // stage 1
         MrPass1Params p;
         p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
         p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
-        p.Rax = g.Rax; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0; p.pstep = pstep;
+        p.Rax = g.row_shift; p.Ray = g.Ray; p.J = g.Jy; p.plane0 = plane0; p.pstep = pstep;
         constexpr int W1 = 8;
         const size_t n_samp1 = (size_t)S * (W1 * kP + g.Jy + kAhead + 1);
         const size_t smem = (n_samp1 * 33 + 1) * sizeof(float) + 2 * n_samp1 * sizeof(float2);
@@ -1504,24 +1722,29 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         KernelTimer timer("k_mr_pass1", st);
         k_mr_pass1<S, W1><<<grid, W1 * 32, smem, st>>>(p, ty);
     }
-    {   // stage 2
+    {   // stage 2 (split: the anchor stage A, tx then holds the G_1 polyphase taps)
+        const bool split = g.R1 > 0;
+        const int Jx = split ? g.J1 : g.Jx;
         MrPass2Params p;
         p.p1 = g.p1; p.plane_stride = g.plane_stride; p.phx = g.phx; p.p2 = g.p2; p.pmax = g.pmax;
         p.nbx = g.nbx_alloc; p.nby = g.nby_alloc;
-        p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = g.Jx; p.plane0 = plane0; p.pstep = pstep;
+        p.Nd = g.Nd; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_alloc = g.n_alloc; p.J = Jx; p.plane0 = plane0; p.pstep = pstep;
         p.n_cand = g.n_cand;
         if (cand_mode == GPA_CAND_GRID) { p.row_c = 1; p.row_p = 0; } else { p.row_c = 0; p.row_p = 1; }
+        if (split) {   // two "candidates": the body-masked and the halo-masked anchor carrier; output A[chunk][2][NdE][Md]
+            p.phx = g.phx1; p.p2 = g.a_st; p.pmax = nullptr; p.Nd = g.NdE; p.n_cand = 2; p.row_c = 1; p.row_p = 0;
+        }
         constexpr int W2 = S == 8 ? 4 : 8;
         constexpr int G2 = 2;
-        const size_t n_samp2 = (size_t)S * (W2 * kP + g.Jx + kAhead + 1);
+        const size_t n_samp2 = (size_t)S * (W2 * kP + Jx + kAhead + 1);
         const size_t smem = n_samp2 * (kLanes + 2 * G2) * sizeof(float2);   // plane tile + 2 carrier buffers per group
         GPA_REQUIRE(smem <= 227 * 1024, "decimation filter too long for shared memory (%zu bytes)", smem);
         GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2<S, W2, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, W2 * kP), count);
-        KernelTimer timer("k_mr_pass2", st);
+        dim3 grid(g.pitch_d / kLanes, ceil_div(p.Nd, W2 * kP), count);
+        KernelTimer timer(split ? "k_mr_pass2a" : "k_mr_pass2", st);
         bool launched = false;
         if constexpr (S >= 4) {   // statically scheduled variant for the common filter lengths (even taps per phase)
-            const size_t ns = (size_t)S * (W2 * kP + g.Jx);
+            const size_t ns = (size_t)S * (W2 * kP + Jx);
             const size_t smem_s = ns * (kLanes + 2 * G2) * sizeof(float2);
 #define GPA_P2S(JTV)                                                                                                   \
     case JTV:                                                                                                          \
@@ -1531,7 +1754,7 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         launched = true;                                                                                               \
         break;
             if (smem_s <= 227 * 1024) {
-                switch (g.Jx) {
+                switch (Jx) {
                     GPA_P2S(18) GPA_P2S(20) GPA_P2S(22) GPA_P2S(24) GPA_P2S(26) GPA_P2S(28) GPA_P2S(30) GPA_P2S(32)
                     default: break;
                 }
@@ -1539,6 +1762,28 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
 #undef GPA_P2S
         }
         if (!launched) k_mr_pass2<S, W2, G2><<<grid, G2 * W2 * 32, smem, st>>>(p, tx);
+    }
+    if (g.R1 > 0) {   // stage B: per candidate, at the coarse rate
+        MrPass2bParams p;
+        p.A = g.a_st; p.carB = g.carB; p.derotB = g.derotB; p.jB = g.jB; p.p2 = g.p2; p.pmax = g.pmax;
+        p.Nd = g.Nd; p.Md = g.Md; p.NdE = g.NdE; p.H = g.H; p.EB = ceil_div(g.R1, S) + 1; p.n_cand = g.n_cand;
+        p.nbx = g.nbx_alloc; p.nby = g.nby_alloc;
+        const int JB = 2 * g.H + 1;
+        const size_t smem = (size_t)(2 * (kWarps * kP + JB - 1) * kLanes + 2 * (kWarps * kP + JB - 1) + 2 * kWarps * kP) * sizeof(float2);
+        dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, kWarps * kP), count);
+        KernelTimer timer("k_mr_pass2b", st);
+#define GPA_P2B(JBV)                                                                                                    \
+    case JBV:                                                                                                           \
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass2b<JBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        k_mr_pass2b<JBV><<<grid, kWarps * 32, smem, st>>>(p, t2);                                                       \
+        break;
+        switch (JB) {
+            GPA_P2B(13) GPA_P2B(15) GPA_P2B(17) GPA_P2B(19) GPA_P2B(21) GPA_P2B(23)
+            default:
+                set_error("split pass 2: unsupported coarse tap count %d", JB);
+                return GPA_ERR_INVALID;
+        }
+#undef GPA_P2B
     }
     {   // stages 3 + 4 + arg-max
         MrInterpParams p;
@@ -1578,24 +1823,27 @@ extern "C" int gpa_set_pruning(int on) {
 }
 
 extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax,
-                                            int Ray, int Rb, int planes_in_flight, size_t* bytes) {
+                                            int Ray, int Rb, int R1x, int H2x, int planes_in_flight, size_t* bytes) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
     if (rc) return rc;
     GPA_REQUIRE(bytes != nullptr, "bytes is null");
     GPA_REQUIRE(planes_in_flight >= 1 && planes_in_flight <= n_planes, "planes_in_flight out of range");
-    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 1024 + 2048;
+    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 1024 + 4096;
     return GPA_OK;
 }
 
 extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double* wx_rows, int n_rows,
                                    const double* wy_planes, int n_planes, int cand_mode, int plane_begin,
                                    int plane_end, int plane_step, int S, const float* taps_ax, int Rax, const float* taps_ay, int Ray,
-                                   const float* taps_bx, const float* taps_by, int Rb, unsigned long long* key,
-                                   void* ws, size_t ws_bytes, void* stream) {
+                                   const float* taps_bx, const float* taps_by, int Rb, const float* taps_1x, int R1x,
+                                   const float* taps_2x, int H2x, double sigma_a, double sigma_1,
+                                   unsigned long long* key, void* ws, size_t ws_bytes, void* stream) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
     if (rc) return rc;
+    GPA_REQUIRE(R1x == 0 || (taps_1x && taps_2x && sigma_1 > 0.0 && sigma_1 < sigma_a),
+                "split pass 2 needs both tap sets and 0 < sigma_1 < sigma_a");
     if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
     GPA_REQUIRE(key != nullptr, "key is null");
     GPA_REQUIRE(plane_step >= 1, "plane_step must be >= 1");
@@ -1606,23 +1854,40 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
         set_error("workspace too small (%zu bytes)", ws_bytes);
         return GPA_ERR_WORKSPACE;
     }
-    TapTable tx, ty, tb;
-    if ((rc = fill_polyphase(tx, taps_ax, Rax, S, g.Jx)) || (rc = fill_polyphase(ty, taps_ay, Ray, S, g.Jy)) ||
-        (rc = fill_interp(tb, taps_bx, taps_by, Rb, S)))
+    TapTable tx, ty, tb, t2;
+    const bool split = g.R1 > 0;
+    if ((rc = split ? fill_polyphase(tx, taps_1x, R1x, S, g.J1) : fill_polyphase(tx, taps_ax, Rax, S, g.Jx)) ||
+        (rc = fill_polyphase(ty, taps_ay, Ray, S, g.Jy)) || (rc = fill_interp(tb, taps_bx, taps_by, Rb, S)))
         return rc;
+    std::memset(&t2, 0, sizeof(t2));
+    if (split)
+        for (int j = 0; j < 2 * H2x + 1; ++j) t2.g[j] = make_float2(taps_2x[j], taps_2x[j]);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {   // carrier tables: same kernel as the direct path, padded-row layout of the decimating stage
         Geometry t;
-        t.N = N; t.M = M; t.n_rows = n_rows; t.n_planes = n_planes; t.Rx = Rax; t.n_alloc = g.n_alloc;
+        t.N = N; t.M = M; t.n_rows = n_rows; t.n_planes = n_planes; t.Rx = g.row_shift; t.n_alloc = g.n_alloc;
         t.wx_d = g.wx_d; t.wy_d = g.wy_d; t.phx = g.phx; t.phy = g.phy;
         if ((rc = build_tables(t, wx_rows, wy_planes, st))) return rc;
+    }
+    if (split) {   // anchor = the middle row of the candidate grid; per-candidate coarse carriers relative to it
+        SplitTabParams tp;
+        tp.phx1 = g.phx1; tp.carB = g.carB; tp.derotB = g.derotB; tp.jB = g.jB; tp.wx_d = g.wx_d;
+        tp.wx0 = wx_rows[n_rows / 2];
+        const double s2sq = sigma_a * sigma_a - sigma_1 * sigma_1;
+        tp.ratio = sigma_a * sigma_a / s2sq;
+        tp.cexp = 2.0 * 9.869604401089358 * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq;
+        tp.n_cand = g.n_cand; tp.N = N; tp.S = S; tp.H = g.H; tp.Nd = g.Nd; tp.NdE = g.NdE; tp.n_alloc = g.n_alloc;
+        tp.Rtot = g.row_shift;
+        dim3 grid(ceil_div(g.n_alloc, 256) < 8 ? ceil_div(g.n_alloc, 256) : 8, g.n_cand + 1);
+        k_build_split_tables<<<grid, 256, 0, st>>>(tp);
+        GPA_CHECK_CUDA(cudaGetLastError());
     }
     for (int i0 = 0; i0 < total; i0 += chunk) {
         const int cnt = total - i0 < chunk ? total - i0 : chunk;
         const int p0 = plane_begin + i0 * plane_step;
-        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
-        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
-        else rc = launch_mr<8>(g, img, ty, tx, tb, p0, plane_step, cnt, cand_mode, key, st);
+        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
+        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
+        else rc = launch_mr<8>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
         if (rc) return rc;
     }
     return GPA_OK;
@@ -1633,11 +1898,11 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
 extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
                                      int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
                                      int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
-                                     const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
-                                     int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
+                                     int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
+                                     int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
                                      size_t ws_bytes, void* stream) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
     if (rc) return rc;
     GPA_REQUIRE(wx_rows && wy_planes && ws && key && lockin, "null pointer argument");
     GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes, "bad plane range");

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._taps import DEFAULT_TRUNC, axis_taps, multirate_taps
+from ._taps import DEFAULT_TRUNC, axis_taps, multirate_taps, split_taps
 
 GRAD_CENTRAL, GRAD_FORWARD, GRAD_NONE = 0, 1, 2
 CAND_GRID, CAND_LIST = 0, 1
@@ -142,15 +142,20 @@ class SweepPlan:
         self.n_cand = self.wx.size * self.wy.size if cand_mode == CAND_GRID else self.wy.size
         # arg-max method: the multirate form when the frame and sigma allow it (and the candidate
         # grid is large enough to amortise its extra passes), else the direct form
-        if method not in ("auto", "direct", "multirate"):
-            raise ValueError("method must be 'auto', 'direct' or 'multirate'")
+        if method not in ("auto", "direct", "multirate", "multirate-single"):
+            raise ValueError("method must be 'auto', 'direct', 'multirate' or 'multirate-single'")
         self.mr = None
         if method != "direct" and trunc == DEFAULT_TRUNC and self.wx.size <= 65535:
             self.mr = multirate_taps(self.n, self.m, float(sigma), trunc)
             if self.mr is not None and method == "auto" and cand_mode == CAND_LIST:
                 self.mr = None
-        if method == "multirate" and self.mr is None:
+        if method in ("multirate", "multirate-single") and self.mr is None:
             raise ValueError("the multirate sweep does not apply to this frame size / sigma")
+        # split pass 2 (anchor stage shared by the candidates of a plane) when the grid is narrow enough;
+        # 'multirate-single' keeps every candidate's own full-rate pass 2
+        self.split = None
+        if self.mr is not None and cand_mode == CAND_GRID and method != "multirate-single":
+            self.split = split_taps(self.n, self.mr, self.wx)
         if self.mr is not None:
             self.mr_in_flight, self.mr_ws_bytes = self._plan_mr(planes_in_flight)
             self.ws_bytes = max(self.ws_bytes, self.mr_ws_bytes)
@@ -161,7 +166,8 @@ class SweepPlan:
 
         def need(p):
             _lib.check(lib.gpa_sweep_mr_workspace_bytes(self.n, self.m, self.wx.size, self.wy.size, self.cand_mode,
-                                                        mr["S"], mr["Ra_x"], mr["Ra_y"], mr["Rb"], p, ctypes.byref(nbytes)))
+                                                        mr["S"], mr["Ra_x"], mr["Ra_y"], mr["Rb"], *self._split_geom(),
+                                                        p, ctypes.byref(nbytes)))
             return nbytes.value
         p = planes_in_flight
         if p is None:
@@ -189,6 +195,15 @@ class SweepPlan:
     def _taps(self):
         return (_lib.as_pf(self.tx), self.rx, _lib.as_pf(self.ty), self.ry)
 
+    def _split_geom(self):
+        return (self.split["R1"], self.split["H"]) if self.split else (0, 0)
+
+    def _split_args(self):
+        sp = self.split
+        if not sp:
+            return (None, 0, None, 0, 0.0, 0.0)
+        return (_lib.as_pf(sp["taps_1"]), sp["R1"], _lib.as_pf(sp["taps_2"]), sp["H"], float(self.mr["sigma_a"]), sp["sigma_1"])
+
     def argmax(self, img_dev, key, plane_begin=0, plane_end=None, plane_step=1):
         """key (N, M) int64 CUDA tensor, updated in place with the candidates of planes
         plane_begin, plane_begin + plane_step, ... < plane_end (a step > 1 needs the multirate form)."""
@@ -202,10 +217,10 @@ class SweepPlan:
             _lib.check(lib.gpa_sweep_argmax_mr(_ptr(img_dev), *self._geom(), plane_begin, plane_end, plane_step, mr["S"],
                                                _lib.as_pf(mr["taps_ax"]), mr["Ra_x"], _lib.as_pf(mr["taps_ay"]), mr["Ra_y"],
                                                _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
-                                               _ptr(key), _ptr(ws), ws.numel(), _stream()))
+                                               *self._split_args(), _ptr(key), _ptr(ws), ws.numel(), _stream()))
             n_local = -(-(plane_end - plane_begin) // plane_step)
             chunks = -(-n_local // self.mr_in_flight) if plane_end > plane_begin else 0
-            _count(2 + 4 * chunks)
+            _count(2 + (6 if self.split else 4) * chunks + (1 if self.split and chunks else 0))
             return
         _lib.check(lib.gpa_sweep_argmax(_ptr(img_dev), *self._geom(), plane_begin, plane_end, *self._taps(),
                                         _ptr(key), _ptr(ws), ws.numel(), _stream()))
@@ -238,6 +253,7 @@ class SweepPlan:
             mr = self.mr
             _lib.check(lib.gpa_sweep_finalize_mr(*self._geom(), plane_begin, plane_end, plane_step, mr["S"], mr["Ra_x"], mr["Ra_y"],
                                                  _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]), mr["Rb"],
+                                                 *self._split_geom(),
                                                  _ptr(key), float(kref[0]), float(kref[1]), grad_mode, int(out_f64),
                                                  _ptr(out["lockin"]), _ptr(out.get("grad")), _ptr(out.get("w")),
                                                  _ptr(out.get("kidx")), _ptr(ws), ws.numel(), _stream()))

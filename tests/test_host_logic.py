@@ -89,3 +89,49 @@ def test_c_side_taps_and_multirate_plan_agree_with_python(n, sigma):
         assert s_c == (mr["S"] if mr else 0)
         if mr:
             assert (ra.value, rb.value) == (mr["Ra_x"], mr["Rb"]) and abs(sa.value - mr["sigma_a"]) < 1e-12
+
+
+def test_split_pass2_plan():
+    """Planner of the split pass 2 (shared anchor stage + coarse-rate stage per candidate): narrow
+    grids get a factorisation whose worst-case transfer-function error stays below the truncation
+    error of the single-stage filter; wide grids and short candidate axes get none."""
+    mr = _taps.multirate_taps(256, 256, 10.0)
+    ks = synth.primary_ks(0.05, 7.0, 3)
+    kw, kstep = synth.sweep_params(ks, 21)
+    wx = np.arange(ks[0][0] - kw, ks[0][0] + kw, kstep)
+    sp = _taps.split_taps(256, mr, wx)
+    assert sp is not None and 2 * sp["H"] + 1 in (13, 15, 17, 19, 21, 23) and sp["err"] <= _taps.SPLIT_TOL
+    assert abs(sp["sigma_1"] ** 2 + sp["sigma_2"] ** 2 - mr["sigma_a"] ** 2) < 1e-9
+    assert sp["taps_1"].size == 2 * sp["R1"] + 1 and sp["taps_2"].size == 2 * sp["H"] + 1
+    assert abs(sp["taps_1"].sum() - 1) < 1e-5 and abs(sp["taps_2"].sum() - 1) < 1e-4
+    assert -(-(2 * sp["R1"] + 1) // mr["S"]) % 2 == 0          # even taps per phase: statically scheduled stage A
+    # independent 1-D check of the whole pipeline against the exact circular Gaussian, border rows included
+    n, S, H, R1 = 256, mr["S"], sp["H"], sp["R1"]
+    rng = np.random.default_rng(3)
+    p1 = rng.normal(size=n) + 1j * rng.normal(size=n)
+    f = np.fft.fftfreq(n)
+    wx0 = wx[wx.size // 2]
+    nd, nde, rtot = n // S, n // S + 2 * H, R1 + S * H
+    xu = np.arange(S * nde + 2 * R1 + 1) - rtot
+    a = p1[xu % n] * np.exp(2j * np.pi * wx0 * (xu % n))
+    body = (xu >= 0) & (xu < n)
+    e = np.arange(nde)
+    A_body = sum(sp["taps_1"][i].astype(float) * np.where(body[S * e + i], a[S * e + i], 0) for i in range(2 * R1 + 1))
+    A_edge = sum(sp["taps_1"][i].astype(float) * np.where(body[S * e + i], 0, a[S * e + i]) for i in range(2 * R1 + 1))
+    for w in (wx[0], wx[5], wx[-1]):
+        exact = np.fft.ifft(np.fft.fft(p1 * np.exp(2j * np.pi * w * np.arange(n))) * np.exp(-2 * np.pi ** 2 * mr["sigma_a"] ** 2 * f ** 2))[::S]
+        dw = w - wx0
+        delta = dw * mr["sigma_a"] ** 2 / sp["sigma_2"] ** 2
+        c = np.exp(2 * np.pi ** 2 * dw ** 2 * mr["sigma_a"] ** 2 * sp["sigma_1"] ** 2 / sp["sigma_2"] ** 2)
+        J = np.where(e - H < nd // 2, np.exp(2j * np.pi * dw * n), np.exp(-2j * np.pi * dw * n))
+        smp = np.exp(2j * np.pi * delta * S * (e - H)) * (A_body + J * A_edge)
+        mx = np.arange(nd)
+        got = c * np.exp(2j * np.pi * (dw - delta) * S * mx) * sum(sp["taps_2"][j].astype(float) * smp[mx + j] for j in range(2 * H + 1))
+        err = np.abs(got - exact).max() / np.abs(p1).max()
+        print("split 1-D error relative to the input amplitude", err)
+        assert err < 3e-6
+    # a grid twice as wide (r_k = 0.1) cannot share one anchor; a 5-point axis is not worth it
+    ks2 = synth.primary_ks(0.1, 7.0, 3)
+    kw2, kstep2 = synth.sweep_params(ks2, 21)
+    assert _taps.split_taps(256, mr, np.arange(ks2[0][0] - kw2, ks2[0][0] + kw2, kstep2)) is None
+    assert _taps.split_taps(256, mr, wx[:5]) is None
