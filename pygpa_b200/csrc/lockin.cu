@@ -947,6 +947,8 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     __shared__ int s_blk[SBX][SBY];       // smallest recorded winner (float bits, >= 0) per bound block of the tile
     __shared__ int s_cnt;
     __shared__ unsigned short s_list[kMaxPruneCand];
+    __shared__ unsigned s_mask[kMaxPruneCand];      // per survivor: bound blocks of the tile in which it can still win
+    static_assert(SBX * SBY <= 32, "one mask bit per bound block of the tile");
     int n_live = prm.n_cand;
     const bool prune = prm.prune != 0;
     if (prune) {
@@ -987,6 +989,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             for (int base = 0; base < prm.n_cand; base += 32) {
                 const int c = base + lane;
                 bool keep = false;
+                unsigned bits = 0u;
                 if (c < prm.n_cand) {
                     const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
                     float m[SBX + 2][SBY + 2];
@@ -1010,11 +1013,16 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
                             for (int di = 0; di < 3; ++di)
 #pragma unroll
                                 for (int dj = 0; dj < 3; ++dj) mm = fmaxf(mm, m[i + di][j + dj]);
-                            keep = keep || !(mm * 1.0002f < thr[i][j]);
+                            if (!(mm * 1.0002f < thr[i][j])) bits |= 1u << (i * SBY + j);
                         }
+                    keep = bits != 0u;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)c;
+                if (keep) {
+                    const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                    s_list[pos] = (unsigned short)c;
+                    s_mask[pos] = bits;
+                }
                 cnt += __popc(bal);
             }
             if (lane == 0) s_cnt = cnt;
@@ -1042,6 +1050,33 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
 #pragma unroll
         for (int p = 0; p < kP / IPR; ++p) bidx[h][p] = 0u;
     }
+    // Bound blocks touched by this thread's two output regions (rows [32h, 32h+32) x columns [16 warp, 16 warp + 16)):
+    // a surviving candidate is interpolated along y only in the regions where its block bound can still win,
+    // and along x only for the tasks such a region reads (exact: it cannot win or tie anywhere else).
+    constexpr int BPXc = kPmB * S;
+    auto region_mask = [&](int h, int w) -> unsigned {
+        unsigned m = 0u;
+        for (int i = (32 * h) / BPXc; i <= (32 * h + 31) / BPXc; ++i)
+            for (int j = (kP * w) / BPXc; j <= (kP * w + kP - 1) / BPXc; ++j) m |= 1u << (i * SBY + j);
+        return m;
+    };
+    unsigned regmask[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) regmask[h] = region_mask(h, warp);
+    constexpr int PER3 = (N3 + 255) / 256;
+    unsigned taskmask[PER3];       // regions (h, w) read p3t rows cy in [w kP/S, w kP/S + NS) and x in [32h, 32h+32)
+#pragma unroll
+    for (int e = 0; e < PER3; ++e) {
+        const int t = threadIdx.x + e * 256;
+        unsigned m = 0u;
+        if (t < N3) {
+            const int cy = t % CY, xb = t / CY;
+            const int h = (xb * Q3) / 32;
+            for (int w = 0; w < kMrTY / kP; ++w)
+                if (cy >= w * (kP / S) && cy < w * (kP / S) + NS) m |= region_mask(h, w);
+        }
+        taskmask[e] = m;
+    }
     const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
     auto fetch = [&](int i) {
         if (i < n_live) {
@@ -1057,7 +1092,11 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     auto interp_x = [&](int c) {
         const float2* p2c = smem + (c & 1) * CX * CY;
         float2* p3t = p3t0 + (c & 1) * CY * P3P;
-        for (int t = threadIdx.x; t < N3; t += 256) {
+        const unsigned live = prune ? s_mask[c] : 0xffffffffu;
+#pragma unroll
+        for (int e = 0; e < PER3; ++e) {
+            const int t = threadIdx.x + e * 256;
+            if (t >= N3 || !(live & taskmask[e])) continue;
             const int cy = t % CY, xb = t / CY;
             float2 smp[NS3], acc[Q3];
 #pragma unroll
@@ -1084,8 +1123,10 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
         const float2* p3t = p3t0 + (i & 1) * CY * P3P;
         const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
+        const unsigned live = prune ? s_mask[i] : 0xffffffffu;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            if (!(live & regmask[h])) continue;       // warp-uniform
             float2 smp[NS], acc[kP];
 #pragma unroll
             for (int i = 0; i < NS; ++i) smp[i] = p3t[(warp * (kP / S) + i) * P3P + lane + 32 * h];
