@@ -812,7 +812,17 @@ k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
         float a2max[kP / kPmB];
 #pragma unroll
         for (int hb = 0; hb < kP / kPmB; ++hb) a2max[hb] = 0.f;
-        if (my < Md) {
+        if (mx0 + warp * kP + kP <= Nd) {      // whole row block inside the grid (warp-uniform): no per-row guards
+            if (my < Md) {
+                float2* o = out + (size_t)(mx0 + warp * kP) * Md + my;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const float2 v = cmul(acc[p], der[p]);
+                    o[(size_t)p * Md] = v;
+                    a2max[p / kPmB] = fmaxf(a2max[p / kPmB], fmaf(v.x, v.x, v.y * v.y));
+                }
+            }
+        } else if (my < Md) {
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
                 const int mx = mx0 + warp * kP + p;
@@ -1060,9 +1070,15 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             for (int j = (kP * w) / BPXc; j <= (kP * w + kP - 1) / BPXc; ++j) m |= 1u << (i * SBY + j);
         return m;
     };
+    // Column block of this warp's two regions: staggered by half a tile between h = 0 and h = 1, because a
+    // candidate is usually alive in neighbouring blocks — the stagger spreads its regions over more warps
+    // (fewer warps waiting at the per-candidate barrier for the ones that own two live regions).
+    constexpr int NCB = kMrTY / kP;
+    static_assert(NCB == 8, "one column block per warp");
+    const int wcol[2] = {warp, (warp + NCB / 2) % NCB};
     unsigned regmask[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) regmask[h] = region_mask(h, warp);
+    for (int h = 0; h < 2; ++h) regmask[h] = region_mask(h, wcol[h]);
     constexpr int PER3 = (N3 + 255) / 256;
     unsigned taskmask[PER3];       // regions (h, w) read p3t rows cy in [w kP/S, w kP/S + NS) and x in [32h, 32h+32)
 #pragma unroll
@@ -1120,7 +1136,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         __syncthreads();          // tile i+1 landed, p3t[i] complete, buffers of phase i-1 released
         fetch(i + 2);
         if (i + 1 < n_live) interp_x(i + 1);
-        // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block `warp`)
+        // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block wcol[h])
         const float2* p3t = p3t0 + (i & 1) * CY * P3P;
         const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
         const unsigned live = prune ? s_mask[i] : 0xffffffffu;
@@ -1129,7 +1145,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             if (!(live & regmask[h])) continue;       // warp-uniform
             float2 smp[NS], acc[kP];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) smp[i] = p3t[(warp * (kP / S) + i) * P3P + lane + 32 * h];
+            for (int i = 0; i < NS; ++i) smp[i] = p3t[(wcol[h] * (kP / S) + i) * P3P + lane + 32 * h];
             interp_block<S, kP>(acc, smp, taps, S * kMrW);
 #pragma unroll
             for (int p = 0; p < kP; ++p) {
@@ -1148,7 +1164,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         const int x = x0 + lane + 32 * h;
 #pragma unroll
         for (int p = 0; p < kP; ++p) {
-            const int y = y0 + warp * kP + p;
+            const int y = y0 + wcol[h] * kP + p;
             if (x < prm.N && y < prm.M && best[h][p] > 0.f) {
                 const unsigned cwin = (bidx[h][p / IPR] >> ((p % IPR) * IB)) & IMASK;
                 const unsigned idx = cwin * (unsigned)prm.idx_c + (unsigned)(plane * prm.idx_p);
