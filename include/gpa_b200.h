@@ -154,6 +154,13 @@ int gpa_set_pruning(int on);
  * wrapped around the frame edge (whose carrier phase jumps by dw N, as the reference's does) are carried
  * separately through the anchor stage.  taps_1x: G_1 (2 R1x + 1 fine taps); taps_2x: S G_2(S m), |m| <= H2x.
  * R1x = 0 selects the single-stage pass 2 (taps_1x, taps_2x, sigma_a, sigma_1 ignored). */
+/* Host-side planner of the split (no CUDA; same search as pygpa_b200/_taps.py): picks the shortest coarse
+ * filter (13 ... 23 taps) whose worst-case transfer-function error against the candidate-centred G_a, over
+ * all input frequencies and the widest dw of wx_rows, stays below 1.3e-6 (the error of truncating G_a at
+ * 4.5 sigma).  Returns 1 and fills R1x, H2x, sigma_1, taps_1x (capacity 446 floats) and taps_2x (23 floats);
+ * returns 0 when the candidate axis is too wide or too short for one shared anchor (use R1x = 0). */
+int gpa_split_plan(int n, int stride, double sigma_a, const double* wx_rows /*host*/, int n_rows,
+                   int* R1x, int* H2x, double* sigma_1, float* taps_1x /*host*/, float* taps_2x /*host*/);
 int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int stride,
                                  int Rax, int Ray, int Rb, int R1x, int H2x, int planes_in_flight, size_t* bytes);
 int gpa_sweep_argmax_mr(const float* img, int N, int M,

@@ -29,6 +29,7 @@ SIGNATURES = {
     "gpa_gaussian_taps": (c_int, [c_int, c_double, c_int, _pf]),
     "gpa_default_radius": (c_int, [c_int, c_double, c_double]),
     "gpa_multirate_plan": (c_int, [c_int, c_int, c_double, _pd, _pd, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "gpa_split_plan": (c_int, [c_int, c_int, c_double, _pd, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _pd, _pf, _pf]),
     "gpa_lockin_workspace_bytes": (c_int, [c_int] * 7 + [ctypes.POINTER(c_size_t)]),
     "gpa_lockin_fixed": (c_int, [c_void_p, c_int, c_int, c_double, c_double, _pf, c_int, _pf, c_int,
                                  c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

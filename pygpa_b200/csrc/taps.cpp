@@ -76,3 +76,81 @@ extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, d
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// split pass 2 planner (same search as pygpa_b200/_taps.py: _split_plan / split_taps)
+// ---------------------------------------------------------------------------------------------
+namespace {
+// max_f | c G_1t(f) h_t(S (f + delta)) - G_a(f + dw) |  over nf frequencies in [-1/2, 1/2)
+double split_error(int s, double sigma_a, double sigma_1, int r1, int h, double dw, int nf = 2048) {
+    const double pi = 3.141592653589793238462643383279;
+    const double s2sq = sigma_a * sigma_a - sigma_1 * sigma_1, sigma_2 = std::sqrt(s2sq);
+    const double delta = dw * sigma_a * sigma_a / s2sq;
+    const double c = std::exp(2.0 * pi * pi * dw * dw * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq);
+    std::vector<double> g1(r1 + 1), h2(h + 1);
+    for (int d = 0; d <= r1; ++d) g1[d] = std::exp(-(double)d * d / (2.0 * sigma_1 * sigma_1)) / (sigma_1 * std::sqrt(2.0 * pi));
+    for (int m = 0; m <= h; ++m) h2[m] = s * std::exp(-(double)(s * m) * (s * m) / (2.0 * s2sq)) / (sigma_2 * std::sqrt(2.0 * pi));
+    double worst = 0.0;
+    for (int i = 0; i < nf; ++i) {
+        const double f = (double)(i - nf / 2) / nf;
+        double G1 = g1[0], H2 = h2[0];                       // both filters are even: cosine sums
+        for (int d = 1; d <= r1; ++d) G1 += 2.0 * g1[d] * std::cos(2.0 * pi * f * d);
+        for (int m = 1; m <= h; ++m) H2 += 2.0 * h2[m] * std::cos(2.0 * pi * s * (f + delta) * m);
+        const double e = std::fabs(c * G1 * H2 - std::exp(-2.0 * pi * pi * sigma_a * sigma_a * (f + dw) * (f + dw)));
+        if (e > worst) worst = e;
+    }
+    return worst;
+}
+}  // namespace
+
+// Plan of the split pass 2 for an axis of length n, multirate stride `stride`, decimation sigma_a and the
+// candidate axis wx_rows (anchor = wx_rows[n_rows / 2]).  Returns 1 and fills R1 (stage-A radius, 2 R1 + 1 fine
+// taps in taps_1), H (stage-B coarse radius, 2 H + 1 taps S G_2(S m) in taps_2) and sigma_1, or returns 0 when
+// no factorisation meets the 1.3e-6 transfer-function tolerance with at most 23 coarse taps (then pass
+// R1x = 0 to gpa_sweep_argmax_mr).  taps_1 must hold 446 floats, taps_2 23.
+extern "C" int gpa_split_plan(int n, int stride, double sigma_a, const double* wx_rows, int n_rows, int* R1, int* H,
+                              double* sigma_1_out, float* taps_1, float* taps_2) {
+    if (n < 1 || !(stride == 2 || stride == 4 || stride == 8) || !(sigma_a > 0.0) || !wx_rows || n_rows < 1 || !R1 || !H ||
+        !sigma_1_out || !taps_1 || !taps_2) {
+        gpa::set_error("gpa_split_plan: bad argument");
+        return GPA_ERR_INVALID;
+    }
+    if (n_rows < 8) return 0;
+    const double pi = 3.141592653589793238462643383279;
+    const int s = stride;
+    double dw_max = 0.0;
+    for (int i = 0; i < n_rows; ++i) dw_max = std::fmax(dw_max, std::fabs(wx_rows[i] - wx_rows[n_rows / 2]));
+    {   // quantised upwards exactly as the Python planner does (shared cache key there)
+        const double q = std::exp2(std::floor(std::log2(std::fmax(dw_max, 1e-12))) - 4.0);
+        dw_max = std::ceil(dw_max / q) * q;
+    }
+    for (int h = 6; h <= 11; ++h) {
+        double best_err = -1.0, best_s1 = 0.0, best_s2 = 0.0;
+        int best_r1 = 0;
+        const double top = std::fmin(h / 4.4, 2.4) + 1e-9;
+        for (int step = 0;; ++step) {
+            const double s2c = 1.35 + 0.05 * step;         // np.arange(1.35, top, 0.05)
+            if (!(s2c < top)) break;
+            const double sigma_2 = s2c * s;
+            if (sigma_2 >= 0.98 * sigma_a) break;
+            const double sigma_1 = std::sqrt(sigma_a * sigma_a - sigma_2 * sigma_2);
+            int r1 = (int)std::ceil(6.0 * sigma_1);
+            int j1 = (2 * r1 + 1 + s - 1) / s;
+            j1 += j1 & 1;
+            if (j1 < 18) j1 = 18;
+            r1 = (s * j1 - 1) / 2;
+            if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446) continue;
+            const double err = std::fmax(split_error(s, sigma_a, sigma_1, r1, h, dw_max), split_error(s, sigma_a, sigma_1, r1, h, 0.5 * dw_max));
+            if (best_err < 0.0 || err < best_err) { best_err = err; best_s1 = sigma_1; best_s2 = sigma_2; best_r1 = r1; }
+        }
+        if (best_err >= 0.0 && best_err <= 1.3e-6) {
+            *R1 = best_r1; *H = h; *sigma_1_out = best_s1;
+            for (int d = -best_r1; d <= best_r1; ++d)
+                taps_1[d + best_r1] = (float)(std::exp(-(double)d * d / (2.0 * best_s1 * best_s1)) / (best_s1 * std::sqrt(2.0 * pi)));
+            for (int m = -h; m <= h; ++m)
+                taps_2[m + h] = (float)(s * std::exp(-(double)(s * m) * (s * m) / (2.0 * best_s2 * best_s2)) / (best_s2 * std::sqrt(2.0 * pi)));
+            return 1;
+        }
+    }
+    return 0;
+}

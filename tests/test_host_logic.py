@@ -135,3 +135,26 @@ def test_split_pass2_plan():
     kw2, kstep2 = synth.sweep_params(ks2, 21)
     assert _taps.split_taps(256, mr, np.arange(ks2[0][0] - kw2, ks2[0][0] + kw2, kstep2)) is None
     assert _taps.split_taps(256, mr, wx[:5]) is None
+
+
+@pytest.mark.parametrize("size,sigma,r_k,n_grid", [(2048, 10.0, 0.05, 41), (256, 10.0, 0.05, 21), (256, 10.0, 0.1, 21),
+                                                    (160, 5.0, 0.1, 9), (320, 22.0, 0.0227, 9), (256, 10.0, 0.05, 5)])
+def test_c_side_split_plan_agrees_with_python(size, sigma, r_k, n_grid):
+    """gpa_split_plan (for non-Python hosts) reproduces pygpa_b200/_taps.split_taps."""
+    import ctypes
+    lib = _lib.load()
+    mr = _taps.multirate_taps(size, size, sigma)
+    assert mr is not None
+    ks = synth.primary_ks(r_k, 7.0, 3)
+    kw, kstep = synth.sweep_params(ks, n_grid)
+    wx = np.ascontiguousarray(np.arange(ks[1][0] - kw, ks[1][0] + kw, kstep))
+    sp = _taps.split_taps(size, mr, wx)
+    r1, h, s1 = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
+    t1, t2 = np.zeros(446, dtype=np.float32), np.zeros(23, dtype=np.float32)
+    rc = lib.gpa_split_plan(size, mr["S"], mr["sigma_a"], _lib.as_pd(wx), wx.size, ctypes.byref(r1), ctypes.byref(h),
+                            ctypes.byref(s1), _lib.as_pf(t1), _lib.as_pf(t2))
+    assert rc == (1 if sp else 0)
+    if sp:
+        assert (r1.value, h.value) == (sp["R1"], sp["H"]) and abs(s1.value - sp["sigma_1"]) < 1e-9
+        assert np.abs(t1[:2 * r1.value + 1] - sp["taps_1"]).max() < 1e-7
+        assert np.abs(t2[:2 * h.value + 1] - sp["taps_2"]).max() < 1e-6
