@@ -100,7 +100,8 @@ def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
 
 @functools.lru_cache(maxsize=64)
 def _split_plan(n, s, sigma_a, dw_max):
-    for h in (6, 7, 8, 9, 10, 11):                       # 13 ... 23 coarse taps per candidate
+    def best_for(h):
+        """(error, sigma_1, sigma_2, R1) of the best coarse-rate sigma for 2h+1 taps, or None."""
         best = None
         for s2c in np.arange(1.35, min(h / 4.4, 2.4) + 1e-9, 0.05):      # coarse-rate sigma of G_2
             sigma_2 = float(s2c * s)
@@ -116,17 +117,29 @@ def _split_plan(n, s, sigma_a, dw_max):
             err = max(_split_error(s, sigma_a, sigma_1, r1, h, dw) for dw in (dw_max, 0.5 * dw_max))
             if best is None or err < best[0]:
                 best = (err, sigma_1, sigma_2, r1)
+        return best
+
+    def plan(h, best):
+        err, sigma_1, sigma_2, r1 = best
+        d = np.arange(-r1, r1 + 1)
+        t1 = (np.exp(-d ** 2 / (2 * sigma_1 ** 2)) / (sigma_1 * np.sqrt(2 * np.pi))).astype(np.float32)
+        m = np.arange(-h, h + 1)
+        t2 = (s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))).astype(np.float32)
+        t1.setflags(write=False)
+        t2.setflags(write=False)
+        return dict(R1=r1, H=h, sigma_1=sigma_1, sigma_2=sigma_2, taps_1=t1, taps_2=t2, err=err,
+                    c_max=float(np.exp(2 * np.pi ** 2 * dw_max ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)))
+
+    # the longest filter (23 coarse taps) first: if even that misses the tolerance — grids too wide for one
+    # anchor — nothing shorter is tried; otherwise the shortest filter that meets it wins
+    longest = best_for(11)
+    if longest is None or longest[0] > SPLIT_TOL:
+        return None
+    for h in (6, 7, 8, 9, 10):                          # 13 ... 21 coarse taps per candidate
+        best = best_for(h)
         if best is not None and best[0] <= SPLIT_TOL:
-            err, sigma_1, sigma_2, r1 = best
-            d = np.arange(-r1, r1 + 1)
-            t1 = (np.exp(-d ** 2 / (2 * sigma_1 ** 2)) / (sigma_1 * np.sqrt(2 * np.pi))).astype(np.float32)
-            m = np.arange(-h, h + 1)
-            t2 = (s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))).astype(np.float32)
-            t1.setflags(write=False)
-            t2.setflags(write=False)
-            return dict(R1=r1, H=h, sigma_1=sigma_1, sigma_2=sigma_2, taps_1=t1, taps_2=t2, err=err,
-                        c_max=float(np.exp(2 * np.pi ** 2 * dw_max ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)))
-    return None
+            return plan(h, best)
+    return plan(11, longest)
 
 
 def split_taps(n, mr, wx_rows):

@@ -124,9 +124,9 @@ extern "C" int gpa_split_plan(int n, int stride, double sigma_a, const double* w
         const double q = std::exp2(std::floor(std::log2(std::fmax(dw_max, 1e-12))) - 4.0);
         dw_max = std::ceil(dw_max / q) * q;
     }
-    for (int h = 6; h <= 11; ++h) {
-        double best_err = -1.0, best_s1 = 0.0, best_s2 = 0.0;
-        int best_r1 = 0;
+    struct Best { double err, s1, s2; int r1; };
+    auto best_for = [&](int h) {
+        Best b{-1.0, 0.0, 0.0, 0};
         const double top = std::fmin(h / 4.4, 2.4) + 1e-9;
         for (int step = 0;; ++step) {
             const double s2c = 1.35 + 0.05 * step;         // np.arange(1.35, top, 0.05)
@@ -141,16 +141,24 @@ extern "C" int gpa_split_plan(int n, int stride, double sigma_a, const double* w
             r1 = (s * j1 - 1) / 2;
             if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446) continue;
             const double err = std::fmax(split_error(s, sigma_a, sigma_1, r1, h, dw_max), split_error(s, sigma_a, sigma_1, r1, h, 0.5 * dw_max));
-            if (best_err < 0.0 || err < best_err) { best_err = err; best_s1 = sigma_1; best_s2 = sigma_2; best_r1 = r1; }
+            if (b.err < 0.0 || err < b.err) b = Best{err, sigma_1, sigma_2, r1};
         }
-        if (best_err >= 0.0 && best_err <= 1.3e-6) {
-            *R1 = best_r1; *H = h; *sigma_1_out = best_s1;
-            for (int d = -best_r1; d <= best_r1; ++d)
-                taps_1[d + best_r1] = (float)(std::exp(-(double)d * d / (2.0 * best_s1 * best_s1)) / (best_s1 * std::sqrt(2.0 * pi)));
-            for (int m = -h; m <= h; ++m)
-                taps_2[m + h] = (float)(s * std::exp(-(double)(s * m) * (s * m) / (2.0 * best_s2 * best_s2)) / (best_s2 * std::sqrt(2.0 * pi)));
-            return 1;
-        }
+        return b;
+    };
+    auto emit = [&](int h, const Best& b) {
+        *R1 = b.r1; *H = h; *sigma_1_out = b.s1;
+        for (int d = -b.r1; d <= b.r1; ++d)
+            taps_1[d + b.r1] = (float)(std::exp(-(double)d * d / (2.0 * b.s1 * b.s1)) / (b.s1 * std::sqrt(2.0 * pi)));
+        for (int m = -h; m <= h; ++m)
+            taps_2[m + h] = (float)(s * std::exp(-(double)(s * m) * (s * m) / (2.0 * b.s2 * b.s2)) / (b.s2 * std::sqrt(2.0 * pi)));
+        return 1;
+    };
+    // the longest filter first: if even 23 coarse taps miss the tolerance nothing shorter is tried
+    const Best longest = best_for(11);
+    if (longest.err < 0.0 || longest.err > 1.3e-6) return 0;
+    for (int h = 6; h <= 10; ++h) {
+        const Best b = best_for(h);
+        if (b.err >= 0.0 && b.err <= 1.3e-6) return emit(h, b);
     }
-    return 0;
+    return emit(11, longest);
 }
