@@ -85,3 +85,33 @@ def test_split_pass2_geometry_is_validated_without_a_gpu():
     assert lib.gpa_sweep_mr_workspace_bytes(88, 88, 41, 41, 0, 4, 43, 43, 20, 43, 7, 41, ctypes.byref(nbytes)) == -1       # edge bands overlap
     r1, h, s1 = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
     assert lib.gpa_split_plan(2048, 3, 8.98, None, 0, ctypes.byref(r1), ctypes.byref(h), ctypes.byref(s1), None, None) == -1
+
+
+def test_integration_stub_prototypes_match_the_binding():
+    """The ctypes prototypes printed in INTEGRATION.md (the stub a pyGPA maintainer would add) are the
+    ones pygpa_b200/_lib.py declares — same arity, same C types in the same order."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    env = {"ctypes": ctypes, "_pd": ctypes.POINTER(ctypes.c_double), "_pf": ctypes.POINTER(ctypes.c_float),
+           "_vp": ctypes.c_void_p, "_i": ctypes.c_int, "_d": ctypes.c_double}
+    found = re.findall(r"^L\.(gpa_[a-z0-9_]+)\.argtypes = (\[.*?\])\n(?=[A-Za-z\n])", text, flags=re.S | re.M)
+    assert len(found) >= 6
+    for name, expr in found:
+        got = eval(expr, env)          # noqa: S307 - our own documentation
+        want = _lib.SIGNATURES[name][1]
+        assert len(got) == len(want), f"{name}: INTEGRATION.md lists {len(got)} arguments, the binding {len(want)}"
+        for a, b in zip(got, want):
+            assert ctypes.sizeof(a) == ctypes.sizeof(b) and (a is b or a._type_ == b._type_), f"{name}: {a} vs {b}"
+
+
+def test_header_prototypes_match_the_binding_arity():
+    """Every prototype of include/gpa_b200.h has as many parameters as the ctypes binding passes."""
+    text = open(os.path.join(ROOT, "include", "gpa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = re.findall(r"\b(gpa_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) >= 40
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert name in _lib.SIGNATURES, f"{name} is declared but not bound"
+        assert n == len(_lib.SIGNATURES[name][1]), f"{name}: header has {n} parameters, the binding {len(_lib.SIGNATURES[name][1])}"
