@@ -49,6 +49,13 @@ extern "C" int gpa_default_radius(int n, double sigma, double trunc) {
     return r < 0 ? 0 : r;
 }
 
+// Shared-memory budget of the decimating pass-2 kernels (lockin.cu, launch_mr): S (W2 kP + J + kAhead + 1) fine rows
+// x (32 columns + two carrier buffers per warp group) of float2 must fit 227 KB.
+static bool pass2_tile_fits(int s, int j) {
+    const int w2 = s == 8 ? 4 : 8;
+    return (long long)s * (w2 * 16 + j + 3) * (32 + 4) * 8 <= 227 * 1024;
+}
+
 // Parameters of the multirate sweep (same rule as pygpa_b200/_taps.py): returns the stride (2, 4 or 8)
 // or 0 when the multirate form does not apply (use the direct form).
 extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, double* sigma_b, int* Ra, int* Rb) {
@@ -68,6 +75,7 @@ extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, d
         }
         if (rb > 5 * s) continue;
         if (2 * ra + 1 > (N < M ? N : M) || s * ((2 * ra + 1 + s - 1) / s) + 2 > 446) continue;
+        if (!pass2_tile_fits(s, (2 * ra + 1 + s - 1) / s)) continue;     // large sigma: try the next smaller stride
         if (sigma_a) *sigma_a = sa;
         if (sigma_b) *sigma_b = sb;
         if (Ra) *Ra = ra;
@@ -139,7 +147,7 @@ extern "C" int gpa_split_plan(int n, int stride, double sigma_a, const double* w
             j1 += j1 & 1;
             if (j1 < 18) j1 = 18;
             r1 = (s * j1 - 1) / 2;
-            if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446) continue;
+            if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446 || !pass2_tile_fits(s, j1)) continue;
             const double err = std::fmax(split_error(s, sigma_a, sigma_1, r1, h, dw_max), split_error(s, sigma_a, sigma_1, r1, h, 0.5 * dw_max));
             if (b.err < 0.0 || err < b.err) b = Best{err, sigma_1, sigma_2, r1};
         }
