@@ -88,6 +88,7 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
 # ---- split pass 2: G_a = G_1 * G_2, anchor stage shared by the candidates of a plane ---------------
 SPLIT_TOL = 1.3e-6       # worst-case transfer-function error; the 4.5 sigma truncation of G_a alone is 1.3e-6
 SPLIT_TRUNC1 = 6.0       # stage A runs once per plane: its truncation is free
+SPLIT_MAX_LOG_GAIN = float(np.log(8.0))   # largest re-amplification c of a candidate (C3: 2.5; stride 8 at sigma = 22: 3.5)
 
 
 def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
@@ -102,7 +103,10 @@ def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
     m = np.arange(-h, h + 1)
     h2 = s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))
     delta = dw * sigma_a ** 2 / sigma_2 ** 2
-    c = np.exp(2 * np.pi ** 2 * dw ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)
+    log_c = 2 * np.pi ** 2 * dw ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2
+    if log_c > SPLIT_MAX_LOG_GAIN:  # the candidate sits far out on G_1's slope: its band leaves the anchor stage attenuated
+        return float("inf")         # by 1/c and fp32 rounding noise comes back amplified by c
+    c = np.exp(log_c)
     H2 = np.exp(-2j * np.pi * np.outer(s * (f + delta), m)) @ h2
     return float(np.abs(c * G1 * H2 - np.exp(-2 * np.pi ** 2 * sigma_a ** 2 * (f + dw) ** 2)).max())
 

@@ -94,7 +94,10 @@ double split_error(int s, double sigma_a, double sigma_1, int r1, int h, double 
     const double pi = 3.141592653589793238462643383279;
     const double s2sq = sigma_a * sigma_a - sigma_1 * sigma_1, sigma_2 = std::sqrt(s2sq);
     const double delta = dw * sigma_a * sigma_a / s2sq;
-    const double c = std::exp(2.0 * pi * pi * dw * dw * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq);
+    const double log_c = 2.0 * pi * pi * dw * dw * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq;
+    if (log_c > 2.0794415416798357) return HUGE_VAL;   // c > 8: the band leaves the anchor stage attenuated by 1/c and
+                                                        // fp32 rounding noise would come back amplified by c
+    const double c = std::exp(log_c);
     std::vector<double> g1(r1 + 1), h2(h + 1);
     for (int d = 0; d <= r1; ++d) g1[d] = std::exp(-(double)d * d / (2.0 * sigma_1 * sigma_1)) / (sigma_1 * std::sqrt(2.0 * pi));
     for (int m = 0; m <= h; ++m) h2[m] = s * std::exp(-(double)(s * m) * (s * m) / (2.0 * s2sq)) / (sigma_2 * std::sqrt(2.0 * pi));

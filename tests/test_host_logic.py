@@ -173,3 +173,24 @@ def test_multirate_plans_fit_the_pass2_tile_in_shared_memory():
         assert s * (w2 * 16 + j + 3) * 36 * 8 <= 227 * 1024, (sigma, s, j)
         assert s * (8 * 16 + j + 3) * (33 * 4 + 16) + 4 <= 227 * 1024          # pass-1 tile
     assert _taps.multirate_taps(2048, 2048, 28.0)["S"] == 8 and _taps.multirate_taps(2048, 2048, 30.0)["S"] == 4
+
+
+def test_split_plans_are_finite_and_bounded():
+    """Wide grids at large sigma used to overflow the planner's gain exp(2 pi^2 dw^2 ...) into NaN, which compared as
+    'within tolerance'.  Every accepted plan must have a finite error below SPLIT_TOL and a re-amplification <= 8
+    (fp32 rounding noise of the anchor stage comes back multiplied by it)."""
+    rng = np.random.default_rng(4)
+    seen = 0
+    for _ in range(60):
+        n = int(rng.choice([96, 128, 256, 512, 1024, 2048]))
+        sigma = float(rng.choice([4.5, 5, 9, 10, 17.9, 22, 29, 35, 49]))
+        mr = _taps.multirate_taps(n, n, sigma)
+        if mr is None:
+            continue
+        ks = synth.primary_ks(float(rng.choice([0.5 / sigma, 0.05, 0.1, 0.02])), 7.0, 3)
+        kw, kstep = synth.sweep_params(ks, int(rng.choice([9, 21, 41])))
+        sp = _taps.split_taps(n, mr, np.arange(ks[0][0] - kw, ks[0][0] + kw, kstep))
+        if sp is not None:
+            seen += 1
+            assert np.isfinite(sp["err"]) and sp["err"] <= _taps.SPLIT_TOL and sp["c_max"] <= 8.0 * 1.001
+    assert seen >= 10
