@@ -194,3 +194,21 @@ def test_split_plans_are_finite_and_bounded():
             seen += 1
             assert np.isfinite(sp["err"]) and sp["err"] <= _taps.SPLIT_TOL and sp["c_max"] <= 8.0 * 1.001
     assert seen >= 10
+
+
+@pytest.mark.parametrize("shape,sigma,r_k,n_grid,peak,expect", [
+    ((2048, 2048), 10, 0.05, 41, 0, (4, 43, 43, 7, 6.8557)),        # BASELINE config 3 (bench.py)
+    ((1024, 1024), 10, 0.05, 21, 0, (4, 43, 43, 7, 6.8557)),        # config 2
+    ((160, 128), 5, 0.1, 9, 1, (2, 21, 21, 7, 3.4278)),
+    ((256, 320), 22, 0.5 / 22, 9, 1, (8, 95, 103, 7, 16.4924)),
+])
+def test_plans_validated_on_hardware_stay_put(shape, sigma, r_k, n_grid, peak, expect):
+    """The multirate / split plans of the configurations whose GPU parity runs are recorded in profiles/ (round 1):
+    a planner change that alters them needs a new run of the -m gpu tests, so it must show up here first."""
+    mr = _taps.multirate_taps(shape[0], shape[1], float(sigma))
+    ks = synth.primary_ks(r_k, 7.0, 3)
+    kw, kstep = synth.sweep_params(ks, n_grid)
+    k = ks[peak]
+    sp = _taps.split_taps(shape[0], mr, np.arange(k[0] - kw, k[0] + kw, kstep))
+    assert sp is not None
+    assert (mr["S"], mr["Ra_x"], sp["R1"], sp["H"]) == expect[:4] and abs(sp["sigma_1"] - expect[4]) < 1e-4
