@@ -393,6 +393,58 @@ int gpa_deconvolve_workspace_bytes(int N, int M, int dr, size_t* bytes);
 int gpa_gaussian_deconvolve(const double* data, int planes, int N, int M, double sigma, int dr,
                             double balance, double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K1e — k-grid sharding over the GPUs of one NVSwitch box (the reference's
+ * cuGPA.py is single-device, so this has no reference twin).  One process per GPU; every rank
+ * gpa_peer_alloc's one arena, the host binding exchanges the 64-byte IPC handles (torch.distributed)
+ * and gpa_peer_open's the arenas of the other ranks, after which the kernels address peer HBM
+ * directly over NVLink.  Per peak and frame:
+ *     gpa_sweep_argmax_mr (local planes)  ->  gpa_peer_signal / gpa_peer_wait  ->  gpa_key_merge
+ *     ->  gpa_peer_signal / gpa_peer_wait  ->  gpa_sweep_finalize_mr_sharded (owner-writes)
+ *     ->  gpa_peer_signal to the destination rank(s), which gpa_peer_wait.
+ * Flags carry a monotonically increasing epoch (one per frame), so they are never reset.
+ * ------------------------------------------------------------------------------------------ */
+#define GPA_MAX_PEERS 8
+#define GPA_PEER_HANDLE_BYTES 64
+/* cudaMalloc + zero + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree.
+ * handle: host buffer of GPA_PEER_HANDLE_BYTES. */
+int gpa_peer_alloc(size_t bytes, void** dev_ptr /*host, out*/, unsigned char* handle /*host, out*/);
+int gpa_peer_open(const unsigned char* handle /*host*/, void** dev_ptr /*host, out*/);
+int gpa_peer_close(void* dev_ptr);
+int gpa_peer_free(void* dev_ptr);
+/* target_slots: host array of n_targets device addresses (the caller's own slot in every target's flag
+ * array, peer-mapped).  Everything enqueued on `stream` before the signal is visible to a rank that
+ * has waited for this epoch. */
+int gpa_peer_signal(void* const* target_slots /*host*/, int n_targets, unsigned long long epoch, void* stream);
+/* Blocks the STREAM (not the host) until flags[0..n_sources) >= epoch; gives up after timeout_s and
+ * sets *status (device int) to 1 + the index of the missing source. */
+int gpa_peer_wait(const unsigned long long* flags, int n_sources, unsigned long long epoch, double timeout_s,
+                  int* status, void* stream);
+/* In-place max-with-index all-reduce of the packed arg-max keys (see gpa_sweep_argmax): key_ptrs is the
+ * host array of the `world` ranks' key buffers (same layout, n_keys each, own buffer at [rank]); this
+ * rank reduces its 1/world slice of every buffer and stores the result into all of them.  The caller
+ * brackets it with signal / wait pairs (all ranks have finished their local arg-max before, all ranks
+ * have merged their slice after). */
+int gpa_key_merge(void* const* key_ptrs /*host*/, int world, int rank, size_t n_keys, void* stream);
+/* w[i] = wx_dev[row], w[comp_stride + i] = wy_dev[plane] of the winner packed in key[i] (0 where nothing
+ * won): the 'w' output of wfr2_grad_opt from merged keys. */
+int gpa_key_to_w(const unsigned long long* key, size_t n, size_t comp_stride, const double* wx_dev,
+                 const double* wy_dev, int n_planes, int list_mode, int out_f64, void* w, void* stream);
+/* gpa_sweep_finalize_mr for one rank's share of the planes with owner-writes: pixel (x, y) of a winner
+ * this rank owns is stored to lockin_dst[x / dst_rows] and grad_dst[x / dst_rows] (host arrays of n_dst
+ * device pointers to full (N, M) / (N, M, 2) arrays, local or peer-mapped; all pixels go to entry 0 when
+ * n_dst == 1).  Pixels nothing won are zero-filled by the rank that passes write_zero != 0.  Results are
+ * bit-identical to the single-GPU gpa_sweep_finalize_mr. */
+int gpa_sweep_finalize_mr_sharded(int N, int M, const double* wx_rows /*host*/, int n_rows,
+                                  const double* wy_planes /*host*/, int n_planes, int cand_mode,
+                                  int plane_begin, int plane_end, int plane_step, int stride, int Rax, int Ray,
+                                  const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
+                                  int R1x, int H2x,
+                                  const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
+                                  int out_f64, void* const* lockin_dst /*host*/, void* const* grad_dst /*host*/,
+                                  int n_dst, int dst_rows, int write_zero,
+                                  void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

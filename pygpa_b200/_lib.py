@@ -75,6 +75,18 @@ SIGNATURES = {
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                ctypes.POINTER(c_int), c_void_p, c_size_t, c_void_p]),
+    "gpa_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_ubyte)]),
+    "gpa_peer_open": (c_int, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(c_void_p)]),
+    "gpa_peer_close": (c_int, [c_void_p]),
+    "gpa_peer_free": (c_int, [c_void_p]),
+    "gpa_peer_signal": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.c_ulonglong, c_void_p]),
+    "gpa_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_ulonglong, c_double, c_void_p, c_void_p]),
+    "gpa_key_merge": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p]),
+    "gpa_key_to_w": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gpa_sweep_finalize_mr_sharded": (c_int, [c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              _pf, _pf, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,
+                                              ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, c_int,
+                                              c_void_p, c_size_t, c_void_p]),
     "gpa_lawler_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_invert_u": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_resample_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

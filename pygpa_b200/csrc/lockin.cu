@@ -483,29 +483,39 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
     return GPA_OK;
 }
 
-// Finalize from the coarse grids left in the workspace by gpa_sweep_argmax_mr.  Requires that call to
-// have covered exactly [plane_begin, plane_end) with all its planes resident (same ws, same arguments).
-extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
-                                     int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
-                                     int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
-                                     int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
-                                     int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
-                                     size_t ws_bytes, void* stream) {
+static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes, int n_planes, int cand_mode,
+                       int plane_begin, int plane_end, int plane_step, int S, int Rax, int Ray, const float* taps_bx,
+                       const float* taps_by, int Rb, int R1x, int H2x, const unsigned long long* key, double kref_x,
+                       double kref_y, int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx,
+                       void* const* lockin_dst, void* const* grad_dst, int n_dst, int dst_rows, int write_zero, void* ws,
+                       size_t ws_bytes, void* stream) {
     MrGeometry g;
     int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
     if (rc) return rc;
-    GPA_REQUIRE(wx_rows && wy_planes && ws && key && lockin, "null pointer argument");
+    GPA_REQUIRE(wx_rows && wy_planes && ws && key && (lockin || n_dst > 0), "null pointer argument");
     GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes, "bad plane range");
     GPA_REQUIRE(grad_mode == GPA_GRAD_CENTRAL || grad_mode == GPA_GRAD_FORWARD || grad_mode == GPA_GRAD_NONE,
                 "bad grad_mode %d", grad_mode);
-    GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr, "grad is null but a gradient was requested");
+    GPA_REQUIRE(grad_mode == GPA_GRAD_NONE || grad != nullptr || n_dst > 0, "grad is null but a gradient was requested");
     GPA_REQUIRE(plane_step >= 1, "plane_step must be >= 1");
-    if (plane_begin == plane_end) return GPA_OK;
-    const int total = ceil_div(plane_end - plane_begin, plane_step);
-    const int chunk = fit_chunk_mr(g, ws, ws_bytes, total);
-    if (chunk != total) {
-        set_error("gpa_sweep_finalize_mr needs every plane of the range resident (workspace holds %d of %d)", chunk, total);
-        return GPA_ERR_WORKSPACE;
+    GPA_REQUIRE(n_dst >= 0 && n_dst <= GPA_MAX_PEERS, "n_dst out of range");
+    if (n_dst > 0) {
+        GPA_REQUIRE(lockin_dst && (grad_mode == GPA_GRAD_NONE || grad_dst), "null destination table");
+        GPA_REQUIRE(n_dst == 1 || (dst_rows >= 1 && (long long)dst_rows * n_dst >= N), "dst_rows * n_dst must cover the frame");
+        for (int d = 0; d < n_dst; ++d)
+            GPA_REQUIRE(lockin_dst[d] && (grad_mode == GPA_GRAD_NONE || grad_dst[d]), "null destination pointer");
+    }
+    const bool nothing = plane_begin == plane_end;
+    if (nothing && !(n_dst > 0 && write_zero)) return GPA_OK;
+    const int total = nothing ? 0 : ceil_div(plane_end - plane_begin, plane_step);
+    if (!nothing) {
+        const int chunk = fit_chunk_mr(g, ws, ws_bytes, total);
+        if (chunk != total) {
+            set_error("gpa_sweep_finalize_mr needs every plane of the range resident (workspace holds %d of %d)", chunk, total);
+            return GPA_ERR_WORKSPACE;
+        }
+    } else {
+        carve_mr(g, ws, ws_bytes, 0);
     }
     TapTable tb;
     if ((rc = fill_interp(tb, taps_bx, taps_by, Rb, S))) return rc;
@@ -518,12 +528,29 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
     f.kref_x = kref_x; f.kref_y = kref_y; f.N = N; f.M = M;
     f.plane0 = plane_begin; f.plane_begin = plane_begin; f.plane_end = plane_end;
     f.list_mode = cand_mode == GPA_CAND_LIST; f.n_planes = n_planes; f.grad_mode = grad_mode;
+    f.n_dst = n_dst; f.dst_rows = dst_rows > 0 ? dst_rows : N; f.write_zero = write_zero;
+    for (int d = 0; d < n_dst; ++d) {
+        f.lockin_dst[d] = lockin_dst[d];
+        f.grad_dst[d] = grad_mode == GPA_GRAD_NONE ? nullptr : grad_dst[d];
+    }
     mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S; mp.pstep = plane_step;
+    KernelTimer timer("k_mr_finalize", st);
+    if (n_dst > 0) {   // a rank's share of the planes: CTA-level compaction of the owned pixels, owner-writes
+        dim3 grid(ceil_div(M, 64), ceil_div(N, 16));
+#define GPA_MRFINS(SS)                                                                       \
+        do {                                                                                     \
+            if (out_f64) k_mr_finalize_sharded<SS, double2><<<grid, 256, 0, st>>>(mp, tb);       \
+            else k_mr_finalize_sharded<SS, float2><<<grid, 256, 0, st>>>(mp, tb);                \
+        } while (0)
+        if (S == 2) GPA_MRFINS(2); else if (S == 4) GPA_MRFINS(4); else GPA_MRFINS(8);
+#undef GPA_MRFINS
+        GPA_CHECK_CUDA(cudaGetLastError());
+        return GPA_OK;
+    }
     // pixels per warp: no compaction needed when every plane is ours, wider spans for smaller shares
     const bool all_planes = plane_begin == 0 && plane_end == n_planes && plane_step == 1;
     const int span = all_planes ? 32 : 128;      // measured on 2 GPUs (C3): 1.67 ms without compaction, 1.70 at 64, 1.49 at 128
     dim3 grid(ceil_div(M, span), ceil_div(N, 8));
-    KernelTimer timer("k_mr_finalize", st);
 #define GPA_MRFIN2(SS, TT)                                                                  \
     do {                                                                                    \
         if (span == 32) k_mr_finalize<SS, TT, 32><<<grid, 256, 0, st>>>(mp, tb);            \
@@ -537,6 +564,34 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
 #undef GPA_MRFIN
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
+}
+
+// Finalize from the coarse grids left in the workspace by gpa_sweep_argmax_mr.  Requires that call to
+// have covered exactly [plane_begin, plane_end) with all its planes resident (same ws, same arguments).
+extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
+                                     int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
+                                     int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
+                                     int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
+                                     int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
+                                     size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(lockin != nullptr, "null pointer argument");
+    return finalize_mr(N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, plane_begin, plane_end, plane_step, S, Rax, Ray,
+                       taps_bx, taps_by, Rb, R1x, H2x, key, kref_x, kref_y, grad_mode, out_f64, lockin, grad, w, kidx,
+                       nullptr, nullptr, 0, 0, 0, ws, ws_bytes, stream);
+}
+
+// Owner-writes variant for a rank's share of the planes (k-grid sharded over GPUs, peer.cu).
+extern "C" int gpa_sweep_finalize_mr_sharded(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
+                                             int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
+                                             int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
+                                             int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
+                                             int grad_mode, int out_f64, void* const* lockin_dst, void* const* grad_dst,
+                                             int n_dst, int dst_rows, int write_zero, void* ws, size_t ws_bytes,
+                                             void* stream) {
+    GPA_REQUIRE(n_dst >= 1, "n_dst must be >= 1");
+    return finalize_mr(N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, plane_begin, plane_end, plane_step, S, Rax, Ray,
+                       taps_bx, taps_by, Rb, R1x, H2x, key, kref_x, kref_y, grad_mode, out_f64, nullptr, nullptr, nullptr,
+                       nullptr, lockin_dst, grad_dst, n_dst, dst_rows, write_zero, ws, ws_bytes, stream);
 }
 
 extern "C" int gpa_lockin_workspace_bytes(int N, int M, int n_rows, int n_planes, int Rx, int Ry,
@@ -617,6 +672,7 @@ static int finalize_direct(Geometry& g, const float* img, const double* wx_rows,
         const int cnt = plane_end - p0 < chunk ? plane_end - p0 : chunk;
         if (!reuse && (rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
         FinalizeParams f;
+        std::memset(&f, 0, sizeof(f));
         f.planes = g.planes; f.plane_stride = g.plane_stride; f.phx = g.phx;
         f.wx_rows = g.wx_d; f.wy_planes = g.wy_d; f.key = key;
         f.lockin = lockin; f.grad = grad_mode == GPA_GRAD_NONE ? nullptr : grad; f.w = w; f.kidx = kidx;

@@ -21,7 +21,22 @@ struct FinalizeParams {
     int list_mode, n_planes;
     int grad_mode;
     double w0x, w0y;         // 'w' of pixels that never accepted a candidate (0 for the arg-max sweeps, klist[0] for wfr4)
+    // owner-writes of the k-grid sharded sweep (n_dst > 0): pixel (x, y) is stored to the arrays of destination
+    // x / dst_rows (local or peer-mapped over NVLink); lockin / grad above are then unused
+    int n_dst, dst_rows, write_zero;
+    void* lockin_dst[GPA_MAX_PEERS];
+    void* grad_dst[GPA_MAX_PEERS];
 };
+
+template <typename T2>
+__device__ __forceinline__ T2* lockin_of(const FinalizeParams& prm, int x) {
+    return static_cast<T2*>(prm.n_dst > 0 ? prm.lockin_dst[prm.n_dst > 1 ? x / prm.dst_rows : 0] : prm.lockin);
+}
+template <typename R>
+__device__ __forceinline__ R* grad_of(const FinalizeParams& prm, int x) {
+    if (prm.grad_mode == GPA_GRAD_NONE) return nullptr;
+    return static_cast<R*>(prm.n_dst > 0 ? prm.grad_dst[prm.n_dst > 1 ? x / prm.dst_rows : 0] : prm.grad);
+}
 
 __device__ __forceinline__ double wrap_to_pi(double v) {
     // (v + pi) mod 2 pi - pi with a non-negative modulo: mathtools.py:72-75
@@ -50,8 +65,8 @@ template <typename T2>
 __device__ __forceinline__ void finalize_store(const FinalizeParams& prm, size_t pix, int x, int y, unsigned idx, int row,
                                                int plane, float2 s_0, float2 s_m, float2 s_p, float2 s_ym, float2 s_yp) {
     using R = typename real_of<T2>::type;
-    T2* const o_lockin = static_cast<T2*>(prm.lockin);
-    R* const o_grad = static_cast<R*>(prm.grad);
+    T2* const o_lockin = lockin_of<T2>(prm, x);
+    R* const o_grad = grad_of<R>(prm, x);
     R* const o_w = static_cast<R*>(prm.w);
     const size_t npix = (size_t)prm.N * prm.M;
     const int N = prm.N, M = prm.M;
@@ -190,8 +205,10 @@ struct MrFinalizeParams {
 };
 
 // winner of pixel (x, y), known to belong to one of this call's planes
-template <int S, typename T2>
-__device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, const TapTable& taps, int x, int y, unsigned idx,
+// tap(i) = entry i of the interpolation table (x table, then y table): the kernel-parameter constant bank when the
+// index is warp-uniform, a shared-memory copy when it varies per lane
+template <int S, typename T2, typename Tap>
+__device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, Tap tap, int x, int y, unsigned idx,
                                                   int plane, int row, int cand) {
     const FinalizeParams& prm = mp.f;
     const size_t pix = (size_t)x * prm.M + y;
@@ -215,7 +232,7 @@ __device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, co
 #pragma unroll
         for (int j = 0; j < kMrW; ++j) {
             const int v = j - offy[e];
-            gy[e][j] = (v >= 0 && v < kMrW - 1) ? taps.g[S * kMrW + phy_ * kMrW + v].x : 0.f;
+            gy[e][j] = (v >= 0 && v < kMrW - 1) ? tap(S * kMrW + phy_ * kMrW + v) : 0.f;
         }
     }
     int colj[kMrW];
@@ -247,7 +264,7 @@ __device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, co
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             const int w = i - offx[e];
-            gx[e] = (w >= 0 && w < kMrW - 1) ? taps.g[phx_[e] * kMrW + w].x : 0.f;
+            gx[e] = (w >= 0 && w < kMrW - 1) ? tap(phx_[e] * kMrW + w) : 0.f;
         }
         s_xm.x = fmaf(gx[0], rv[1].x, s_xm.x); s_xm.y = fmaf(gx[0], rv[1].y, s_xm.y);
         s_0.x = fmaf(gx[1], rv[1].x, s_0.x);   s_0.y = fmaf(gx[1], rv[1].y, s_0.y);
@@ -321,7 +338,79 @@ k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) 
             row = (int)(idx / (unsigned)prm.n_planes);
             cand = row;
         }
-        mr_finalize_pixel<S, T2>(mp, taps, x, y, idx, plane, row, cand);
+        mr_finalize_pixel<S, T2>(mp, [&](int i) { return taps.g[i].x; }, x, y, idx, plane, row, cand);
     }
 }
 
+
+// Sharded twin of k_mr_finalize (k-grid split over GPUs): a rank owns only the pixels whose winner lies in its
+// planes — 1/W of the frame, finely interleaved.  The CTA compacts the owned pixels of a 16 x 64 tile into a
+// shared list (ballot + one shared atomic per warp) and all 256 threads then work through the list, so the
+// time scales with the rank's share; the tile is compact in both axes, which keeps the 12 x 12 coarse windows
+// of its pixels in L1.  x varies per lane here, so the interpolation taps come from shared memory.  The same
+// sequence of FMAs per pixel as k_mr_finalize: bit-identical results.  Stores go to the destination arrays
+// of the pixel (FinalizeParams::lockin_dst / grad_dst, possibly peer memory).
+template <int S, typename T2>
+__global__ void __launch_bounds__(256)
+k_mr_finalize_sharded(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
+    const FinalizeParams& prm = mp.f;
+    using R = typename real_of<T2>::type;
+    constexpr int FX = 16, FY = 64;
+    __shared__ unsigned short s_list[FX * FY];
+    __shared__ int s_cnt;
+    __shared__ float s_tap[2 * S * kMrW];
+    const int lane = threadIdx.x & 31;
+    const int x0 = blockIdx.y * FX, y0 = blockIdx.x * FY;
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int i = threadIdx.x; i < 2 * S * kMrW; i += 256) s_tap[i] = taps.g[i].x;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < FX * FY / 256; ++j) {
+        const int p = threadIdx.x + 256 * j;
+        const int x = x0 + p / FY, y = y0 + p % FY;
+        bool own = false;
+        if (x < prm.N && y < prm.M) {
+            const size_t pix = (size_t)x * prm.M + y;
+            const unsigned long long k = prm.key[pix];
+            if ((k >> 32) == 0ull) {      // nothing ever exceeded |0|: geometric_phase_analysis.py:806 keeps the zeros
+                if (prm.write_zero) {
+                    T2 z;
+                    z.x = 0;
+                    z.y = 0;
+                    lockin_of<T2>(prm, x)[pix] = z;
+                    R* const g = grad_of<R>(prm, x);
+                    if (g) {
+                        g[2 * pix] = 0;
+                        g[2 * pix + 1] = 0;
+                    }
+                }
+            } else {
+                const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+                const int plane = prm.list_mode ? (int)idx : (int)(idx % (unsigned)prm.n_planes);
+                own = plane >= prm.plane_begin && plane < prm.plane_end && (plane - prm.plane_begin) % mp.pstep == 0;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, own);
+        int base = 0;
+        if (lane == 0 && mask) base = atomicAdd(&s_cnt, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (own) s_list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)p;
+    }
+    __syncthreads();
+    const int count = s_cnt;
+    for (int t = threadIdx.x; t < count; t += 256) {
+        const int p = s_list[t];
+        const int x = x0 + p / FY, y = y0 + p % FY;
+        const unsigned long long k = prm.key[(size_t)x * prm.M + y];
+        const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+        int plane, row, cand;
+        if (prm.list_mode) {
+            plane = (int)idx; row = plane; cand = 0;
+        } else {
+            plane = (int)(idx % (unsigned)prm.n_planes);
+            row = (int)(idx / (unsigned)prm.n_planes);
+            cand = row;
+        }
+        mr_finalize_pixel<S, T2>(mp, [&](int i) { return s_tap[i]; }, x, y, idx, plane, row, cand);
+    }
+}

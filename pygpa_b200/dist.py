@@ -1,46 +1,78 @@
-"""Multi-GPU sharding of the adaptive sweep: one process per GPU, torch.distributed (NCCL).
+"""Multi-GPU sharding of the adaptive sweep: one process per GPU of one NVSwitch box.
 
-The candidates are independent until the per-pixel arg-max, so the k-grid shards with ONE
-exchange step: every rank holds the whole frame, runs pass 1 / pass 2 for its share of the
-first-pass planes (sharding over wy duplicates no work), and the packed keys
-(|sf|^2 bits << 32 | ~flat_index) are combined with an integer MAX all-reduce — largest
-amplitude wins, exact ties go to the lowest flat index, which is the reference's strict-'>'
-first-wins rule (geometric_phase_analysis.py:806).  Each rank then finalises the pixels whose
-winner it owns; the payload is combined with a SUM all-reduce (exactly one non-zero
-contributor per pixel, so the sum is exact and the N-GPU result is bit-identical to 1 GPU).
+The candidates are independent until the per-pixel arg-max, so the k-grid shards with ONE exchange
+step: every rank holds the whole frame, runs the arg-max kernels for its
+share of the flattened (peak, first-pass plane) list — sharding over wy duplicates no work — and the
+packed keys (|sf|^2 bits << 32 | ~flat_index) are combined with an integer MAX: largest amplitude
+wins, exact ties go to the lowest flat index, which is the reference's strict-'>' first-wins rule
+(geometric_phase_analysis.py:806).  Each rank then finalises the pixels whose winner it owns.
 
-The helpers work on CPU tensors with the gloo backend too (tests/test_dist_gloo.py).
+Two transports:
+
+* ``peer`` (default on CUDA, world <= 8): the exchange runs inside our own kernels over NVLink peer
+  memory (csrc/peer.cu, peer.py).  Per peak: local arg-max -> flag signal/wait -> ``k_key_merge``
+  (in-place reduce-scatter + all-gather of the keys, every rank reduces 1/W of the pixels and stores
+  the result into all ranks) -> signal/wait -> ``k_mr_finalize_sharded``, which writes the lock-in /
+  gradient of the pixels a rank owns STRAIGHT INTO THE DESTINATION RANK'S output arrays (owner-writes:
+  exactly one rank owns a pixel, so there is no payload reduction at all) -> signal to the
+  destination.  The peaks run on priority-ordered streams, so the exchange and finalize of peak p
+  overlap the arg-max of peak p+1; only the last peak's exchange is exposed.
+* ``collective`` (fallback: direct-form plans, shared workspaces, CPU tensors with gloo in the
+  tests): one MAX all-reduce of the stacked keys and one SUM reduction of the zero-padded payload
+  through torch.distributed, as in round 1.
+
+Both give results bit-identical to one GPU (tests/test_dist_gpu.py, bench.py's multi_gpu_check).
 """
 from __future__ import annotations
 
+import ctypes
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_units", "shard_units_interleaved", "merge_keys", "merge_payload", "pack_key", "unpack_key", "sharded_sweep"]
+__all__ = ["shard_units", "shard_units_interleaved", "merge_keys", "merge_payload", "pack_key", "unpack_key",
+           "sharded_sweep", "ShardedSweep"]
+
+
+def _counts(n_peaks, n_planes):
+    """Per-peak plane counts: an int applies to every peak, a sequence is taken as is.  np.arange grids are
+    rounding dependent (6 or 7 planes for ksteps = 3), so the peaks of one lattice may differ."""
+    if np.isscalar(n_planes):
+        return [int(n_planes)] * int(n_peaks)
+    counts = [int(c) for c in n_planes]
+    if len(counts) != n_peaks:
+        raise ValueError(f"{n_peaks} peaks but {len(counts)} plane counts")
+    return counts
 
 
 def shard_units(n_peaks, n_planes, world, rank):
     """Split the flattened (peak, plane) list into `world` contiguous, balanced shares.
+    n_planes: planes per peak (int, or one count per peak).
     Returns [(plane_begin, plane_end)] * n_peaks for `rank` (empty ranges have begin == end)."""
-    total = n_peaks * n_planes
+    counts = _counts(n_peaks, n_planes)
+    total = sum(counts)
     lo = (total * rank) // world
     hi = (total * (rank + 1)) // world
-    out = []
-    for p in range(n_peaks):
-        a, b = max(lo, p * n_planes), min(hi, (p + 1) * n_planes)
-        out.append((a - p * n_planes, b - p * n_planes) if b > a else (0, 0))
+    out, off = [], 0
+    for c in counts:
+        a, b = max(lo, off), min(hi, off + c)
+        out.append((a - off, b - off) if b > a else (0, 0))
+        off += c
     return out
 
 
 def shard_units_interleaved(n_peaks, n_planes, world, rank):
-    """Round-robin share of the flattened (peak, plane) list: unit u = peak * n_planes + plane goes
-    to rank u % world.  Returns [(plane_begin, plane_end, plane_step)] * n_peaks.  Every rank gets
-    planes spread over the whole grid (in particular some near its centre, where the winners
-    usually are), which keeps the exact pruning of the multirate arg-max effective on every rank."""
-    out = []
-    for p in range(n_peaks):
-        begin = (rank - p * n_planes) % world
-        out.append((begin, n_planes, world) if begin < n_planes else (0, 0, 1))
+    """Round-robin share of the flattened (peak, plane) list: unit u = offset(peak) + plane goes to rank
+    u % world (offset = planes of the earlier peaks).  Returns [(plane_begin, plane_end, plane_step)] *
+    n_peaks.  Every rank gets planes spread over the whole grid (in particular some near its centre,
+    where the winners usually are), which keeps the exact pruning of the multirate arg-max effective on
+    every rank."""
+    out, off = [], 0
+    for c in _counts(n_peaks, n_planes):
+        begin = (rank - off) % world
+        out.append((begin, c, world) if begin < c else (0, 0, 1))
+        off += c
     return out
 
 
@@ -74,48 +106,164 @@ def merge_payload(tensors, group=None):
     return tensors
 
 
-def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
-    """All peaks of one frame, k-grid sharded over the ranks of `group`.
-    plans: one engine.SweepPlan per peak (identical on every rank; give them private workspaces so
-    the finalize reuses what the arg-max left and stays bit-identical to one GPU).  A single rank with
-    private multirate plans takes the same route (no collectives): its peaks overlap on their streams.
-    Returns [dict(lockin, grad, kidx, key)] per peak — on every rank, or with dst=<rank> the payload
-    (lockin, grad) is only reduced to that rank.
+# ----------------------------------------------------------------------------------------------
+# the sharded sweep
+# ----------------------------------------------------------------------------------------------
+_PH_ARGMAX, _PH_MERGED, _PH_DELIVERED = 0, 1, 2
+_FLAG_BYTES = 4096
 
-    Exactly two collectives per frame, each issued when every rank has finished its local work:
-    one MAX all-reduce of the stacked keys (8 B/pixel/peak) and one SUM reduction of the stacked
-    payload (16 B/pixel/peak).  They are deliberately NOT overlapped with the arg-max kernels: the
-    plane shares of the ranks start at different peaks, so an early collective would make NCCL's
-    CTAs spin on the slower peer while occupying SMs the sweep kernels need (measured: +4 ms per
-    frame on 2 GPUs, against 0.75 ms for the two collectives issued at the end)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    n_peaks, n, m, dev = len(plans), plans[0].n, plans[0].m, img_dev.device
-    private = all(p._private and p.mr is not None and p.mr_in_flight == p.wy.size for p in plans)
-    if world == 1 and not (private and dev.type == "cuda"):
-        return [plan.run(img_dev, kref, grad_mode) for plan, kref in zip(plans, krefs)]
-    # multirate plans with their own workspace take an interleaved share (good pruning thresholds on
-    # every rank); otherwise contiguous plane ranges
-    interleave = all(p.mr is not None and p._private and p.mr_in_flight >= -(-p.wy.size // world) for p in plans)
-    if interleave:
-        ranges = shard_units_interleaved(n_peaks, plans[0].wy.size, world, rank)
-    else:
-        ranges = [(lo, hi, 1) for lo, hi in shard_units(n_peaks, plans[0].wy.size, world, rank)]
-    # The peaks are independent until the collectives.  With private workspaces their kernels go to one
-    # stream per peak: a rank's share of one peak is only a few planes (5 of 41 on 8 GPUs = 320 pass-2
-    # CTAs = 2.2 waves of the 148 SMs, which run as 3), so the tail of one peak is filled by the next.
-    side = _peak_streams(dev, n_peaks) if dev.type == "cuda" and all(p._private for p in plans) else None
-    keys = torch.zeros((n_peaks, n, m), dtype=torch.int64, device=dev)
 
-    def per_peak(fn):
+class ShardedSweep:
+    """All peaks of one frame, k-grid sharded over the ranks of `group`; reusable for every frame of that
+    shape (collective constructor: every rank builds it with identical arguments).
+
+    plans   one engine.SweepPlan per peak, identical on every rank.  The peer transport needs multirate
+            plans with private workspaces that keep a rank's whole share resident (then the finalize
+            interpolates from the coarse grids the arg-max left, exactly as on one GPU).
+    dst     where the winner payload lands: a rank number (default 0: whole arrays on that rank),
+            'rows' (row slice r of every array on rank r: N/W rows each, what the host-facing path uses —
+            every GPU then copies its slice out over its own PCIe link), or None with the collective
+            transport (every rank gets everything).
+    A call returns, per peak, a dict of tensors that live in this object's buffers (valid until the next
+    call): key, lockin, grad, kidx, w (if want_w), plus 'rows' = the (begin, end) rows that are valid on
+    this rank ((0, 0) on a rank that is not a destination)."""
+
+    def __init__(self, plans, krefs, group=None, dst=0, out_f64=False, want_w=False, transport="auto", timeout_s=20.0):
+        from . import _lib
+        self.plans, self.krefs, self.group = list(plans), [tuple(map(float, k)) for k in krefs], group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        p0 = self.plans[0]
+        self.n, self.m, self.dev = p0.n, p0.m, p0.device
+        if any((p.n, p.m) != (self.n, self.m) for p in self.plans):
+            raise ValueError("all plans must share one frame shape")
+        self.n_peaks = len(self.plans)
+        self.out_f64, self.want_w = bool(out_f64), bool(want_w)
+        self.timeout_s = float(timeout_s)
+        counts = [p.wy.size for p in self.plans]
+        world, rank = self.world, self.rank
+        private_mr = all(p._private and p.mr is not None for p in self.plans)
+        # multirate plans with their own workspace take an interleaved share (good pruning thresholds on
+        # every rank) if it fits their resident planes; otherwise contiguous plane ranges
+        inter = shard_units_interleaved(self.n_peaks, counts, world, rank)
+        fits = all(-(-(hi - lo) // st) <= p.mr_in_flight for p, (lo, hi, st) in zip(self.plans, inter)) if private_mr else False
+        self.ranges = inter if fits else [(lo, hi, 1) for lo, hi in shard_units(self.n_peaks, counts, world, rank)]
+        can_peer = self.dev.type == "cuda" and private_mr and fits and world <= 8
+        if transport == "auto":
+            transport = "peer" if can_peer else "collective"
+        if transport == "peer" and not can_peer:
+            raise ValueError("the peer transport needs multirate plans with private workspaces holding a rank's share, "
+                             "a CUDA device and at most 8 ranks")
+        if transport not in ("peer", "collective"):
+            raise ValueError("transport must be 'auto', 'peer' or 'collective'")
+        self.transport = transport
+        if dst == "rows" and transport != "peer":
+            raise ValueError("dst='rows' needs the peer transport")
+        if dst is None and transport == "peer":
+            dst = "rows"
+        self.dst = dst
+        self.lib = _lib.load() if self.dev.type == "cuda" else None
+        self.epoch = 0
+        self.record = False          # True: bracket the phases of every peak with CUDA events (bench.py)
+        self._events = None
+        self._streams = _peak_streams(self.dev, self.n_peaks) if self.dev.type == "cuda" and all(p._private for p in self.plans) else None
+        n, m, P = self.n, self.m, self.n_peaks
+        cb, rb = (16, 8) if self.out_f64 else (8, 4)
+        if transport == "peer":
+            from .peer import PeerArena
+            off_key = _FLAG_BYTES
+            off_lock = off_key + P * n * m * 8
+            off_grad = off_lock + P * n * m * cb
+            total = off_grad + P * n * m * 2 * rb
+            self.arena = PeerArena(total, group=group, device=self.dev)
+            self._off = {"key": off_key, "lockin": off_lock, "grad": off_grad}
+            self.keys = self.arena.tensor(off_key, (P, n, m), torch.int64)
+            self.lockin = self.arena.tensor(off_lock, (P, n, m), torch.complex128 if self.out_f64 else torch.complex64)
+            self.grad = self.arena.tensor(off_grad, (P, n, m, 2), torch.float64 if self.out_f64 else torch.float32)
+            self._status = self.arena.tensor(2048, (4,), torch.int32)
+            if dst == "rows":
+                self.dst_ranks, self.dst_rows = list(range(world)), -(-n // world)
+            else:
+                self.dst_ranks, self.dst_rows = [int(dst)], n
+            r0 = self.dst_ranks.index(rank) * self.dst_rows if rank in self.dst_ranks else 0
+            self.rows = (min(r0, n), min(r0 + self.dst_rows, n)) if rank in self.dst_ranks else (0, 0)
+        else:
+            self.arena = None
+            self.keys = torch.zeros((P, n, m), dtype=torch.int64, device=self.dev)
+            self.rows = (0, n) if (dst is None or dst == rank or world == 1) else (0, 0)
+        self.kidx = torch.empty((P, n, m), dtype=torch.int32, device=self.dev)
+        self.w = torch.empty((P, 2, n, m), dtype=torch.float64 if self.out_f64 else torch.float32, device=self.dev) if want_w else None
+        if self.dev.type == "cuda":
+            self._axes = [(torch.from_numpy(p.wx).to(self.dev), torch.from_numpy(p.wy).to(self.dev)) for p in self.plans]
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def _flag_off(self, phase, peak, src=0):
+        return ((phase * self.n_peaks + peak) * 8 + src) * 8
+
+    def _signal(self, phase, peak, targets):
+        from . import _lib, engine
+        slots = (ctypes.c_void_p * len(targets))(*[self.arena.addr(t, self._flag_off(phase, peak, self.rank)) for t in targets])
+        _lib.check(self.lib.gpa_peer_signal(slots, len(targets), self.epoch, engine._stream()))
+        engine._count(1)
+
+    def _wait(self, phase, peak):
+        from . import _lib, engine
+        _lib.check(self.lib.gpa_peer_wait(ctypes.c_void_p(self.arena.addr(self.rank, self._flag_off(phase, peak))), self.world,
+                                          self.epoch, self.timeout_s, engine._ptr(self._status), engine._stream()))
+        engine._count(1)
+
+    def _mark(self, peak, name):
+        if self.record:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events[peak][name] = ev
+
+    def check(self):
+        """Raise if a flag wait timed out since the last check (host-synchronising)."""
+        if self.transport == "peer":
+            st = int(self._status[0].item())
+            if st:
+                self._status.zero_()
+                from ._lib import GpaError
+                raise GpaError(f"rank {self.rank}: peer flag wait timed out (missing source rank {st - 1})")
+
+    def timings(self):
+        """Per-peak phase durations (ms) of the last recorded call; synchronises."""
+        torch.cuda.synchronize(self.dev)
+        out = []
+        order = ["start", "argmax", "peers_ready", "merged", "finalized", "delivered"]
+        for evs in self._events or []:
+            row = {}
+            prev = "start"
+            for name in order[1:]:
+                if name in evs:
+                    row[name + "_ms"] = evs[prev].elapsed_time(evs[name])
+                    prev = name
+            row["total_ms"] = evs["start"].elapsed_time(evs[prev])
+            out.append(row)
+        return out
+
+    def close(self):
+        if self.arena is not None:
+            self.arena.close()
+            self.arena = None
+
+    # ---- one frame ------------------------------------------------------------------------------
+    def __call__(self, img_dev, grad_mode=0):
+        if self.transport == "peer":
+            return self._run_peer(img_dev, grad_mode)
+        return self._run_collective(img_dev, grad_mode)
+
+    def _per_peak(self, fn):
+        side = self._streams
         if side is None:
-            for p in range(n_peaks):
+            for p in range(self.n_peaks):
                 fn(p)
             return
-        main = torch.cuda.current_stream(dev)
+        main = torch.cuda.current_stream(self.dev)
         start = torch.cuda.Event()
         start.record(main)
-        for p in range(n_peaks):
+        for p in range(self.n_peaks):
             side[p].wait_event(start)
             with torch.cuda.stream(side[p]):
                 fn(p)
@@ -123,51 +271,161 @@ def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None):
             done.record(side[p])
             main.wait_event(done)
 
-    def argmax_peak(p):
-        lo, hi, step = ranges[p]
-        if hi > lo:
-            plans[p].argmax(img_dev, keys[p], lo, hi, step)
-    per_peak(argmax_peak)
-    if world > 1:
-        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
-    want_grad = grad_mode != 2
-    # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)] float32, zero where this rank owns nothing
-    payload = torch.zeros((2 if want_grad else 1, n_peaks, n, m, 2), dtype=torch.float32, device=dev)
-    lockin = torch.view_as_complex(payload[0])
-    outs = [{"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None}
-            for p in range(n_peaks)]
+    def _outs(self):
+        return [{"key": self.keys[p], "lockin": self.lockin[p], "grad": self.grad[p], "kidx": self.kidx[p],
+                 "w": self.w[p] if self.w is not None else None, "rows": self.rows} for p in range(self.n_peaks)]
 
-    def finalize_peak(p):
-        lo, hi, step = ranges[p]
-        if hi > lo:
-            plans[p].finalize(img_dev, keys[p], krefs[p], grad_mode, plane_begin=lo, plane_end=hi, want_kidx=False,
-                              planes_valid=plans[p]._private, out=outs[p], plane_step=step)
-    per_peak(finalize_peak)
-    for p in range(n_peaks):
-        outs[p]["key"] = keys[p]
-    if world == 1:
-        pass
-    elif dst is None:
-        dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
-    else:
-        dist.reduce(payload, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    kidx = torch.empty((n_peaks, n, m), dtype=torch.int32, device=dev)
-    if dev.type == "cuda":
+    def _run_peer(self, img_dev, grad_mode):
         from . import _lib, engine
-        _lib.check(_lib.load().gpa_key_to_kidx(engine._ptr(keys), engine._ptr(kidx), keys.numel(), engine._stream()))
-    else:
-        kidx.copy_(unpack_key(keys)[1])
-    for p, o in enumerate(outs):
-        o["kidx"] = kidx[p]
-    return outs
+        lib, world, rank, n, m = self.lib, self.world, self.rank, self.n, self.m
+        self.epoch += 1
+        everyone = list(range(world))
+        want_grad = grad_mode != engine.GRAD_NONE
+        cb, rb = (16, 8) if self.out_f64 else (8, 4)
+        if self.record:
+            self._events = [dict() for _ in range(self.n_peaks)]
+
+        def peak(p):
+            plan = self.plans[p]
+            lo, hi, step = self.ranges[p]
+            self._mark(p, "start")
+            self.keys[p].zero_()
+            if hi > lo:
+                plan.argmax(img_dev, self.keys[p], lo, hi, step)
+            self._mark(p, "argmax")
+            if world > 1:
+                self._signal(_PH_ARGMAX, p, everyone)
+                self._wait(_PH_ARGMAX, p)
+                self._mark(p, "peers_ready")
+                ptrs = (ctypes.c_void_p * world)(*[self.arena.addr(r, self._off["key"] + p * n * m * 8) for r in everyone])
+                _lib.check(lib.gpa_key_merge(ptrs, world, rank, n * m, engine._stream()))
+                engine._count(1)
+                self._signal(_PH_MERGED, p, everyone)
+                self._wait(_PH_MERGED, p)
+                self._mark(p, "merged")
+            lock_dst = (ctypes.c_void_p * len(self.dst_ranks))(*[self.arena.addr(r, self._off["lockin"] + p * n * m * cb) for r in self.dst_ranks])
+            grad_dst = (ctypes.c_void_p * len(self.dst_ranks))(*[self.arena.addr(r, self._off["grad"] + p * n * m * 2 * rb) for r in self.dst_ranks])
+            mr = plan.mr
+            ws = plan._workspace()
+            _lib.check(lib.gpa_sweep_finalize_mr_sharded(
+                *plan._geom(), lo, hi, step, mr["S"], mr["Ra_x"], mr["Ra_y"], _lib.as_pf(mr["taps_bx"]), _lib.as_pf(mr["taps_by"]),
+                mr["Rb"], *plan._split_geom(), engine._ptr(self.keys[p]), self.krefs[p][0], self.krefs[p][1], grad_mode,
+                int(self.out_f64), lock_dst, grad_dst if want_grad else None, len(self.dst_ranks), self.dst_rows,
+                int(rank == 0), engine._ptr(ws), ws.numel(), engine._stream()))
+            engine._count(1)
+            self._mark(p, "finalized")
+            if world > 1:
+                self._signal(_PH_DELIVERED, p, self.dst_ranks)
+                if rank in self.dst_ranks:
+                    self._wait(_PH_DELIVERED, p)
+            r0, r1 = self.rows
+            if r1 > r0:       # k-index and w of this rank's rows, decoded from the merged keys
+                kk = self.keys[p, r0:r1]
+                _lib.check(lib.gpa_key_to_kidx(engine._ptr(kk), engine._ptr(self.kidx[p, r0:r1]), kk.numel(), engine._stream()))
+                engine._count(1)
+                if self.w is not None:
+                    wx_d, wy_d = self._axes[p]
+                    _lib.check(lib.gpa_key_to_w(engine._ptr(kk), kk.numel(), n * m, engine._ptr(wx_d), engine._ptr(wy_d), plan.wy.size,
+                                                int(plan.cand_mode == engine.CAND_LIST), int(self.out_f64),
+                                                ctypes.c_void_p(self.w[p].data_ptr() + r0 * m * rb), engine._stream()))
+                    engine._count(1)
+            self._mark(p, "delivered")
+        self._per_peak(peak)
+        return self._outs()
+
+    def _run_collective(self, img_dev, grad_mode):
+        """Round-1 transport: one MAX all-reduce of the stacked keys, one SUM reduction of the zero-padded payload.
+        The collectives are issued when every rank has finished its local work (an early collective makes NCCL's
+        CTAs spin on the slower peer while holding SMs the sweep kernels need)."""
+        from . import _lib, engine
+        world, rank, n, m, dev, P = self.world, self.rank, self.n, self.m, self.dev, self.n_peaks
+        if world == 1 and not (self._streams is not None and all(p.mr is not None and p.mr_in_flight == p.wy.size for p in self.plans)):
+            outs = [plan.run(img_dev, kref, grad_mode, out_f64=self.out_f64, want_w=self.want_w)
+                    for plan, kref in zip(self.plans, self.krefs)]
+            for o in outs:
+                o["rows"] = (0, n)
+            return outs
+        keys = self.keys
+        keys.zero_()
+
+        def argmax_peak(p):
+            lo, hi, step = self.ranges[p]
+            if hi > lo:
+                self.plans[p].argmax(img_dev, keys[p], lo, hi, step)
+        self._per_peak(argmax_peak)
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=self.group)
+        want_grad = grad_mode != engine.GRAD_NONE
+        real = torch.float64 if self.out_f64 else torch.float32
+        # payload buffer: [lockin (P,N,M,2) | grad (P,N,M,2)], zero where this rank owns nothing
+        payload = torch.zeros((2 if want_grad else 1, P, n, m, 2), dtype=real, device=dev)
+        lockin = torch.view_as_complex(payload[0])
+        outs = [{"lockin": lockin[p], "grad": payload[1, p] if want_grad else None, "w": None, "kidx": None} for p in range(P)]
+
+        def finalize_peak(p):
+            lo, hi, step = self.ranges[p]
+            if hi > lo:
+                self.plans[p].finalize(img_dev, keys[p], self.krefs[p], grad_mode, out_f64=self.out_f64, plane_begin=lo,
+                                       plane_end=hi, want_kidx=False, planes_valid=self.plans[p]._private, out=outs[p],
+                                       plane_step=step)
+        self._per_peak(finalize_peak)
+        if world == 1:
+            pass
+        elif self.dst is None:
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.reduce(payload, dst=self.dst, op=dist.ReduceOp.SUM, group=self.group)
+        lib = self.lib
+        _lib.check(lib.gpa_key_to_kidx(engine._ptr(keys), engine._ptr(self.kidx), keys.numel(), engine._stream()))
+        for p, o in enumerate(outs):
+            o["key"], o["kidx"], o["rows"] = keys[p], self.kidx[p], self.rows
+            if self.w is not None:
+                wx_d, wy_d = self._axes[p]
+                _lib.check(lib.gpa_key_to_w(engine._ptr(keys[p]), n * m, n * m, engine._ptr(wx_d), engine._ptr(wy_d),
+                                            self.plans[p].wy.size, int(self.plans[p].cand_mode == engine.CAND_LIST),
+                                            int(self.out_f64), engine._ptr(self.w[p]), engine._stream()))
+                o["w"] = self.w[p]
+        return outs
+
+
+_sweeps = {}
+
+
+def sharded_sweep(img_dev, plans, krefs, grad_mode=0, group=None, dst=None, transport="auto"):
+    """All peaks of one frame, k-grid sharded over the ranks of `group` (function form of ShardedSweep; the
+    executor — plans, peer arena, streams — is cached per plan set, so every rank must call this with the same
+    plans in the same order).  dst=None: every rank gets the whole result with the collective transport; the peer
+    transport delivers rows [r N/W, (r+1) N/W) to rank r.  dst=<rank>: everything lands on that rank.
+    Returns [dict(key, lockin, grad, kidx, rows)] per peak; the tensors are reused by the next call."""
+    key = (tuple(id(p) for p in plans), id(group), dst, transport)
+    sw = _sweeps.get(key)
+    if sw is None:
+        if len(_sweeps) >= 4:
+            for old in _sweeps.values():
+                old.close()
+            _sweeps.clear()
+        if dst is None and transport == "auto":
+            transport = "collective"
+        sw = ShardedSweep(plans, krefs, group=group, dst=dst, transport=transport)
+        _sweeps[key] = sw
+    sw.krefs = [tuple(map(float, k)) for k in krefs]
+    return sw(img_dev, grad_mode)
+
+
+def release():
+    """Close every cached executor (collective: unmaps the peer arenas)."""
+    for sw in _sweeps.values():
+        sw.close()
+    _sweeps.clear()
 
 
 _side_streams = {}
 
 
 def _peak_streams(dev, n):
-    """One side stream per peak and device, created once."""
+    """One side stream per peak and device, created once, in DESCENDING priority: peak 0's kernels are scheduled
+    first, so its key exchange and finalize overlap the arg-max of the later peaks."""
     pool = _side_streams.setdefault(str(dev), [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
+        pool.append(torch.cuda.Stream(device=dev, priority=-(n - 1 - len(pool))))
     return pool[:n]

@@ -43,6 +43,18 @@ def test_interleaved_shares_are_balanced_and_complete():
         assert (seen == 1).all() and max(sizes) - min(sizes) <= 1
 
 
+def test_unequal_plane_counts_use_every_plane():
+    """peaks with different np.arange lengths must each be swept over their OWN plane count."""
+    for world in (1, 2, 3, 8):
+        seen = [np.zeros(c, dtype=int) for c in (6, 7, 6)]
+        for rank in range(world):
+            for p, (lo, hi, st) in enumerate(gdist.shard_units_interleaved(3, (6, 7, 6), world, rank)):
+                seen[p][lo:hi:st] += 1
+            for p, (lo, hi) in enumerate(gdist.shard_units(3, (6, 7, 6), world, rank)):
+                seen[p][lo:hi] += 1
+        assert all((s == 2).all() for s in seen)
+
+
 def test_pack_unpack_and_tie_break():
     amp2 = torch.tensor([0.0, 1.5, 1.5, 3.0e-20])
     idx = torch.tensor([7, 3, 2, 1680])
