@@ -60,6 +60,10 @@ int gpa_device_sm_count(void);  /* of the current device; <0 on error */
 int gpa_profile_enable(int on);
 int gpa_profile_read(const char* kernel, double* total_ms, int* launches, int reset);
 
+/* Measured FP32 FMA-pipe peak of the current device in TFLOP/s (register-only fma.rn.f32x2 loop, best of 5,
+ * CUDA events; synchronises).  bench.py uses it as the denominator of the K1 roofline.  ws: >= 1.5 MB. */
+int gpa_fp32_peak_tflops(void* ws, size_t ws_bytes, double* tflops /*host, out*/, void* stream);
+
 /* Staging helper for the host binding: the reference takes float64 images
  * (cp.asarray(image), cuGPA.py:52); the kernels read float32. */
 int gpa_cast_f64_to_f32(const double* in, float* out, size_t n, void* stream);
@@ -420,6 +424,12 @@ int gpa_peer_signal(void* const* target_slots /*host*/, int n_targets, unsigned 
  * sets *status (device int) to 1 + the index of the missing source. */
 int gpa_peer_wait(const unsigned long long* flags, int n_sources, unsigned long long epoch, double timeout_s,
                   int* status, void* stream);
+/* dst <- src on `stream`; either side may be local, peer-mapped or page-locked host memory (cudaMemcpyDefault). */
+int gpa_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+/* Page-lock an existing host range (a shared-memory segment every rank maps) so that each GPU can DMA its
+ * share of the results into it over its own PCIe link. */
+int gpa_host_register(void* host_ptr /*host*/, size_t bytes);
+int gpa_host_unregister(void* host_ptr /*host*/);
 /* In-place max-with-index all-reduce of the packed arg-max keys (see gpa_sweep_argmax): key_ptrs is the
  * host array of the `world` ranks' key buffers (same layout, n_keys each, own buffer at [rank]); this
  * rank reduces its 1/world slice of every buffer and stores the result into all of them.  The caller

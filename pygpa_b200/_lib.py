@@ -23,6 +23,7 @@ SIGNATURES = {
     "gpa_device_sm_count": (c_int, []),
     "gpa_profile_enable": (c_int, [c_int]),
     "gpa_profile_read": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_double), ctypes.POINTER(c_int), c_int]),
+    "gpa_fp32_peak_tflops": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_double), c_void_p]),
     "gpa_cast_f64_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_key_to_kidx": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_phase_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
@@ -81,6 +82,9 @@ SIGNATURES = {
     "gpa_peer_free": (c_int, [c_void_p]),
     "gpa_peer_signal": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.c_ulonglong, c_void_p]),
     "gpa_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_ulonglong, c_double, c_void_p, c_void_p]),
+    "gpa_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_host_register": (c_int, [c_void_p, c_size_t]),
+    "gpa_host_unregister": (c_int, [c_void_p]),
     "gpa_key_merge": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p]),
     "gpa_key_to_w": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gpa_sweep_finalize_mr_sharded": (c_int, [c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

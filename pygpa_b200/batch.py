@@ -47,13 +47,13 @@ class FramePipeline:
     def __call__(self, frame, undistort=True):
         """One frame (NumPy or tensor) -> dict(u, corrected) of CUDA tensors (float64)."""
         arr = frame if isinstance(frame, torch.Tensor) else np.asarray(frame, dtype=np.float64)
-        arr = arr - arr.mean()
-        f32 = engine.image_to_device(arr, self.device)
+        f32 = engine.image_to_device(arr - arr.mean(), self.device)
         u = self.displacement(f32)
         out = {"u": u}
         if undistort:
-            # the extracted field is minus the physical displacement (lock-in phase = -2 pi k.u)
-            out["corrected"] = solvers.undistort(f32.double(), -u)
+            # the extracted field is minus the physical displacement (lock-in phase = -2 pi k.u); the ORIGINAL float64
+            # frame is resampled, as undistort_image(frame, -u) does (zeros outside the frame, geometric_phase_analysis.py:973)
+            out["corrected"] = solvers.undistort(solvers.to_device_f64(arr, self.device), -u)
         return out
 
 

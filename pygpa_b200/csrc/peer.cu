@@ -191,6 +191,25 @@ extern "C" int gpa_peer_wait(const unsigned long long* flags, int n_sources, uns
     return GPA_OK;
 }
 
+extern "C" int gpa_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    GPA_REQUIRE(dst && src, "null pointer argument");
+    if (bytes == 0) return GPA_OK;
+    GPA_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return GPA_OK;
+}
+
+extern "C" int gpa_host_register(void* host_ptr, size_t bytes) {
+    GPA_REQUIRE(host_ptr && bytes > 0, "bad argument");
+    GPA_CHECK_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return GPA_OK;
+}
+
+extern "C" int gpa_host_unregister(void* host_ptr) {
+    GPA_REQUIRE(host_ptr, "bad argument");
+    GPA_CHECK_CUDA(cudaHostUnregister(host_ptr));
+    return GPA_OK;
+}
+
 extern "C" int gpa_key_merge(void* const* key_ptrs, int world, int rank, size_t n_keys, void* stream) {
     GPA_REQUIRE(key_ptrs && world >= 1 && world <= GPA_MAX_PEERS && rank >= 0 && rank < world, "bad argument");
     if (n_keys == 0 || world == 1) return GPA_OK;

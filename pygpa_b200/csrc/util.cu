@@ -70,3 +70,74 @@ extern "C" int gpa_key_to_kidx(const unsigned long long* key, int* kidx, size_t 
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FP32 pipe peak, measured: the denominator of the K1 roofline (MEASURED_PEAKS.json has no fp32 figure).
+// Pure register FFMA2 (fma.rn.f32x2, the instruction the sweep kernels issue), 16 independent accumulators
+// per thread, 4 CTAs of 256 threads per SM, no memory traffic in the loop.
+// ---------------------------------------------------------------------------------------------
+namespace gpa {
+__global__ void __launch_bounds__(256) k_ffma_peak(float2* __restrict__ out, const float2* __restrict__ in, int iters) {
+    float2 acc[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        acc[i] = in[threadIdx.x + i * 256];
+        b[i] = in[threadIdx.x + (i + 16) * 256];
+    }
+    for (int it = 0; it < iters; ++it) {
+        const float2 g = make_float2(b[0].x + (float)it, b[0].y + (float)it);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __ffma2_rn(g, b[(i + r) & 15], acc[i]);
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        s.x += acc[i].x;
+        s.y += acc[i].y;
+    }
+    out[(size_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
+}  // namespace gpa
+
+extern "C" int gpa_fp32_peak_tflops(void* ws, size_t ws_bytes, double* tflops, void* stream) {
+    GPA_REQUIRE(ws && tflops, "null pointer argument");
+    int dev = 0, sms = 0;
+    GPA_CHECK_CUDA(cudaGetDevice(&dev));
+    GPA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 4, iters = 8192;
+    const size_t need = (size_t)(32 * 256 + grid * 256) * sizeof(float2);
+    if (ws_bytes < need) {
+        gpa::set_error("workspace too small (%zu bytes, need %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float2* in = static_cast<float2*>(ws);
+    float2* out = in + 32 * 256;
+    GPA_CHECK_CUDA(cudaMemsetAsync(in, 0, 32 * 256 * sizeof(float2), st));
+    cudaEvent_t e0, e1;
+    GPA_CHECK_CUDA(cudaEventCreate(&e0));
+    GPA_CHECK_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {       // the first repetition warms up
+        cudaEventRecord(e0, st);
+        gpa::k_ffma_peak<<<grid, 256, 0, st>>>(out, in, iters);
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            gpa::set_error("gpa_fp32_peak_tflops: %s", cudaGetErrorString(e));
+            return GPA_ERR_CUDA;
+        }
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // per thread and iteration: 4 x 16 FFMA2 = 64 x 2 lanes x 2 flop
+    *tflops = (double)grid * 256.0 * iters * 64.0 * 4.0 / ((double)best * 1e-3) / 1e12;
+    return GPA_OK;
+}

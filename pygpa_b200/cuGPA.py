@@ -20,7 +20,8 @@ import torch
 
 from . import engine
 
-__all__ = ["cuGPA", "wfr2_grad_opt", "wfr2_grad_single", "wfr2_only_lockin", "wfr2_only_grad"]
+__all__ = ["cuGPA", "wfr2_grad_opt", "wfr2_grad_single", "wfr2_only_lockin", "wfr2_only_grad",
+           "wfr2_grad_opt_peaks", "clear_plans"]
 
 
 def _grad_mode(grad):
@@ -42,20 +43,33 @@ def _to_host(t):
     return host
 
 
+# The reference is stateless.  The only state kept here is derived, never results: the
+# geometry of a call (candidate axes, tap tables, scratch sizing), which costs a few ms of host time to build.
+# The cache is a small LRU (8 entries; the scratch itself is one shared grow-only buffer per device, see
+# engine.workspace) and clear_plans() drops everything, scratch included.
+_PLAN_CACHE_SIZE = 8
 _plans = {}
+_host_sweeps = {}
+
+
+def clear_plans():
+    """Drop every cached plan, batched executor and the device scratch buffers."""
+    _plans.clear()
+    for hs in _host_sweeps.values():
+        hs.close()
+    _host_sweeps.clear()
+    engine.release_workspaces()
 
 
 def _plan_for(shape, sigma, kx, ky, kw, kstep, device):
-    """SweepPlan cache: the geometry (candidate axes, taps, scratch sizing) of a call depends only on
-    these arguments, and building it costs a few ms of host time (cudaMemGetInfo, tap tables)."""
     key = (tuple(shape), float(sigma), float(kx), float(ky), float(kw), float(kstep), str(device))
-    plan = _plans.get(key)
+    plan = _plans.pop(key, None)
     if plan is None:
-        if len(_plans) >= 64:
-            _plans.clear()
+        while len(_plans) >= _PLAN_CACHE_SIZE:
+            _plans.pop(next(iter(_plans)))          # least recently used
         wxs, wys = engine.grid_axes(kx, ky, kw, kstep)
         plan = engine.SweepPlan(shape, wxs, wys, sigma, engine.CAND_GRID, device=device)
-        _plans[key] = plan
+    _plans[key] = plan                              # most recently used last
     return plan
 
 
@@ -107,3 +121,34 @@ def wfr2_only_grad(image, sigma, kvec, kw, kstep, grad=None):
     """cuGPA.py:161-202: only the phase gradient (N, M, 2)."""
     kx, ky = kvec
     return _sweep(image, sigma, kx, ky, kw, kstep, _grad_mode(grad), want_w=False)['grad']
+
+
+def wfr2_grad_opt_peaks(image, sigma, kvecs, kw, kstep, grad=None, shape=None):
+    """wfr2_grad_opt for SEVERAL primary k-vectors of one frame in one call — the loop of
+    extract_displacement_field (geometric_phase_analysis.py:916-921) as a batch: returns
+    [wfr2_grad_opt(image, sigma, k[0], k[1], kw, kstep, grad) for k in kvecs] (same dicts, same dtypes), but the
+    image is uploaded once and the device-to-host copy of peak p's arrays overlaps the sweep of peak p+1.
+
+    With torch.distributed initialised (one process per GPU) the call is SPMD: every rank calls it, the k-grid is
+    sharded over the GPUs, every GPU copies its rows of the results out over its own PCIe link, and rank 0 gets the
+    arrays (the other ranks pass image=None and shape=<frame shape>, and get None).  The returned arrays are views of a page-locked buffer
+    owned by the cached executor: valid until the next call with the same geometry (copy them to keep them)."""
+    import torch.distributed as tdist
+    from . import dist as gdist
+    device = engine.require_cuda()
+    rank = tdist.get_rank() if tdist.is_initialized() else 0
+    kvecs = [tuple(map(float, k)) for k in kvecs]
+    if rank == 0:
+        shape = tuple(np.shape(image))
+    elif shape is None:
+        raise ValueError("ranks other than 0 must pass shape=(N, M)")
+    shape = tuple(int(v) for v in shape)
+    key = (shape, float(sigma), tuple(kvecs), float(kw), float(kstep), str(grad), str(device))
+    hs = _host_sweeps.get(key)
+    if hs is None:
+        for old in _host_sweeps.values():           # one batched executor at a time: it pins 48 B per pixel and peak
+            old.close()
+        _host_sweeps.clear()
+        hs = gdist.HostSweep(shape, sigma, kvecs, kw, kstep, grad=grad)
+        _host_sweeps[key] = hs
+    return hs(image if rank == 0 else None)

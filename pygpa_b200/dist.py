@@ -32,7 +32,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_units", "shard_units_interleaved", "merge_keys", "merge_payload", "pack_key", "unpack_key",
-           "sharded_sweep", "ShardedSweep"]
+           "sharded_sweep", "ShardedSweep", "HostSweep"]
 
 
 def _counts(n_peaks, n_planes):
@@ -165,6 +165,7 @@ class ShardedSweep:
         self.lib = _lib.load() if self.dev.type == "cuda" else None
         self.epoch = 0
         self.record = False          # True: bracket the phases of every peak with CUDA events (bench.py)
+        self.after_peak = None       # optional callable(p), run on peak p's stream once its rows are delivered
         self._events = None
         self._streams = _peak_streams(self.dev, self.n_peaks) if self.dev.type == "cuda" and all(p._private for p in self.plans) else None
         n, m, P = self.n, self.m, self.n_peaks
@@ -330,6 +331,8 @@ class ShardedSweep:
                                                 ctypes.c_void_p(self.w[p].data_ptr() + r0 * m * rb), engine._stream()))
                     engine._count(1)
             self._mark(p, "delivered")
+            if self.after_peak is not None:
+                self.after_peak(p)
         self._per_peak(peak)
         return self._outs()
 
@@ -386,6 +389,146 @@ class ShardedSweep:
                                             int(self.out_f64), engine._ptr(self.w[p]), engine._stream()))
                 o["w"] = self.w[p]
         return outs
+
+
+class HostSweep:
+    """cuGPA.wfr2_grad_opt for every peak of a frame on all GPUs of the box: NumPy image in on rank 0, the reference's
+    NumPy arrays out on rank 0 ('lockin' (N,M) c16, 'w' (2,N,M) f8, 'grad' (N,M,2) f8 per peak; cuGPA.py:41-87).
+    SPMD: every rank constructs it and calls it once per frame; only rank 0 passes the image and gets the results.
+
+    Data path per frame: rank 0 copies the frame to its GPU and casts it to float32 into its peer arena; the other
+    ranks pull it over NVLink.  The sweep runs k-grid sharded with dst='rows' (ShardedSweep), so rank r ends up with
+    rows [r N/W, (r+1) N/W) of every output array, already widened to float64 / complex128, and copies them over
+    ITS OWN PCIe link into one page-locked shared-memory segment that all ranks map — the device-to-host traffic of
+    the reference's result arrays (48 B per pixel and peak) is spread over W links, and each peak's copy overlaps the
+    arg-max of the next peak.  The arrays rank 0 returns are views of that segment, valid until the next call."""
+
+    def __init__(self, shape, sigma, kvecs, kw, kstep, group=None, grad=None, planes_in_flight=None):
+        from multiprocessing import shared_memory
+        from . import _lib, cuGPA, engine
+        from .peer import PeerArena
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = engine.require_cuda()
+        self.lib = _lib.load()
+        self.n, self.m = int(shape[0]), int(shape[1])
+        self.kvecs = [tuple(map(float, k)) for k in kvecs]
+        self.grad_mode = cuGPA._grad_mode(grad)
+        P, n, m = len(self.kvecs), self.n, self.m
+        plans = []
+        for k in self.kvecs:
+            wxs, wys = engine.grid_axes(k[0], k[1], kw, kstep)
+            plans.append(engine.SweepPlan((n, m), wxs, wys, sigma, device=self.dev, private_ws=True,
+                                          planes_in_flight=planes_in_flight))
+        self.sweep = ShardedSweep(plans, self.kvecs, group=group, dst="rows", out_f64=True, want_w=True, transport="peer")
+        self.sweep.after_peak = self._copy_out
+        self.img_arena = PeerArena(_FLAG_BYTES + n * m * 4, group=group, device=self.dev)
+        self.img = self.img_arena.tensor(_FLAG_BYTES, (n, m), torch.float32)
+        self._stage = torch.empty((n, m), dtype=torch.float64, device=self.dev) if self.rank == 0 else None
+        # shared, page-locked result segment: [host flags 4096 B | lockin P c16 | w P 2 f8 | grad P .. 2 f8]
+        self._seg_bytes = 4096 + P * n * m * 48
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=self._seg_bytes)
+            name[0] = self._shm.name
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:        # the creator unlinks; attaching processes must not (Python < 3.13 registers them with the tracker)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        buf = np.frombuffer(self._shm.buf, dtype=np.uint8, count=self._seg_bytes)
+        self._buf_addr = buf.ctypes.data
+        _lib.check(self.lib.gpa_host_register(ctypes.c_void_p(self._buf_addr), self._seg_bytes))
+        self._hflags = np.frombuffer(self._shm.buf, dtype=np.int64, count=64)
+        if self.rank == 0:
+            self._hflags[:] = 0
+        off = 4096
+        self._h_lock = np.frombuffer(self._shm.buf, dtype=np.complex128, count=P * n * m, offset=off).reshape(P, n, m)
+        off += P * n * m * 16
+        self._h_w = np.frombuffer(self._shm.buf, dtype=np.float64, count=P * 2 * n * m, offset=off).reshape(P, 2, n, m)
+        off += P * n * m * 16
+        self._h_grad = np.frombuffer(self._shm.buf, dtype=np.float64, count=P * n * m * 2, offset=off).reshape(P, n, m, 2)
+        self.calls = 0
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def _host_ptr(self, arr, *index):
+        view = arr[index]
+        return ctypes.c_void_p(view.ctypes.data)
+
+    def _copy_out(self, p):
+        """Rows of peak p that live on this rank -> the shared host segment (on peak p's stream)."""
+        from . import _lib, engine
+        r0, r1 = self.sweep.rows
+        if r1 <= r0:
+            return
+        sw, m, st = self.sweep, self.m, engine._stream()
+        rows = r1 - r0
+        _lib.check(self.lib.gpa_peer_copy(self._host_ptr(self._h_lock, p, r0), engine._ptr(sw.lockin[p, r0:r1]), rows * m * 16, st))
+        if self.grad_mode != 2:
+            _lib.check(self.lib.gpa_peer_copy(self._host_ptr(self._h_grad, p, r0), engine._ptr(sw.grad[p, r0:r1]), rows * m * 16, st))
+        for c in range(2):
+            _lib.check(self.lib.gpa_peer_copy(self._host_ptr(self._h_w, p, c, r0), engine._ptr(sw.w[p, c, r0:r1]), rows * m * 8, st))
+
+    def __call__(self, image=None):
+        from . import _lib, engine
+        self.calls += 1
+        ep, world, rank = self.calls, self.world, self.rank
+        st = engine._stream()
+        if rank == 0:
+            arr = np.ascontiguousarray(image, dtype=np.float64)
+            if arr.shape != (self.n, self.m):
+                raise ValueError(f"image must have shape {(self.n, self.m)}")
+            self._hflags[8] = ep                       # go: the workers may enqueue this frame
+            self._stage.copy_(torch.from_numpy(arr), non_blocking=True)
+            _lib.check(self.lib.gpa_cast_f64_to_f32(engine._ptr(self._stage), engine._ptr(self.img), arr.size, st))
+            if world > 1:
+                slots = (ctypes.c_void_p * world)(*[self.img_arena.addr(r, 0) for r in range(world)])
+                _lib.check(self.lib.gpa_peer_signal(slots, world, ep, st))
+        else:
+            while self._hflags[8] < ep:                # host-side: no device spin while rank 0's caller is busy elsewhere
+                pass
+            _lib.check(self.lib.gpa_peer_wait(ctypes.c_void_p(self.img_arena.addr(rank, 0)), 1, ep, self.sweep.timeout_s,
+                                              engine._ptr(self.sweep._status), st))
+            _lib.check(self.lib.gpa_peer_copy(engine._ptr(self.img), ctypes.c_void_p(self.img_arena.addr(0, _FLAG_BYTES)),
+                                              self.n * self.m * 4, st))
+        self.sweep(self.img, self.grad_mode)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self._hflags[16 + rank] = ep                   # this rank's rows are in the segment
+        if rank != 0:
+            return None
+        for r in range(1, world):
+            while self._hflags[16 + r] < ep:
+                pass
+        self.sweep.check()
+        return [{"lockin": self._h_lock[p], "w": self._h_w[p], "grad": self._h_grad[p]} if self.grad_mode != 2 else
+                {"lockin": self._h_lock[p], "w": self._h_w[p]} for p in range(len(self.kvecs))]
+
+    @property
+    def d2h_bytes_per_rank(self):
+        r0, r1 = self.sweep.rows
+        return (r1 - r0) * self.m * 48 * len(self.kvecs)
+
+    def close(self):
+        if getattr(self, "_shm", None) is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        self.sweep.close()
+        self.img_arena.close()
+        self.lib.gpa_host_unregister(ctypes.c_void_p(self._buf_addr))
+        self._hflags = self._h_lock = self._h_w = self._h_grad = None
+        try:
+            self._shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            self._shm.unlink()
+        self._shm = None
 
 
 _sweeps = {}

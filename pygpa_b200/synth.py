@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["primary_ks", "gaussian_bump", "smooth_random_field", "lattice_image",
-           "sweep_params", "make_config"]
+           "sweep_params", "make_config", "make_config_device", "frame_series_device"]
 
 
 def primary_ks(r_k, xi0_deg=0.0, n=3):
@@ -103,3 +103,100 @@ def make_config(name, size=None, n_grid=None):
     img = img - img.mean()
     kw, kstep = sweep_params(ks, ng)
     return dict(image=img, ks=ks, sigma=10, kw=kw, kstep=kstep, n_grid=ng, u=u, name=name)
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side generators for the large benchmark inputs (BASELINE configs 4 and 5): the same formulas
+# evaluated with torch on the GPU, because an 8192 x 8192 frame takes ~40 s of NumPy on the host.
+# Synthetic-input plumbing only; nothing here is on the measured path.
+# ----------------------------------------------------------------------------------------------
+def _smooth_field_device(shape, max_grad, seed, device, modes=8):
+    import torch
+    rng = np.random.default_rng(seed)
+    n, m = shape
+    x = torch.arange(n, dtype=torch.float64, device=device)[:, None] / n
+    y = torch.arange(m, dtype=torch.float64, device=device)[None, :] / m
+    u = torch.zeros((2, n, m), dtype=torch.float64, device=device)
+    for c in range(2):
+        for _ in range(modes):
+            fx, fy = rng.integers(0, 3, size=2)
+            if fx == 0 and fy == 0:
+                fx = 1
+            amp = rng.normal()
+            ph = rng.uniform(0, 2 * np.pi)
+            u[c] += amp * torch.sin(2 * np.pi * (int(fx) * x + int(fy) * y) + ph)
+    g = max(float(torch.diff(u, dim=1).abs().max()), float(torch.diff(u, dim=2).abs().max()))
+    return u * (max_grad / g)
+
+
+def _lattice_device(shape, ks, u, noise, seed, device):
+    import torch
+    n, m = shape
+    x = torch.arange(n, dtype=torch.float64, device=device)[:, None] + u[0]
+    y = torch.arange(m, dtype=torch.float64, device=device)[None, :] + u[1]
+    img = torch.zeros((n, m), dtype=torch.float64, device=device)
+    for k in np.asarray(ks, dtype=np.float64):
+        img += torch.cos(2 * np.pi * (float(k[0]) * x + float(k[1]) * y))
+    if noise:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(seed))
+        img += noise * torch.randn((n, m), dtype=torch.float64, device=device, generator=gen)
+    return img
+
+
+def make_config_device(name, device, size=None, n_grid=None):
+    """C5: stitched 8192 x 8192 mosaic — a C3-type smooth twist-gradient field plus a
+    constant extra rotation per tile of a 4 x 4 mosaic, blended over 128 px — generated on `device`.
+    'C2' / 'C3' give the same kind of frame as make_config (not the same random numbers).  Returns dict with
+    image (float64 CUDA tensor, zero mean), ks, sigma, kw, kstep, n_grid."""
+    import torch
+    table = {"C2": (1024, 0.15, 21, 1, 2, 0), "C3": (2048, 0.30, 41, 3, 4, 0), "C5": (8192, 0.30, 41, 5, 6, 4)}
+    n, max_grad, ng, su, sn, tiles = table[name]
+    n = size or n
+    ng = n_grid or ng
+    ks = primary_ks(0.05, 7.0, 3)
+    u = _smooth_field_device((n, n), max_grad, su, device)
+    if tiles:
+        rng = np.random.default_rng(su + 100)
+        theta = rng.normal(scale=0.01, size=(tiles, tiles))            # extra twist per tile, radians
+        t = n // tiles
+        pos = torch.arange(n, dtype=torch.float64, device=device)
+        idx = torch.clamp((pos / t).floor().long(), max=tiles - 1)
+        # smooth-step blend of the per-tile twist over 128 px around every tile boundary
+        frac = (pos - idx * t) / t
+        edge = 64.0 / t
+        wgt = torch.clamp((frac - (1 - edge)) / (2 * edge), 0, 1)       # 0 inside the tile, -> 0.5 at the boundary
+        wgt = wgt * wgt * (3 - 2 * wgt)
+        nxt = torch.clamp(idx + 1, max=tiles - 1)
+        th = torch.from_numpy(theta).to(device)
+        tw = (th[idx][:, idx] * (1 - wgt)[:, None] * (1 - wgt)[None, :] + th[nxt][:, idx] * wgt[:, None] * (1 - wgt)[None, :]
+              + th[idx][:, nxt] * (1 - wgt)[:, None] * wgt[None, :] + th[nxt][:, nxt] * wgt[:, None] * wgt[None, :])
+        cx = (pos - (idx.double() + 0.5) * t)
+        u = u.clone()
+        u[0] += -tw * cx[None, :]
+        u[1] += tw * cx[:, None]
+    img = _lattice_device((n, n), ks, u, 0.3, sn, device)
+    img -= img.mean()
+    kw, kstep = sweep_params(ks, ng)
+    return dict(image=img, ks=ks, sigma=10, kw=kw, kstep=kstep, n_grid=ng, name=name)
+
+
+def frame_series_device(n_frames, device, size=1024, t0=0, total=512):
+    """C4: frames t0 .. t0 + n_frames - 1 of a `total`-frame LEEM-like series on `device`:
+    the C2 lattice with u_t = u (1 + 0.2 sin(2 pi t / total)) + drift(t), a Gaussian illumination envelope, noise
+    seeded per frame, quantised to 16 bit.  Returns (frames (n_frames, size, size) float64 CUDA tensor, ks)."""
+    import torch
+    ks = primary_ks(0.05, 7.0, 3)
+    u = _smooth_field_device((size, size), 0.15, 1, device)
+    ax = (torch.arange(size, dtype=torch.float64, device=device) - size / 2) / size
+    env = torch.exp(-(ax[:, None] ** 2 + ax[None, :] ** 2) / 0.5)
+    frames = torch.empty((n_frames, size, size), dtype=torch.float64, device=device)
+    for i in range(n_frames):
+        t = t0 + i
+        ut = u * (1 + 0.2 * np.sin(2 * np.pi * t / total))
+        ut[0] += 2.0 * t / total
+        ut[1] -= 1.0 * t / total
+        f = (3.0 + _lattice_device((size, size), ks, ut, 0.3, 1000 + t, device)) * env
+        f = torch.clamp(f / 8.0, 0, 1)
+        frames[i] = torch.round(f * 65535.0)
+    return frames, ks

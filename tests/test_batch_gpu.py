@@ -29,6 +29,23 @@ def test_frame_series_matches_single_frame_api_and_oracle():
         u_api = GPA.extract_displacement_field(frame, ks)
         assert np.abs(res[t]["u"] - u_api).max() < 1e-9
         assert res[t]["corrected"].shape == shape
-        assert np.abs(res[t]["corrected"] - GPA.undistort_image(frame - frame.mean(), -u_api)).max() < 1e-5
-    u_ref = oracle.extract_displacement_field(frames[1], ks)
-    assert np.percentile(np.abs(res[1]["u"] - u_ref), 99.9) < DISP_TOL
+        # the ORIGINAL float64 frame is resampled, exactly as undistort_image(frame, -u) does
+        assert np.abs(res[t]["corrected"] - GPA.undistort_image(frame, -u_api)).max() < 1e-9
+
+    # against the oracle: EVERY pixel within 1e-3 px, except around pixels where the sweep legitimately picked another
+    # candidate (near-tie, oracle top-2 gap < 1e-5): those carry a different lock-in phase, visible in u at that pixel
+    import scipy.ndimage as ndi
+
+    def sweep(im, s_, kx, ky, kw, kstep):
+        return oracle.wfr_sweep(im, s_, kx, ky, kw, kstep, want_grad=False, return_diag=True)
+    u_ref, gs_ref = oracle.extract_displacement_field(frames[1], ks, return_gs=True, sweep=sweep)
+    _u, gs = GPA.extract_displacement_field(frames[1], ks, return_gs=True)
+    flips = np.zeros(shape, dtype=bool)
+    for g_, r_ in zip(gs, gs_ref):
+        differs = ~np.all(g_['w'] == r_['w'], axis=0)
+        gap = (r_['amp1'] - r_['amp2']) / r_['amp1']
+        assert np.all(gap[differs] < 1e-5)
+        flips |= differs
+    assert flips.mean() < 1e-3
+    near = ndi.binary_dilation(flips, iterations=2)
+    assert np.abs(res[1]["u"] - u_ref).max(axis=0)[~near].max() < DISP_TOL
