@@ -242,11 +242,15 @@ def run_ours(args, cfg):
         plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=world > 1))
     taps = 2 * plans[0].rx + 1
     transport = os.environ.get("GPA_TRANSPORT", "auto")
-    sweep = gdist.ShardedSweep(plans, ks, dst=0, transport=transport) if world > 1 else None
+    sweep = gdist.ShardedSweep(plans, ks, dst=0, transport=transport, gossip=os.environ.get("GPA_GOSSIP", "1") != "0") if world > 1 else None
+    # N > 1, frame stream: the caller's stream does not join the per-peak streams between frames (exactly like the single
+    # stream of N = 1, nothing synchronises between the K steps), so the exchange tail of frame t overlaps frame t + 1;
+    # multi_gpu.frame_latency_ms is the time of ONE isolated frame
+    pipelined = sweep is not None and sweep.transport == "peer" and os.environ.get("GPA_PIPELINE", "1") != "0"
 
     def step():
         if sweep is not None:
-            return sweep(img)
+            return sweep(img, join=not pipelined)
         return [plan.run(img, k) for plan, k in zip(plans, ks)]
 
     # measured FP32 peak (register-only FFMA2 loop) before anything else warms the chip differently
@@ -262,6 +266,8 @@ def run_ours(args, cfg):
         sampler.start()
     for _ in range(args.warmup):
         step()
+    if pipelined:
+        sweep.join()
     barrier()
     lib.gpa_profile_enable(1)
     launches0 = engine.launch_count
@@ -271,6 +277,8 @@ def run_ours(args, cfg):
     e0.record()
     for _ in range(args.steps):
         step()
+    if pipelined:
+        sweep.join()
     e1.record()
     barrier()
     lib.gpa_profile_enable(0)
@@ -313,6 +321,18 @@ def run_ours(args, cfg):
     # ---- N > 1: where the time goes, and is the result the single-GPU one? -------------------------------------
     multi = None
     if sweep is not None:
+        lat = []
+        for _ in range(5):           # isolated frames: barrier, one frame, join
+            barrier()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            sweep(img)
+            l1.record()
+            torch.cuda.synchronize()
+            lat.append(l0.elapsed_time(l1))
+        lat_t = torch.tensor([sorted(lat)[len(lat) // 2]], device=dev)
+        dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
+        frame_latency_ms = float(lat_t.item())
         sweep.record = True
         outs = sweep(img)
         phases = sweep.timings() if sweep.transport == "peer" else []
@@ -359,12 +379,16 @@ def run_ours(args, cfg):
                     "step_end_ms_per_rank": [max(r[p]["total_ms"] for p in range(len(ks))) for r in every],
                     "what": "time from the start of the step to the end of the rank's last arg-max kernel (the peaks' streams overlap); "
                             "step_end = its last delivery wait"},
+                "frame_latency_ms": frame_latency_ms,
+                "pipelined_frames": bool(pipelined),
+                "threshold_gossip": bool(sweep.gossip),
                 "exposed_tail_ms": max(max(r[p]["total_ms"] for p in range(len(ks))) - max(r[p]["argmax_ms"] for p in range(len(ks))) for r in every),
                 "k_key_merge_ms_per_step_rank0": kernels["k_key_merge"][0] / args.steps,
                 "check": check,
             }
         elif rank == 0:
-            multi = {"transport": "torch.distributed collectives (MAX all-reduce of the keys + SUM reduce of the payload)", "check": check}
+            multi = {"transport": "torch.distributed collectives (MAX all-reduce of the keys + SUM reduce of the payload)", "check": check,
+                     "frame_latency_ms": frame_latency_ms}
 
     # ---- end to end through the public host API ------------------------------------------------------------------
     n_e2e = max(3, min(args.steps, 5))

@@ -440,6 +440,14 @@ int gpa_key_merge(void* const* key_ptrs /*host*/, int world, int rank, size_t n_
  * won): the 'w' output of wfr2_grad_opt from merged keys. */
 int gpa_key_to_w(const unsigned long long* key, size_t n, size_t comp_stride, const double* wx_dev,
                  const double* wy_dev, int n_planes, int list_mode, int out_f64, void* w, void* stream);
+/* Threshold gossip for the exact pruning of a sharded sweep.  A rank only sweeps its own planes, so the winners it has
+ * recorded are weaker pruning thresholds than a single GPU would have.  hint_ptrs: host array of n_ranks device arrays
+ * of (N / B) x (M / B) uint64 (B = 8 * stride pixels per bound block), entry 0 this rank's own, the rest the peers'
+ * (peer-mapped), zero-initialised once.  The NEXT gpa_sweep_argmax_mr call on this thread then (a) raises its per-block
+ * thresholds to the bounds found there for `epoch` and (b) pushes every bound it improves to all n_ranks arrays
+ * (64-bit max over NVLink, tagged with the epoch: stale frames never match, nothing is ever reset).  Any published
+ * value is a lower bound of the block's final winners, so results stay bit-identical to the unpruned sweep. */
+int gpa_sweep_arm_gossip(void* const* hint_ptrs /*host*/, int n_ranks, unsigned int epoch);
 /* gpa_sweep_finalize_mr for one rank's share of the planes with owner-writes: pixel (x, y) of a winner
  * this rank owns is stored to lockin_dst[x / dst_rows] and grad_dst[x / dst_rows] (host arrays of n_dst
  * device pointers to full (N, M) / (N, M, 2) arrays, local or peer-mapped; all pixels go to entry 0 when

@@ -169,6 +169,14 @@ static int check_common(const float* img, const double* wx_rows, const double* w
 // ---------------------------------------------------------------------------------------------
 static int g_prune_enabled = 1;
 
+// threshold gossip of a k-grid sharded sweep: armed by gpa_sweep_arm_gossip, consumed by the next gpa_sweep_argmax_mr
+struct GossipArm {
+    unsigned long long* hint[GPA_MAX_PEERS];
+    int n = 0;
+    unsigned epoch = 0;
+};
+static thread_local GossipArm g_gossip;
+
 struct MrGeometry {
     int N, M, S, Nd, Md, pitch_d, n_rows, n_planes, Rax, Ray, Rb, Jx, Jy, txd, warps2, n_alloc, n_rows_filled, n_cand;
     int nbx_alloc, nby_alloc, can_prune;
@@ -307,6 +315,9 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         const int tiles = ceil_div(g.n_rows_filled, 32) * ceil_div(g.pitch_d, W1 * kP);
         int ppc = 1;
         while (ppc < 8 && (long long)tiles * ceil_div(count, ppc * 2) >= 4 * 296) ppc *= 2;
+        // a small share of the planes (k-grid sharded over GPUs): one CTA per tile takes all of them, so the image tile
+        // fill (about as expensive as one plane's filter) is paid once instead of once per plane
+        if (count <= 8 && tiles >= 200) ppc = count;
         p.count = count; p.planes_per_cta = ppc;
         dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, W1 * kP), ceil_div(count, ppc));
         KernelTimer timer("k_mr_pass1", st);
@@ -360,7 +371,14 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.nbx = g.nbx_alloc; p.nby = g.nby_alloc;
         const int JB = 2 * g.H + 1;
         const size_t smem = (size_t)(2 * (kWarps * kP + JB - 1) * kLanes + 2 * (kWarps * kP + JB - 1) + 2 * kWarps * kP) * sizeof(float2);
-        dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, kWarps * kP), count);
+        // few planes (a rank's share of a sharded sweep): split the candidates of a (tile, plane) over several CTAs so that
+        // the grid is >= ~4 waves of the 2 x 148 CTA slots instead of e.g. 320 CTAs = 1.08 waves running as 2
+        const int tiles2b = (g.pitch_d / kLanes) * ceil_div(g.Nd, kWarps * kP);
+        int c_split = ceil_div(4 * 296, tiles2b * count);
+        if (c_split > g.n_cand / 8) c_split = g.n_cand / 8;      // keep >= 8 candidates per staged tile
+        if (c_split < 1) c_split = 1;
+        p.c_split = c_split;
+        dim3 grid(g.pitch_d / kLanes, ceil_div(g.Nd, kWarps * kP), count * c_split);
         KernelTimer timer("k_mr_pass2b", st);
 #define GPA_P2B(JBV)                                                                                                    \
     case JBV:                                                                                                           \
@@ -381,6 +399,9 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.nbx = g.Nd / kPmB; p.nby = g.Md / kPmB; p.nbx_alloc = g.nbx_alloc; p.nby_alloc = g.nby_alloc; p.count = count;
         p.prune = g.can_prune && g_prune_enabled;
         p.perm = g.perm;
+        p.n_hint = p.prune ? g_gossip.n : 0;
+        p.epoch = g_gossip.epoch;
+        for (int r = 0; r < GPA_MAX_PEERS; ++r) p.hint[r] = r < g_gossip.n ? g_gossip.hint[r] : nullptr;
         if (p.prune) {
             dim3 tg(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX));
             KernelTimer timer("k_mr_order", st);
@@ -406,6 +427,17 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
 }  // namespace gpa
 
 using namespace gpa;
+
+extern "C" int gpa_sweep_arm_gossip(void* const* hint_ptrs, int n_ranks, unsigned int epoch) {
+    GPA_REQUIRE(n_ranks >= 0 && n_ranks <= GPA_MAX_PEERS && (n_ranks == 0 || hint_ptrs), "bad argument");
+    for (int r = 0; r < n_ranks; ++r) {
+        GPA_REQUIRE(hint_ptrs[r] != nullptr, "null hint array");
+        g_gossip.hint[r] = static_cast<unsigned long long*>(hint_ptrs[r]);
+    }
+    g_gossip.n = n_ranks;
+    g_gossip.epoch = epoch;
+    return GPA_OK;
+}
 
 extern "C" int gpa_set_pruning(int on) {
     g_prune_enabled = on != 0;
@@ -478,9 +510,10 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
         if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
         else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
         else rc = launch_mr<8>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
-        if (rc) return rc;
+        if (rc) break;
     }
-    return GPA_OK;
+    g_gossip.n = 0;      // one call per arming
+    return rc;
 }
 
 static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes, int n_planes, int cand_mode,
@@ -536,13 +569,20 @@ static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const do
     mp.p2 = g.p2; mp.Nd = g.Nd; mp.Md = g.Md; mp.n_cand = g.n_cand; mp.S = S; mp.pstep = plane_step;
     KernelTimer timer("k_mr_finalize", st);
     if (n_dst > 0) {   // a rank's share of the planes: CTA-level compaction of the owned pixels, owner-writes
-        dim3 grid(ceil_div(M, 64), ceil_div(N, 16));
-#define GPA_MRFINS(SS)                                                                       \
-        do {                                                                                     \
-            if (out_f64) k_mr_finalize_sharded<SS, double2><<<grid, 256, 0, st>>>(mp, tb);       \
-            else k_mr_finalize_sharded<SS, float2><<<grid, 256, 0, st>>>(mp, tb);                \
+        // tile rows per CTA: ~256 owned pixels per 256-thread CTA (a rank owns about total / n_planes of the pixels)
+        const bool small_share = !nothing && (long long)total * 6 <= n_planes;
+        const int fx = small_share ? 32 : 16;
+        dim3 grid(ceil_div(M, 64), ceil_div(N, fx));
+#define GPA_MRFINS2(SS, TT)                                                                       \
+        do {                                                                                          \
+            if (fx == 32) k_mr_finalize_sharded<SS, TT, 32><<<grid, 256, 0, st>>>(mp, tb);            \
+            else k_mr_finalize_sharded<SS, TT, 16><<<grid, 256, 0, st>>>(mp, tb);                     \
         } while (0)
-        if (S == 2) GPA_MRFINS(2); else if (S == 4) GPA_MRFINS(4); else GPA_MRFINS(8);
+#define GPA_MRFINS(SS)                          \
+        if (out_f64) GPA_MRFINS2(SS, double2);      \
+        else GPA_MRFINS2(SS, float2)
+        if (S == 2) { GPA_MRFINS(2); } else if (S == 4) { GPA_MRFINS(4); } else { GPA_MRFINS(8); }
+#undef GPA_MRFINS2
 #undef GPA_MRFINS
         GPA_CHECK_CUDA(cudaGetLastError());
         return GPA_OK;

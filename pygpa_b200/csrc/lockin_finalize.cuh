@@ -344,18 +344,18 @@ k_mr_finalize(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) 
 
 
 // Sharded twin of k_mr_finalize (k-grid split over GPUs): a rank owns only the pixels whose winner lies in its
-// planes — 1/W of the frame, finely interleaved.  The CTA compacts the owned pixels of a 16 x 64 tile into a
+// planes — 1/W of the frame, finely interleaved.  The CTA compacts the owned pixels of an FX x 64 tile (FX = 16, or 32 for shares below 1/6) into a
 // shared list (ballot + one shared atomic per warp) and all 256 threads then work through the list, so the
 // time scales with the rank's share; the tile is compact in both axes, which keeps the 12 x 12 coarse windows
 // of its pixels in L1.  x varies per lane here, so the interpolation taps come from shared memory.  The same
 // sequence of FMAs per pixel as k_mr_finalize: bit-identical results.  Stores go to the destination arrays
 // of the pixel (FinalizeParams::lockin_dst / grad_dst, possibly peer memory).
-template <int S, typename T2>
+template <int S, typename T2, int FX>
 __global__ void __launch_bounds__(256)
 k_mr_finalize_sharded(const MrFinalizeParams mp, const __grid_constant__ TapTable taps) {
     const FinalizeParams& prm = mp.f;
     using R = typename real_of<T2>::type;
-    constexpr int FX = 16, FY = 64;
+    constexpr int FY = 64;
     __shared__ unsigned short s_list[FX * FY];
     __shared__ int s_cnt;
     __shared__ float s_tap[2 * S * kMrW];

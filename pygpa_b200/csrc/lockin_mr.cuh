@@ -347,6 +347,7 @@ struct MrPass2bParams {
     float2* p2;             // [chunk][n_cand][Nd][Md]
     float* pmax;            // [chunk][n_cand][nbx][nby]
     int Nd, Md, NdE, H, EB /* coarse rows next to the frame edge that A_edge reaches */, n_cand, nbx, nby;
+    int c_split;            // CTAs per (tile, plane): each takes a contiguous share of the candidates (small plane counts: fills the SMs)
 };
 
 // CTA: kWarps * kP coarse output rows x 32 coarse columns (lane = column) of one plane; the A tile is
@@ -367,7 +368,9 @@ k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int my0 = blockIdx.x * kLanes;
     const int mx0 = blockIdx.y * TO;
-    const int pl = blockIdx.z;
+    const int pl = blockIdx.z / prm.c_split;
+    const int part = blockIdx.z % prm.c_split;
+    const int c_begin = (prm.n_cand * part) / prm.c_split, c_end = (prm.n_cand * (part + 1)) / prm.c_split;
     const int Nd = prm.Nd, Md = prm.Md, NdE = prm.NdE;
     const float2 zero = make_float2(0.f, 0.f);
     const int lo_end = prm.H + prm.EB, hi_begin = Nd + prm.H - prm.EB;     // A_edge is zero on rows [lo_end, hi_begin)
@@ -401,7 +404,7 @@ k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
         }
         cp_async_commit();
     };
-    stage(0, 0);
+    if (c_begin < c_end) stage(c_begin, 0);
     cp_async_wait_all();
     __syncthreads();
     const int e0 = mx0 + warp * kP;                          // first A row of this warp
@@ -413,9 +416,9 @@ k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
     float2 g[JB];
 #pragma unroll
     for (int j = 0; j < JB; ++j) g[j] = taps.g[j];
-    for (int c = 0; c < prm.n_cand; ++c) {
-        const int slot = c & 1;
-        if (c + 1 < prm.n_cand) stage(c + 1, slot ^ 1);
+    for (int c = c_begin; c < c_end; ++c) {
+        const int slot = (c - c_begin) & 1;
+        if (c + 1 < c_end) stage(c + 1, slot ^ 1);
         const float2* car = scar + slot * TR + warp * kP;
         float2 acc[kP];
 #pragma unroll
@@ -506,7 +509,22 @@ struct MrInterpParams {
     const unsigned short* perm;   // [tiles][count] plane order per tile (k_mr_order); used when prune != 0
     unsigned long long* key;
     int N, M, Nd, Md, plane0, pstep, n_cand, idx_c, idx_p, nbx, nby, nbx_alloc, nby_alloc, count, prune;   // nbx, nby: logical (wrap) block grid
+    // Threshold gossip between the ranks of a k-grid sharded sweep (n_hint > 0): hint[r][block] = (epoch << 32) | float bits of
+    // a LOWER bound of the final winner's |sf|^2 over the pixels of a bound block, as found by any rank so far.
+    // hint[0] is this rank's array (read here), hint[1..] are the peers' (peer-mapped; every improvement is pushed to all).
+    unsigned long long* hint[GPA_MAX_PEERS];
+    int n_hint;
+    unsigned epoch;
 };
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_max_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor list can hold
 
@@ -622,6 +640,19 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             if (lane % SPAN == 0) atomicMin(&s_blk[i][col / BPX], __float_as_int(tmin[i]));
         }
         __syncthreads();
+        if (prm.n_hint > 0) {
+            // another rank may already know a better lower bound of the final winners of these blocks (it owns planes
+            // closer to the local optimum): any such bound is valid for every pixel of the block, so the pruning stays exact
+            if (threadIdx.x < SBX * SBY) {
+                const int i = threadIdx.x / SBY, j = threadIdx.x % SBY;
+                const int gbx = x0 / BPX + i, gby = y0 / BPX + j;
+                if (gbx < prm.nbx && gby < prm.nby) {
+                    const unsigned long long h = ld_relaxed_sys_u64(prm.hint[0] + (size_t)gbx * prm.nby + gby);
+                    if ((unsigned)(h >> 32) == prm.epoch) s_blk[i][j] = max(s_blk[i][j], (int)(unsigned)(h & 0xffffffffull));
+                }
+            }
+            __syncthreads();
+        }
         if (warp == 0) {
             float thr[SBX][SBY];
 #pragma unroll
@@ -805,6 +836,42 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
                 const unsigned long long k =
                     ((unsigned long long)__float_as_uint(best[h][p]) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
                 atomicMax(prm.key + (size_t)x * prm.M + y, k);
+            }
+        }
+    }
+    if (prune && prm.n_hint > 0) {
+        // Publish what this CTA learned: min over a bound block of max(old winner, this plane's best) >= max(old block
+        // minimum, block minimum of this plane's best) is a lower bound of the final winners of the block.
+        constexpr int BPX = kPmB * S;
+        __shared__ int s_new[SBX][SBY];
+        __syncthreads();                    // every warp is past its last use of s_blk / s_mask
+        if (threadIdx.x < SBX * SBY) s_new[threadIdx.x / SBY][threadIdx.x % SBY] = 0x7f7fffff;
+        __syncthreads();
+        constexpr int SPANX = BPX < 32 ? BPX : 32;       // lanes (rows) of a warp inside one bound-block row
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int x = x0 + lane + 32 * h;
+            float mn = 3.4028234e38f;
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int y = y0 + wcol[h] * kP + p;
+                if (x < prm.N && y < prm.M) mn = fminf(mn, best[h][p]);
+            }
+#pragma unroll
+            for (int o = SPANX / 2; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (lane % SPANX == 0) atomicMin(&s_new[(lane + 32 * h) / BPX][(wcol[h] * kP) / BPX], __float_as_int(mn));
+        }
+        __syncthreads();
+        if (threadIdx.x < SBX * SBY) {
+            const int i = threadIdx.x / SBY, j = threadIdx.x % SBY;
+            const int gbx = x0 / BPX + i, gby = y0 / BPX + j;
+            const int nb = max(s_blk[i][j] == 0x7f7fffff ? 0 : s_blk[i][j], s_new[i][j] == 0x7f7fffff ? 0 : s_new[i][j]);
+            if (gbx < prm.nbx && gby < prm.nby && nb > 0) {
+                const size_t blk = (size_t)gbx * prm.nby + gby;
+                const unsigned long long mine = ((unsigned long long)prm.epoch << 32) | (unsigned)nb;
+                if (ld_relaxed_sys_u64(prm.hint[0] + blk) < mine) {      // nobody has published a better bound for this frame yet
+                    for (int r = 0; r < prm.n_hint; ++r) red_max_sys_u64(prm.hint[r] + blk, mine);
+                }
             }
         }
     }

@@ -128,7 +128,8 @@ class ShardedSweep:
     call): key, lockin, grad, kidx, w (if want_w), plus 'rows' = the (begin, end) rows that are valid on
     this rank ((0, 0) on a rank that is not a destination)."""
 
-    def __init__(self, plans, krefs, group=None, dst=0, out_f64=False, want_w=False, transport="auto", timeout_s=20.0):
+    def __init__(self, plans, krefs, group=None, dst=0, out_f64=False, want_w=False, transport="auto", timeout_s=20.0,
+                 gossip=True):
         from . import _lib
         self.plans, self.krefs, self.group = list(plans), [tuple(map(float, k)) for k in krefs], group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -164,6 +165,7 @@ class ShardedSweep:
         self.dst = dst
         self.lib = _lib.load() if self.dev.type == "cuda" else None
         self.epoch = 0
+        self._pending, self._join = [], True
         self.record = False          # True: bracket the phases of every peak with CUDA events (bench.py)
         self.after_peak = None       # optional callable(p), run on peak p's stream once its rows are delivered
         self._events = None
@@ -172,12 +174,19 @@ class ShardedSweep:
         cb, rb = (16, 8) if self.out_f64 else (8, 4)
         if transport == "peer":
             from .peer import PeerArena
+            if 3 * P * 64 > 2048:
+                raise ValueError("too many peaks for the flag block")
             off_key = _FLAG_BYTES
             off_lock = off_key + P * n * m * 8
             off_grad = off_lock + P * n * m * cb
-            total = off_grad + P * n * m * 2 * rb
+            off_hint = off_grad + P * n * m * 2 * rb
+            # threshold gossip (gpa_sweep_arm_gossip): one uint64 per bound block (8 coarse cells = 8 S pixels) and peak
+            blk = 8 * self.plans[0].mr["S"]
+            self._hint_n = (n // blk) * (m // blk) if all(p.mr["S"] * 8 == blk for p in self.plans) and n % blk == 0 and m % blk == 0 else 0
+            self.gossip = bool(gossip) and world > 1 and self._hint_n > 0
+            total = off_hint + (-(-P * self._hint_n * 8 // 256) * 256 if self.gossip else 0)
             self.arena = PeerArena(total, group=group, device=self.dev)
-            self._off = {"key": off_key, "lockin": off_lock, "grad": off_grad}
+            self._off = {"key": off_key, "lockin": off_lock, "grad": off_grad, "hint": off_hint}
             self.keys = self.arena.tensor(off_key, (P, n, m), torch.int64)
             self.lockin = self.arena.tensor(off_lock, (P, n, m), torch.complex128 if self.out_f64 else torch.complex64)
             self.grad = self.arena.tensor(off_grad, (P, n, m, 2), torch.float64 if self.out_f64 else torch.float32)
@@ -241,6 +250,9 @@ class ShardedSweep:
                     row[name + "_ms"] = evs[prev].elapsed_time(evs[name])
                     prev = name
             row["total_ms"] = evs["start"].elapsed_time(evs[prev])
+            if getattr(self, "_base", None) is not None:
+                row["start_offset_ms"] = self._base.elapsed_time(evs["start"])      # from the caller's stream entering the call
+                row["frame_ms"] = self._base.elapsed_time(self._tail)               # ... to the caller's stream past the join
             out.append(row)
         return out
 
@@ -250,10 +262,21 @@ class ShardedSweep:
             self.arena = None
 
     # ---- one frame ------------------------------------------------------------------------------
-    def __call__(self, img_dev, grad_mode=0):
+    def __call__(self, img_dev, grad_mode=0, join=True):
+        """join=False (peer transport, frame streams): the caller's stream does NOT wait for the peaks' streams, so the
+        exchange / finalize tail of this frame overlaps the arg-max of the next call; call join() before using the
+        results on the caller's stream (they are reused by the next call on the same per-peak streams, in order)."""
+        self._join = bool(join) or self.transport != "peer"
         if self.transport == "peer":
             return self._run_peer(img_dev, grad_mode)
         return self._run_collective(img_dev, grad_mode)
+
+    def join(self):
+        """Make the current stream wait for everything the last call(s) enqueued on the per-peak streams."""
+        main = torch.cuda.current_stream(self.dev)
+        for ev in self._pending:
+            main.wait_event(ev)
+        self._pending = []
 
     def _per_peak(self, fn):
         side = self._streams
@@ -262,15 +285,24 @@ class ShardedSweep:
                 fn(p)
             return
         main = torch.cuda.current_stream(self.dev)
+        if self.record:
+            self._base = torch.cuda.Event(enable_timing=True)
+            self._base.record(main)
         start = torch.cuda.Event()
         start.record(main)
+        self._pending = []
         for p in range(self.n_peaks):
             side[p].wait_event(start)
             with torch.cuda.stream(side[p]):
                 fn(p)
             done = torch.cuda.Event()
             done.record(side[p])
-            main.wait_event(done)
+            self._pending.append(done)
+        if getattr(self, "_join", True):
+            self.join()
+        if self.record:
+            self._tail = torch.cuda.Event(enable_timing=True)
+            self._tail.record(main)
 
     def _outs(self):
         return [{"key": self.keys[p], "lockin": self.lockin[p], "grad": self.grad[p], "kidx": self.kidx[p],
@@ -292,6 +324,10 @@ class ShardedSweep:
             self._mark(p, "start")
             self.keys[p].zero_()
             if hi > lo:
+                if self.gossip:      # own array first, then the peers'
+                    order = [rank] + [r for r in everyone if r != rank]
+                    hp = (ctypes.c_void_p * world)(*[self.arena.addr(r, self._off["hint"] + p * self._hint_n * 8) for r in order])
+                    _lib.check(lib.gpa_sweep_arm_gossip(hp, world, self.epoch & 0xFFFFFFFF))
                 plan.argmax(img_dev, self.keys[p], lo, hi, step)
             self._mark(p, "argmax")
             if world > 1:

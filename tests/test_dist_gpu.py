@@ -49,7 +49,7 @@ def _worker(rank, world, port, img, ks, kw, kstep, sigma, out_dir):
         for transport, dst in (("peer", 0), ("peer", "rows"), ("collective", None), ("collective", 0)):
             sw = gdist.ShardedSweep(plans, ks, dst=dst, want_w=True, transport=transport, timeout_s=5.0)
             for rep in range(3):        # epochs: the flags are never reset
-                outs = sw(d_img)
+                outs = sw(d_img, join=rep != 1)     # a frame stream may skip the join between frames
             torch.cuda.synchronize()
             sw.check()
             rows = outs[0]["rows"]

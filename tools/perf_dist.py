@@ -44,10 +44,14 @@ for spec in (sys.argv[1:] or ["peer:0", "peer:rows", "collective:0"]):
     barrier()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(n):
-        outs = sw(img)
+        outs = sw(img, join=False)
+    sw.join()
     e1.record()
+    enqueue_ms = (time.perf_counter() - t0) / n * 1e3
     barrier()
     sw.check()
     ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
@@ -68,7 +72,7 @@ for spec in (sys.argv[1:] or ["peer:0", "peer:rows", "collective:0"]):
     else:
         rows = [tm]
     if rank == 0:
-        print(json.dumps({"transport": transport, "dst": dst, "world": world, "ms_per_step": float(ms.item()),
+        print(json.dumps({"transport": transport, "dst": dst, "world": world, "ms_per_step": float(ms.item()), "host_enqueue_ms_per_step": enqueue_ms,
                           "bit_identical_to_single_gpu": ok, "phases_per_rank": rows}), flush=True)
     sw.close()
 if world > 1:
