@@ -332,6 +332,17 @@ int gpa_fit_plane_huber(const double* img, int n, int m, double f_scale, int max
  * iteration, as the reference).  *iterations (host, optional) receives the iteration count and
  * forces a stream synchronisation.
  * ------------------------------------------------------------------------------------------ */
+/* Device mirrors of the reference's solver helpers, all float64:
+ *   gpa_dctn           scipy.fft.dctn / idctn (type 2, norm=None) of an (N, M) array — the transform pair of solvePoisson
+ *                      and solvePoisson_precomped (phase_unwrap.py:81-103); ws as gpa_unwrap_workspace_bytes(N, M)
+ *   gpa_poisson_scale  precomp_Poissonscaling (phase_unwrap.py:106-115): 2 (cos(pi I/M) + cos(pi J/N) - 2), [0,0] = 1
+ *   gpa_divide_f64     out = a / b elementwise (dctn(rho) / scale)
+ *   gpa_apply_q        applyQ (phase_unwrap.py:118-132); ws >= 512 + 8 ceil(M/64) ceil(N/32) bytes */
+int gpa_dctn(const double* in, int N, int M, int inverse, double* out, void* ws, size_t ws_bytes, void* stream);
+int gpa_poisson_scale(int N, int M, double* scale, void* stream);
+int gpa_divide_f64(const double* a, const double* b, double* out, size_t n, void* stream);
+int gpa_apply_q(const double* p, const double* wwx, const double* wwy, int N, int M, double* q,
+                void* ws, size_t ws_bytes, void* stream);
 int gpa_unwrap_workspace_bytes(int N, int M, size_t* bytes);
 int gpa_unwrap_pcg(const double* psi, const double* dx, const double* dy, const double* weight,
                    int N, int M, int kmax, double* phi, int* iterations /*host or NULL*/,

@@ -73,6 +73,10 @@ SIGNATURES = {
     "gpa_gaussian_deconvolve": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_double, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),
     "gpa_norm_axis0": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
+    "gpa_dctn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_poisson_scale": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "gpa_divide_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_apply_q": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_unwrap_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_unwrap_pcg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                ctypes.POINTER(c_int), c_void_p, c_size_t, c_void_p]),

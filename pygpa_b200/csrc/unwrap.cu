@@ -555,9 +555,112 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
     return GPA_OK;
 }
 
+// twiddle / Makhoul / Bluestein tables of both axes and the cosines of the Poisson scale (a few us; the workspace is
+// the caller's and may have been reused by other entry points since the last call, so they are rebuilt per call)
+static int build_uw_tables(const UwPlan& u, cudaStream_t st) {
+    for (const AxisTables* ax : {&u.axN, &u.axM}) {
+        const int mode = ax->pow2 ? 2 : (ax->bs.L ? 1 : 0);
+        const int cnt = mode ? ax->n : 4 * ax->n;
+        k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, mode);
+        if (ax->bs.L) {       // chirp, FFT_L twiddles and the transformed chirp of the Bluestein convolution
+            k_bs_tables<<<ceil_div(ax->bs.L, 256), 256, 0, st>>>(ax->bs.chirp, ax->bs.tw, ax->bs.P, ax->bs.L);
+            int threads, per;
+            fft_launch_shape(ax->bs.L, threads, per);
+            const size_t smem = (size_t)ax->bs.L * sizeof(double2);
+            if (per <= 1) {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+                k_bs_prep<1><<<1, threads, smem, st>>>(ax->bs);
+            } else {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+                k_bs_prep<2><<<1, threads, smem, st>>>(ax->bs);
+            }
+        }
+    }
+    k_uw_cos_table<<<ceil_div(u.N, 256), 256, 0, st>>>(u.cosI, u.N, u.M);
+    k_uw_cos_table<<<ceil_div(u.M, 256), 256, 0, st>>>(u.cosJ, u.M, u.N);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+// scale[I][J] = 2 (cos(pi I / M) + cos(pi J / N) - 2), [0][0] = 1        (phase_unwrap.py:106-115, N / M swapped as there)
+__global__ void k_uw_poisson_scale(double* __restrict__ scale, int N, int M) {
+    const size_t n = (size_t)N * M;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        scale[i] = poisson_scale((int)(i / M), (int)(i % M), N, M);
+}
+
+__global__ void k_uw_divide(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] / b[i];
+}
+
 }  // namespace gpa
 
 using namespace gpa;
+
+// scipy.fft.dctn / idctn (type 2, norm=None) of an (N, M) float64 array: the transform pair of solvePoisson
+// (phase_unwrap.py:81-103), exposed so that the helper functions of the reference have device mirrors.
+extern "C" int gpa_dctn(const double* in, int N, int M, int inverse, double* out, void* ws, size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(in && out && ws && N >= 2 && M >= 2, "bad argument");
+    UwPlan u;
+    const size_t need = carve_unwrap(u, ws, ws_bytes, N, M);
+    if (need > ws_bytes) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = build_uw_tables(u, st);
+    if (rc) return rc;
+    GPA_CHECK_CUDA(cudaMemsetAsync(u.sc, 0, sizeof(UwScalars), st));
+    DctArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = u.sc; a.dimN = N; a.dimM = M;
+    a.in = in; a.out = u.z; a.rows = N;                                     // along axis 1
+    if ((rc = inverse ? launch_rows<1>(u.axM, a, st) : launch_rows<0>(u.axM, a, st))) return rc;
+    transpose(u.z, u.t, N, M, u.sc, st);
+    a.in = u.t; a.out = u.z; a.rows = M;                                    // along axis 0
+    if ((rc = inverse ? launch_rows<1>(u.axN, a, st) : launch_rows<0>(u.axN, a, st))) return rc;
+    transpose(u.z, out, M, N, u.sc, st);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_poisson_scale(int N, int M, double* scale, void* stream) {
+    GPA_REQUIRE(scale && N >= 1 && M >= 1, "bad argument");
+    size_t blocks = ((size_t)N * M + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_uw_poisson_scale<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(scale, N, M);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+extern "C" int gpa_divide_f64(const double* a, const double* b, double* out, size_t n, void* stream) {
+    GPA_REQUIRE(a && b && out, "null pointer argument");
+    if (n == 0) return GPA_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_uw_divide<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+// q = (A^T)(W^T)(W)(A) p for edge weights wwx (N, M-1), wwy (N-1, M)             (applyQ, phase_unwrap.py:118-132)
+extern "C" int gpa_apply_q(const double* p, const double* wwx, const double* wwy, int N, int M, double* q, void* ws,
+                           size_t ws_bytes, void* stream) {
+    GPA_REQUIRE(p && wwx && wwy && q && ws && N >= 2 && M >= 2, "bad argument");
+    dim3 g2(ceil_div(M, 64), ceil_div(N, kUwRows));
+    const size_t need = 512 + (size_t)g2.x * g2.y * sizeof(double);
+    if (need > ws_bytes) {
+        set_error("workspace too small (%zu < %zu)", ws_bytes, need);
+        return GPA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UwScalars* sc = static_cast<UwScalars*>(ws);
+    double* partial = reinterpret_cast<double*>(static_cast<char*>(ws) + 512);
+    GPA_CHECK_CUDA(cudaMemsetAsync(sc, 0, sizeof(UwScalars), st));
+    k_uw_apply_q<<<g2, 256, 0, st>>>(p, wwx, wwy, q, partial, N, M, sc);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
 
 extern "C" int gpa_unwrap_workspace_bytes(int N, int M, size_t* bytes) {
     GPA_REQUIRE(bytes && N >= 2 && M >= 2, "frame must be at least 2x2");
@@ -581,26 +684,10 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t nm = (size_t)N * M;
-    for (const AxisTables* ax : {&u.axN, &u.axM}) {
-        const int mode = ax->pow2 ? 2 : (ax->bs.L ? 1 : 0);
-        const int cnt = mode ? ax->n : 4 * ax->n;
-        k_uw_tables<<<ceil_div(cnt, 256), 256, 0, st>>>(ax->tw, ax->mk, ax->ct, ax->n, mode);
-        if (ax->bs.L) {       // chirp, FFT_L twiddles and the transformed chirp of the Bluestein convolution
-            k_bs_tables<<<ceil_div(ax->bs.L, 256), 256, 0, st>>>(ax->bs.chirp, ax->bs.tw, ax->bs.P, ax->bs.L);
-            int threads, per;
-            fft_launch_shape(ax->bs.L, threads, per);
-            const size_t smem = (size_t)ax->bs.L * sizeof(double2);
-            if (per <= 1) {
-                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
-                k_bs_prep<1><<<1, threads, smem, st>>>(ax->bs);
-            } else {
-                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_bs_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
-                k_bs_prep<2><<<1, threads, smem, st>>>(ax->bs);
-            }
-        }
+    {
+        int rc = build_uw_tables(u, st);
+        if (rc) return rc;
     }
-    k_uw_cos_table<<<ceil_div(N, 256), 256, 0, st>>>(u.cosI, N, M);
-    k_uw_cos_table<<<ceil_div(M, 256), 256, 0, st>>>(u.cosJ, M, N);
     dim3 g2(ceil_div(M, 64), ceil_div(N, kUwRows));
     const int n2 = g2.x * g2.y;
     GPA_REQUIRE(n2 <= u.npart && N <= u.npart && M <= u.npart, "frame too large for the reduction scratch");

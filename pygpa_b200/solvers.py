@@ -46,6 +46,60 @@ def unwrap(psi=None, dx=None, dy=None, weight=None, kmax=100, return_iters=False
     return (phi, iters.value) if return_iters else phi
 
 
+def _uw_ws(n, m, dev):
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(_lib.load().gpa_unwrap_workspace_bytes(n, m, ctypes.byref(nbytes)))
+    return workspace(nbytes.value, dev)
+
+
+def dctn(x, inverse=False):
+    """scipy.fft.dctn / idctn (type 2, unnormalised) of a float64 CUDA matrix, on the device."""
+    lib = _lib.load()
+    n, m = x.shape
+    ws = _uw_ws(n, m, x.device)
+    out = torch.empty_like(x)
+    _lib.check(lib.gpa_dctn(_ptr(x.contiguous()), n, m, int(bool(inverse)), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    _count(4)
+    return out
+
+
+def poisson_scale(n, m, device=None):
+    """precomp_Poissonscaling (phase_unwrap.py:106-115) for an (n, m) grid, float64 CUDA tensor."""
+    device = device or require_cuda()
+    out = torch.empty((n, m), dtype=torch.float64, device=device)
+    _lib.check(_lib.load().gpa_poisson_scale(n, m, _ptr(out), _stream()))
+    _count(1)
+    return out
+
+
+def divide(a, b):
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().gpa_divide_f64(_ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(out), a.numel(), _stream()))
+    _count(1)
+    return out
+
+
+def solve_poisson(rho, scale=None):
+    """idctn(dctn(rho) / scale) (solvePoisson_precomped, phase_unwrap.py:95-103); scale=None uses precomp_Poissonscaling."""
+    n, m = rho.shape
+    if scale is None:
+        scale = poisson_scale(n, m, rho.device)
+    return dctn(divide(dctn(rho), scale), inverse=True)
+
+
+def apply_q(p, wwx, wwy):
+    """applyQ (phase_unwrap.py:118-132) on float64 CUDA tensors: p (N, M), wwx (N, M-1), wwy (N-1, M)."""
+    lib = _lib.load()
+    n, m = p.shape
+    if tuple(wwx.shape) != (n, m - 1) or tuple(wwy.shape) != (n - 1, m):
+        raise ValueError("wwx must be (N, M-1) and wwy (N-1, M)")
+    ws = workspace(512 + 8 * (-(-m // 64)) * (-(-n // 32)) + 256, p.device)
+    q = torch.empty_like(p)
+    _lib.check(lib.gpa_apply_q(_ptr(p.contiguous()), _ptr(wwx.contiguous()), _ptr(wwy.contiguous()), n, m, _ptr(q), _ptr(ws), ws.numel(), _stream()))
+    _count(1)
+    return q
+
+
 def lstsq(src, kind, kvecs, weights=None, matrix=None, subtract_mean=False):
     """Per-pixel least squares on the device, (2, n, m) float64 (see include/gpa_b200.h, K3)."""
     lib = _lib.load()

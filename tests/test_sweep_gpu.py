@@ -199,7 +199,11 @@ def test_fixed_reference_lockin(noisy_case):
             assert got.dtype == np.complex128
             assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
     stack = GPA.vecGPA(c["img"], c["ks"], 6)
-    assert stack.shape == (3,) + c["img"].shape
+    assert stack.shape == (3,) + c["img"].shape and stack.dtype == np.complex128
+    for i, k in enumerate(c["ks"]):         # values: every plane is that k-vector's lock-in (geometric_phase_analysis.py:79-89)
+        ref = oracle.lockin_fixed(c["img"], k, 6)
+        assert np.abs(stack[i] - ref).max() < 1e-4 * np.abs(ref).max()
+        assert np.array_equal(stack[i], GPA.optGPA(c["img"], k, 6))
     g = load_golden("fixed_64x64.npz")
     got = np.stack([GPA.optGPA(g["in_image"], k, int(g["in_sigma"])) for k in g["in_ks"]])
     assert np.abs(got - g["out_lockin"]).max() < 1e-4 * np.abs(g["out_lockin"]).max()

@@ -124,3 +124,39 @@ def test_constant_phase_returns_zero_without_iterating():
     got, k = solvers.unwrap(psi=solvers.to_device_f64(psi, dev), kmax=50, return_iters=True)
     assert k == 0 and not got.cpu().numpy().any()
     assert not oracle.phase_unwrap(psi, None, kmax=50).any()
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (40, 56), (96, 81)])
+def test_solver_helper_mirrors(shape):
+    """solvePoisson, solvePoisson_precomped, precomp_Poissonscaling and applyQ
+    (phase_unwrap.py:81-132) as device mirrors, against scipy's dctn / idctn and the oracle's restatement."""
+    from scipy.fft import dctn, idctn
+    from oracle import ref_numpy
+    rng = np.random.default_rng(sum(shape))
+    n, m = shape
+    rho = rng.normal(size=shape)
+    # precomp_Poissonscaling, with the reference's swapped N / M
+    scale = PU.precomp_Poissonscaling(rho)
+    i, j = np.ogrid[0:n, 0:m]
+    want = 2 * (np.cos(np.pi * i / m) + np.cos(np.pi * j / n) - 2)
+    want[0, 0] = 1.0
+    assert scale.shape == shape and np.allclose(scale, want, rtol=1e-13, atol=1e-13)
+    assert np.allclose(scale, ref_numpy._poisson_scale(shape), rtol=1e-13, atol=1e-13)
+    # the transform pair itself
+    x = solvers.to_device_f64(rho)
+    fwd = solvers.dctn(x).cpu().numpy()
+    assert np.allclose(fwd, dctn(rho), rtol=1e-11, atol=1e-10)
+    assert np.allclose(solvers.dctn(solvers.to_device_f64(fwd), inverse=True).cpu().numpy(), rho, rtol=1e-11, atol=1e-11)
+    # solvePoisson_precomped with the reference's scale and with an arbitrary one
+    assert np.allclose(PU.solvePoisson_precomped(rho, want), idctn(dctn(rho) / want), rtol=1e-10, atol=1e-11)
+    other = 1.0 + rng.random(shape)
+    assert np.allclose(PU.solvePoisson_precomped(rho, other), idctn(dctn(rho) / other), rtol=1e-10, atol=1e-11)
+    # solvePoisson: the [0, 0] coefficient is zeroed instead of kept
+    with np.errstate(divide='ignore', invalid='ignore'):
+        d = dctn(rho) / 2 / (np.cos(np.pi * i / m) + np.cos(np.pi * j / n) - 2)
+    d[0, 0] = 0
+    assert np.allclose(PU.solvePoisson(rho), idctn(d), rtol=1e-10, atol=1e-11)
+    # applyQ
+    wwx, wwy = rng.random((n, m - 1)), rng.random((n - 1, m))
+    p = rng.normal(size=shape)
+    assert np.allclose(PU.applyQ(p, wwx, wwy), ref_numpy._apply_q(p, wwx, wwy), rtol=1e-12, atol=1e-12)
