@@ -40,9 +40,18 @@ __device__ __forceinline__ void dft8(double2 (&u)[8]) {
     u[0] = a0; u[1] = b0; u[2] = a1; u[3] = b1; u[4] = a2; u[5] = b2; u[6] = a3; u[7] = b3;
 }
 
+// fft_pow2_g: the same transform run by a GROUP of nthr threads (tid = index inside the group) on the group's own
+// buffer; every group of the CTA must call it with the same n (the barriers are CTA-wide).
+template <int MAXB>
+__device__ __forceinline__ void fft_pow2_g(double2* buf, int n, const double2* __restrict__ tw, int tid, int nthr);
+
 template <int MAXB>
 __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __restrict__ tw) {
-    const int nthr = blockDim.x;
+    fft_pow2_g<MAXB>(buf, n, tw, (int)threadIdx.x, (int)blockDim.x);
+}
+
+template <int MAXB>
+__device__ __forceinline__ void fft_pow2_g(double2* buf, int n, const double2* __restrict__ tw, const int tid, const int nthr) {
     const int lg = 31 - __clz(n);
     int ns = 1;
     if (lg % 3 == 1) {                               // one radix-2 stage (ns = 1: twiddles are 1)
@@ -50,7 +59,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         double2 a[4 * MAXB], b[4 * MAXB];
 #pragma unroll
         for (int q = 0; q < 4 * MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < half) {
                 a[q] = buf[j];
                 b[q] = buf[j + half];
@@ -59,7 +68,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 4 * MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < half) {
                 buf[2 * j] = zadd(a[q], b[q]);
                 buf[2 * j + 1] = zsub(a[q], b[q]);
@@ -72,7 +81,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         double2 v[2 * MAXB][4];
 #pragma unroll
         for (int q = 0; q < 2 * MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < quarter) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[q][i] = buf[j + i * quarter];
@@ -81,7 +90,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 2 * MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < quarter) {
                 dft4(v[q][0], v[q][1], v[q][2], v[q][3]);
 #pragma unroll
@@ -97,7 +106,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         const int tstep = e / ns;                    // e^{-2 pi i q k/(8 ns)} = tw[q k n/(8 ns)]
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < e) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) u[q][i] = buf[j + i * e];
@@ -119,7 +128,7 @@ __device__ __forceinline__ void fft_pow2(double2* buf, int n, const double2* __r
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < MAXB; ++q) {
-            const int j = threadIdx.x + q * nthr;
+            const int j = tid + q * nthr;
             if (j < e) {
                 const int k = j & (ns - 1);
                 const int j0 = ((j - k) << 3) + k;

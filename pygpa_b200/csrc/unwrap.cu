@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "fft_device.cuh"
 
+#include <utility>
+
 namespace gpa {
 
 constexpr double kPi = 3.141592653589793238462643383279;
@@ -299,6 +301,109 @@ __global__ void k_dct2_rows_direct(const DctArgs a) {
     }
 }
 
+// Fused column stage of the Poisson solve for power-of-two N: the CTA owns a strip of CW columns of the (N, M) array
+// (row-DCT coefficients), transforms every column (DCT-II along axis 0), divides by the Poisson scale and transforms
+// back (DCT-III), all inside shared memory: z <- idct_0(dct_0(z) / scale).  One read and one write of the array instead
+// of transpose + row pass + row pass + transpose (6 passes -> 2).  Columns are paired like the rows of
+// k_dct2_rows_pow2 (columns c, c+1 ride in the real / imaginary part of one complex FFT); a group of n / (8 MAXB)
+// threads runs each FFT, CW / 2 groups per CTA.  Global accesses are CW x 8 B contiguous per row (whole sectors for
+// CW >= 4).  The arithmetic per element is that of k_dct2_rows_pow2 (epilogue) followed by k_idct2_rows_pow2 (prologue).
+struct ColArgs {
+    double* z;                 // (N, M) row-major, in place
+    int N, M, CW, tpf;         // strip width, threads per FFT
+    const double2 *tw, *mk;    // FFT tables of length N
+    const double *cos_k, *cos_c;   // cos(pi k / M), k < N ; cos(pi c / N), c < M      (phase_unwrap.py:109, swapped on purpose)
+    const UwScalars* sc;
+};
+
+template <int MAXB>
+__global__ void __launch_bounds__(MAXB == 1 ? 1024 : 512, 1) k_poisson_cols(const ColArgs a) {
+    if (a.sc->done) return;
+    extern __shared__ double2 cbuf[];
+    const int n = a.N, M = a.M, CW = a.CW, tpf = a.tpf;
+    const int gstride = n + 1;                      // one complex of padding: the groups' buffers start 4 banks apart
+    const int c0 = blockIdx.x * CW;
+    const int nthr = blockDim.x;
+    double* const flat = reinterpret_cast<double*>(cbuf);
+    // ---- load the strip, Makhoul order, columns (2g, 2g+1) -> (re, im) of group g
+    for (int base = 0; base < n * CW; base += nthr * 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int idx = base + threadIdx.x + q * nthr;
+            const int r = idx / CW, cc = idx - r * CW;
+            v[q] = (idx < n * CW && c0 + cc < M) ? a.z[(size_t)r * M + c0 + cc] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int idx = base + threadIdx.x + q * nthr;
+            if (idx < n * CW) {
+                const int r = idx / CW, cc = idx - r * CW;
+                const int pos = (r & 1) ? n - 1 - (r >> 1) : (r >> 1);
+                flat[((size_t)(cc >> 1) * gstride + pos) * 2 + (cc & 1)] = v[q];
+            }
+        }
+    }
+    __syncthreads();
+    const int g = threadIdx.x / tpf, gt = threadIdx.x - g * tpf;
+    double2* const buf = cbuf + (size_t)g * gstride;
+    fft_pow2_g<MAXB>(buf, n, a.tw, gt, tpf);
+    // ---- DCT-II epilogue, Poisson scale, DCT-III prologue: pairs (k, n - k) are independent of each other
+    {
+        const int ca = c0 + 2 * g, cb = ca + 1;                  // the two columns of this group (axis-1 frequencies J)
+        const double cra = ca < M ? a.cos_c[ca] : 0.0, crb = cb < M ? a.cos_c[cb] : 0.0;
+        const int half = n >> 1;
+        for (int k = gt; k <= half; k += tpf) {
+            const int kn = k ? n - k : 0;
+            const double2 zk = buf[k], zn = buf[kn];
+            const double2 wk = __ldg(a.mk + k);
+            // forward coefficients at k (as k_dct2_rows_pow2)
+            double ra_k = wk.x * (zk.x + zn.x) - wk.y * (zk.y - zn.y);
+            double rb_k = wk.x * (zk.y + zn.y) + wk.y * (zk.x - zn.x);
+            const double ck = a.cos_k[k];
+            ra_k /= (k == 0 && ca == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
+            rb_k /= 2.0 * (ck + crb - 2.0);
+            double ra_n = 0.0, rb_n = 0.0;
+            double2 wn = make_double2(0.0, 0.0);
+            if (k != 0) {
+                if (k == half) {
+                    ra_n = ra_k; rb_n = rb_k; wn = wk;
+                } else {      // forward coefficients at n - k: Z and conj-partner swap roles
+                    wn = __ldg(a.mk + kn);
+                    ra_n = wn.x * (zn.x + zk.x) - wn.y * (zn.y - zk.y);
+                    rb_n = wn.x * (zn.y + zk.y) + wn.y * (zn.x - zk.x);
+                    const double cn = a.cos_k[kn];
+                    ra_n /= 2.0 * (cn + cra - 2.0);
+                    rb_n /= 2.0 * (cn + crb - 2.0);
+                }
+            }
+            // inverse prologue at k (as k_idct2_rows_pow2): partner value is the coefficient at n - k (0 for k = 0)
+            {
+                const double re_a = 0.5 * (wk.x * ra_k - wk.y * ra_n), im_a = 0.5 * (-wk.y * ra_k - wk.x * ra_n);
+                const double re_b = 0.5 * (wk.x * rb_k - wk.y * rb_n), im_b = 0.5 * (-wk.y * rb_k - wk.x * rb_n);
+                buf[k] = make_double2(re_a - im_b, -im_a - re_b);
+            }
+            if (k != 0 && k != half) {
+                const double re_a = 0.5 * (wn.x * ra_n - wn.y * ra_k), im_a = 0.5 * (-wn.y * ra_n - wn.x * ra_k);
+                const double re_b = 0.5 * (wn.x * rb_n - wn.y * rb_k), im_b = 0.5 * (-wn.y * rb_n - wn.x * rb_k);
+                buf[kn] = make_double2(re_a - im_b, -im_a - re_b);
+            }
+        }
+    }
+    __syncthreads();
+    fft_pow2_g<MAXB>(buf, n, a.tw, gt, tpf);
+    // ---- store: x[j] = Re / -Im of F[perm(j)] / n
+    const double inv = 1.0 / (double)n;
+    for (int idx = threadIdx.x; idx < n * CW; idx += nthr) {
+        const int r = idx / CW, cc = idx - r * CW;
+        if (c0 + cc < M) {
+            const int pos = (r & 1) ? n - 1 - (r >> 1) : (r >> 1);
+            const double f = flat[((size_t)(cc >> 1) * gstride + pos) * 2 + (cc & 1)];
+            a.z[(size_t)r * M + c0 + cc] = (cc & 1) ? -f * inv : f * inv;
+        }
+    }
+}
+
 __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
                             const UwScalars* sc) {
     if (sc->done) return;
@@ -542,6 +647,26 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
     KernelTimer timer("uw_poisson_solve", st);
     a.in = u.r; a.out = u.z; a.rows = N;                                   // rows along axis 1
     if ((rc = launch_rows<0>(u.axM, a, st))) return rc;
+    if (u.axN.pow2 && M % 2 == 0) {       // fused column stage: z <- idct_0(dct_0(z) / scale) in one pass over the array
+        ColArgs c;
+        c.z = u.z; c.N = N; c.M = M; c.tw = u.axN.tw; c.mk = u.axN.mk; c.cos_k = u.cosI; c.cos_c = u.cosJ; c.sc = u.sc;
+        const int maxb = N / 8 > 512 ? 2 : 1;
+        c.tpf = N / (8 * maxb) < 32 ? 32 : N / (8 * maxb);
+        int cw = 8;
+        while (cw > 2 && ((size_t)(cw / 2) * (N + 1) * sizeof(double2) > 200 * 1024 || (cw / 2) * c.tpf > (maxb == 1 ? 1024 : 512))) cw /= 2;
+        c.CW = cw;
+        const size_t smem = (size_t)(cw / 2) * (N + 1) * sizeof(double2);
+        const int threads = (cw / 2) * c.tpf;
+        if (maxb == 1) {
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_poisson_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+            k_poisson_cols<1><<<ceil_div(M, cw), threads, smem, st>>>(c);
+        } else {
+            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_poisson_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+            k_poisson_cols<2><<<ceil_div(M, cw), threads, smem, st>>>(c);
+        }
+        a.in = u.z; a.out = u.t; a.rows = N; a.dot_with = u.r; a.partial = u.partial;
+        return launch_rows<1>(u.axM, a, st);                               // t = z_k, partial = <r, z> rows
+    }
     transpose(u.z, u.t, N, M, u.sc, st);                                   // t: (M, N)
     a.in = u.t; a.out = u.z; a.rows = M; a.fuse_scale = 1;                 // rows along axis 0, then / scale
     a.cos_col = u.cosI; a.cos_row = u.cosJ;
@@ -711,6 +836,8 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
         if (rc) return rc;
         {
             KernelTimer timer("uw_vector_ops", st);
+            // (fusing p = z + beta p into the stencil kernel was measured SLOWER on B200: 0.115 vs 0.097 ms per iteration at
+            // 2048^2 — the stencil is LSU- / latency-bound, not DRAM-bound, and the fused form doubles its loads)
             k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
             k_uw_apply_q<<<g2, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
             k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
