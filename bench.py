@@ -234,7 +234,7 @@ def run_ours(args, cfg):
     gpu_launches = engine.launch_count - launches0
     tot, n = ctypes.c_double(0), ctypes.c_int(0)
     kernels = {}
-    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize",
+    names = ("k_mr_pass1", "k_mr_pass1a", "k_mr_pass1b", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize",
              "k_pass1", "k_pass2_argmax", "k_finalize")
     for name in names:
         _lib.check(lib.gpa_profile_read(name.encode(), ctypes.byref(tot), ctypes.byref(n), 0))
