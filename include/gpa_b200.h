@@ -157,7 +157,7 @@ int gpa_set_pruning(int on);
 /* Host-side planner of the split (no CUDA; same search as pygpa_b200/_taps.py): picks the shortest coarse
  * filter (13 ... 23 taps) whose worst-case transfer-function error against the candidate-centred G_a, over
  * all input frequencies and the widest dw of wx_rows, stays below 1.3e-6 (the error of truncating G_a at
- * 4.5 sigma).  Returns 1 and fills R1x, H2x, sigma_1, taps_1x (capacity 446 floats) and taps_2x (23 floats);
+ * 4.5 sigma) with a re-amplification c <= 8 (fp32 rounding noise of the anchor stage is multiplied by it).  Returns 1 and fills R1x, H2x, sigma_1, taps_1x (capacity 446 floats) and taps_2x (23 floats);
  * returns 0 when the candidate axis is too wide or too short for one shared anchor (use R1x = 0). */
 int gpa_split_plan(int n, int stride, double sigma_a, const double* wx_rows /*host*/, int n_rows,
                    int* R1x, int* H2x, double* sigma_1, float* taps_1x /*host*/, float* taps_2x /*host*/);

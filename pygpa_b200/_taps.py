@@ -42,6 +42,13 @@ def _kernel_taps(n, sigma, r):
     return np.ascontiguousarray(kernel[np.arange(-r, r + 1) % n], dtype=np.float32)
 
 
+def _pass2_tile_fits(s, j):
+    """Shared-memory budget of the decimating pass-2 kernels (csrc/lockin.cu, launch_mr): the plane tile of
+    S (W2 kP + J + kAhead + 1) fine rows x 32 columns plus two carrier buffers per warp group must fit 227 KB."""
+    w2 = 4 if s == 8 else 8
+    return s * (w2 * 16 + j + 3) * (32 + 4) * 8 <= 227 * 1024
+
+
 @functools.lru_cache(maxsize=64)
 def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
     """Parameters of the multirate sweep for an (n, m) frame, or None when it does not apply.
@@ -70,6 +77,8 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
             continue
         if 2 * ra + 1 > min(n, m) or s * (-(-(2 * ra + 1) // s)) + 2 > MAX_TAPS:
             continue
+        if not _pass2_tile_fits(s, -(-(2 * ra + 1) // s)):
+            continue          # large sigma: fall through to a smaller stride (shorter tile in fine rows)
         return dict(S=s, Ra_x=ra, Ra_y=ra, Rb=rb, sigma_a=sigma_a, sigma_b=sigma_b,
                     taps_ax=_kernel_taps(n, sigma_a, ra), taps_ay=_kernel_taps(m, sigma_a, ra),
                     taps_bx=_kernel_taps(n, sigma_b, rb), taps_by=_kernel_taps(m, sigma_b, rb))
@@ -79,6 +88,7 @@ def multirate_taps(n, m, sigma, trunc=DEFAULT_TRUNC):
 # ---- split pass 2: G_a = G_1 * G_2, anchor stage shared by the candidates of a plane ---------------
 SPLIT_TOL = 1.3e-6       # worst-case transfer-function error; the 4.5 sigma truncation of G_a alone is 1.3e-6
 SPLIT_TRUNC1 = 6.0       # stage A runs once per plane: its truncation is free
+SPLIT_MAX_LOG_GAIN = float(np.log(8.0))   # largest re-amplification c of a candidate (C3: 2.5; stride 8 at sigma = 22: 3.5)
 
 
 def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
@@ -93,7 +103,10 @@ def _split_error(s, sigma_a, sigma_1, r1, h, dw, nf=2048):
     m = np.arange(-h, h + 1)
     h2 = s * np.exp(-(s * m) ** 2 / (2 * sigma_2 ** 2)) / (sigma_2 * np.sqrt(2 * np.pi))
     delta = dw * sigma_a ** 2 / sigma_2 ** 2
-    c = np.exp(2 * np.pi ** 2 * dw ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2)
+    log_c = 2 * np.pi ** 2 * dw ** 2 * sigma_a ** 2 * sigma_1 ** 2 / sigma_2 ** 2
+    if log_c > SPLIT_MAX_LOG_GAIN:  # the candidate sits far out on G_1's slope: its band leaves the anchor stage attenuated
+        return float("inf")         # by 1/c and fp32 rounding noise comes back amplified by c
+    c = np.exp(log_c)
     H2 = np.exp(-2j * np.pi * np.outer(s * (f + delta), m)) @ h2
     return float(np.abs(c * G1 * H2 - np.exp(-2 * np.pi ** 2 * sigma_a ** 2 * (f + dw) ** 2)).max())
 
@@ -112,7 +125,7 @@ def _split_plan(n, s, sigma_a, dw_max):
             j1 = -(-(2 * r1 + 1) // s)
             j1 = max(18, j1 + (j1 & 1))                 # even, >= 18: the statically scheduled stage-A kernels
             r1 = (s * j1 - 1) // 2
-            if r1 + s * (h + 1) > n or n // s <= 2 * (-(-r1 // s) + 1) or s * j1 + 2 > MAX_TAPS:
+            if r1 + s * (h + 1) > n or n // s <= 2 * (-(-r1 // s) + 1) or s * j1 + 2 > MAX_TAPS or not _pass2_tile_fits(s, j1):
                 continue
             err = max(_split_error(s, sigma_a, sigma_1, r1, h, dw) for dw in (dw_max, 0.5 * dw_max))
             if best is None or err < best[0]:

@@ -49,6 +49,13 @@ extern "C" int gpa_default_radius(int n, double sigma, double trunc) {
     return r < 0 ? 0 : r;
 }
 
+// Shared-memory budget of the decimating pass-2 kernels (lockin.cu, launch_mr): S (W2 kP + J + kAhead + 1) fine rows
+// x (32 columns + two carrier buffers per warp group) of float2 must fit 227 KB.
+static bool pass2_tile_fits(int s, int j) {
+    const int w2 = s == 8 ? 4 : 8;
+    return (long long)s * (w2 * 16 + j + 3) * (32 + 4) * 8 <= 227 * 1024;
+}
+
 // Parameters of the multirate sweep (same rule as pygpa_b200/_taps.py): returns the stride (2, 4 or 8)
 // or 0 when the multirate form does not apply (use the direct form).
 extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, double* sigma_b, int* Ra, int* Rb) {
@@ -68,6 +75,7 @@ extern "C" int gpa_multirate_plan(int N, int M, double sigma, double* sigma_a, d
         }
         if (rb > 5 * s) continue;
         if (2 * ra + 1 > (N < M ? N : M) || s * ((2 * ra + 1 + s - 1) / s) + 2 > 446) continue;
+        if (!pass2_tile_fits(s, (2 * ra + 1 + s - 1) / s)) continue;     // large sigma: try the next smaller stride
         if (sigma_a) *sigma_a = sa;
         if (sigma_b) *sigma_b = sb;
         if (Ra) *Ra = ra;
@@ -86,7 +94,10 @@ double split_error(int s, double sigma_a, double sigma_1, int r1, int h, double 
     const double pi = 3.141592653589793238462643383279;
     const double s2sq = sigma_a * sigma_a - sigma_1 * sigma_1, sigma_2 = std::sqrt(s2sq);
     const double delta = dw * sigma_a * sigma_a / s2sq;
-    const double c = std::exp(2.0 * pi * pi * dw * dw * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq);
+    const double log_c = 2.0 * pi * pi * dw * dw * sigma_a * sigma_a * sigma_1 * sigma_1 / s2sq;
+    if (log_c > 2.0794415416798357) return HUGE_VAL;   // c > 8: the band leaves the anchor stage attenuated by 1/c and
+                                                        // fp32 rounding noise would come back amplified by c
+    const double c = std::exp(log_c);
     std::vector<double> g1(r1 + 1), h2(h + 1);
     for (int d = 0; d <= r1; ++d) g1[d] = std::exp(-(double)d * d / (2.0 * sigma_1 * sigma_1)) / (sigma_1 * std::sqrt(2.0 * pi));
     for (int m = 0; m <= h; ++m) h2[m] = s * std::exp(-(double)(s * m) * (s * m) / (2.0 * s2sq)) / (sigma_2 * std::sqrt(2.0 * pi));
@@ -139,7 +150,7 @@ extern "C" int gpa_split_plan(int n, int stride, double sigma_a, const double* w
             j1 += j1 & 1;
             if (j1 < 18) j1 = 18;
             r1 = (s * j1 - 1) / 2;
-            if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446) continue;
+            if (r1 + s * (h + 1) > n || n / s <= 2 * ((r1 + s - 1) / s + 1) || s * j1 + 2 > 446 || !pass2_tile_fits(s, j1)) continue;
             const double err = std::fmax(split_error(s, sigma_a, sigma_1, r1, h, dw_max), split_error(s, sigma_a, sigma_1, r1, h, 0.5 * dw_max));
             if (b.err < 0.0 || err < b.err) b = Best{err, sigma_1, sigma_2, r1};
         }

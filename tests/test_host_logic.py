@@ -81,7 +81,8 @@ def test_c_side_taps_and_multirate_plan_agree_with_python(n, sigma):
     got = np.zeros(2 * r + 1, dtype=np.float32)
     assert lib.gpa_gaussian_taps(n, sigma, r, _lib.as_pf(got)) == 0
     assert np.abs(got - ref).max() <= 2e-7 * ref.max()
-    for size, sg in ((2048, 10.0), (1024, 10.0), (256, 5.0), (2048, 22.0), (64, 4.0), (500, 9.0), (250, 10.0)):
+    for size, sg in ((2048, 10.0), (1024, 10.0), (256, 5.0), (2048, 22.0), (64, 4.0), (500, 9.0), (250, 10.0),
+                     (2048, 29.0), (2048, 30.0), (2048, 35.0), (2048, 49.0)):
         sa, sb = ctypes.c_double(0), ctypes.c_double(0)
         ra, rb = ctypes.c_int(0), ctypes.c_int(0)
         s_c = lib.gpa_multirate_plan(size, size, sg, ctypes.byref(sa), ctypes.byref(sb), ctypes.byref(ra), ctypes.byref(rb))
@@ -158,3 +159,38 @@ def test_c_side_split_plan_agrees_with_python(size, sigma, r_k, n_grid):
         assert (r1.value, h.value) == (sp["R1"], sp["H"]) and abs(s1.value - sp["sigma_1"]) < 1e-9
         assert np.abs(t1[:2 * r1.value + 1] - sp["taps_1"]).max() < 1e-7
         assert np.abs(t2[:2 * h.value + 1] - sp["taps_2"]).max() < 1e-6
+
+
+def test_multirate_plans_fit_the_pass2_tile_in_shared_memory():
+    """Large sigma: the stride-8 plan's pass-2 tile (S (W2 kP + J + 3) fine rows) would exceed 227 KB of shared
+    memory from sigma ~ 29.5 on; the planner must then pick a smaller stride instead of a plan that fails at launch."""
+    for sigma in (5.0, 10.0, 17.0, 22.0, 28.0, 29.5, 30.0, 33.0, 40.0, 48.0):
+        mr = _taps.multirate_taps(2048, 2048, sigma)
+        assert mr is not None
+        s = mr["S"]
+        j = -(-(2 * mr["Ra_x"] + 1) // s)
+        w2 = 4 if s == 8 else 8
+        assert s * (w2 * 16 + j + 3) * 36 * 8 <= 227 * 1024, (sigma, s, j)
+        assert s * (8 * 16 + j + 3) * (33 * 4 + 16) + 4 <= 227 * 1024          # pass-1 tile
+    assert _taps.multirate_taps(2048, 2048, 28.0)["S"] == 8 and _taps.multirate_taps(2048, 2048, 30.0)["S"] == 4
+
+
+def test_split_plans_are_finite_and_bounded():
+    """Wide grids at large sigma used to overflow the planner's gain exp(2 pi^2 dw^2 ...) into NaN, which compared as
+    'within tolerance'.  Every accepted plan must have a finite error below SPLIT_TOL and a re-amplification <= 8
+    (fp32 rounding noise of the anchor stage comes back multiplied by it)."""
+    rng = np.random.default_rng(4)
+    seen = 0
+    for _ in range(60):
+        n = int(rng.choice([96, 128, 256, 512, 1024, 2048]))
+        sigma = float(rng.choice([4.5, 5, 9, 10, 17.9, 22, 29, 35, 49]))
+        mr = _taps.multirate_taps(n, n, sigma)
+        if mr is None:
+            continue
+        ks = synth.primary_ks(float(rng.choice([0.5 / sigma, 0.05, 0.1, 0.02])), 7.0, 3)
+        kw, kstep = synth.sweep_params(ks, int(rng.choice([9, 21, 41])))
+        sp = _taps.split_taps(n, mr, np.arange(ks[0][0] - kw, ks[0][0] + kw, kstep))
+        if sp is not None:
+            seen += 1
+            assert np.isfinite(sp["err"]) and sp["err"] <= _taps.SPLIT_TOL and sp["c_max"] <= 8.0 * 1.001
+    assert seen >= 10
