@@ -288,7 +288,7 @@ def run_ours(args, cfg):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     gpu_launches = engine.launch_count - launches0
-    names = ("k_mr_pass1", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize",
+    names = ("k_mr_pass1", "k_mr_pass1a", "k_mr_pass1b", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize",
              "k_key_merge", "k_pass1", "k_pass2_argmax", "k_finalize")
     kernels = _profile_read(lib, names, reset_with="k_pass1")
     if sweep is not None:

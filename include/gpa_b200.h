@@ -166,7 +166,8 @@ int gpa_set_pruning(int on);
 int gpa_split_plan(int n, int stride, double sigma_a, const double* wx_rows /*host*/, int n_rows,
                    int* R1x, int* H2x, double* sigma_1, float* taps_1x /*host*/, float* taps_2x /*host*/);
 int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int stride,
-                                 int Rax, int Ray, int Rb, int R1x, int H2x, int planes_in_flight, size_t* bytes);
+                                 int Rax, int Ray, int Rb, int R1x, int H2x, int R1y, int H2y, int planes_in_flight,
+                                 size_t* bytes);
 int gpa_sweep_argmax_mr(const float* img, int N, int M,
                         const double* wx_rows /*host*/, int n_rows,
                         const double* wy_planes /*host*/, int n_planes, int cand_mode,
@@ -175,6 +176,7 @@ int gpa_sweep_argmax_mr(const float* img, int N, int M,
                         const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
                         const float* taps_1x /*host*/, int R1x, const float* taps_2x /*host*/, int H2x,
                         double sigma_a, double sigma_1,
+                        const float* taps_1y /*host*/, int R1y, const float* taps_2y /*host*/, int H2y, double sigma_1y,
                         unsigned long long* key, void* ws, size_t ws_bytes, void* stream);
 
 /* gpa_sweep_finalize computed from the coarse grids gpa_sweep_argmax_mr left in ws (same ws, same
@@ -185,7 +187,7 @@ int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows /*host*/, int n_ro
                           const double* wy_planes /*host*/, int n_planes, int cand_mode,
                           int plane_begin, int plane_end, int plane_step, int stride, int Rax, int Ray,
                           const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
-                          int R1x, int H2x,
+                          int R1x, int H2x, int R1y, int H2y,
                           const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
                           int out_f64, void* lockin, void* grad, void* w, int* kidx,
                           void* ws, size_t ws_bytes, void* stream);
@@ -468,7 +470,7 @@ int gpa_sweep_finalize_mr_sharded(int N, int M, const double* wx_rows /*host*/, 
                                   const double* wy_planes /*host*/, int n_planes, int cand_mode,
                                   int plane_begin, int plane_end, int plane_step, int stride, int Rax, int Ray,
                                   const float* taps_bx /*host*/, const float* taps_by /*host*/, int Rb,
-                                  int R1x, int H2x,
+                                  int R1x, int H2x, int R1y, int H2y,
                                   const unsigned long long* key, double kref_x, double kref_y, int grad_mode,
                                   int out_f64, void* const* lockin_dst /*host*/, void* const* grad_dst /*host*/,
                                   int n_dst, int dst_rows, int write_zero,

@@ -37,12 +37,12 @@ SIGNATURES = {
     "gpa_sweep_argmax": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int,
                                  _pf, c_int, _pf, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_set_pruning": (c_int, [c_int]),
-    "gpa_sweep_mr_workspace_bytes": (c_int, [c_int] * 12 + [ctypes.POINTER(c_size_t)]),
+    "gpa_sweep_mr_workspace_bytes": (c_int, [c_int] * 14 + [ctypes.POINTER(c_size_t)]),
     "gpa_sweep_argmax_mr": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _pf, c_int, _pf, c_int, _pf, _pf, c_int, _pf, c_int, _pf, c_int, c_double, c_double,
-                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    _pf, c_int, _pf, c_int, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_sweep_finalize_mr": (c_int, [c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                      _pf, _pf, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,
+                                      _pf, _pf, c_int, c_int, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_sweep_finalize": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int,
                                    _pf, c_int, _pf, c_int, c_void_p, c_double, c_double, c_int, c_int,
@@ -93,7 +93,7 @@ SIGNATURES = {
     "gpa_sweep_arm_gossip": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.c_uint]),
     "gpa_key_to_w": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gpa_sweep_finalize_mr_sharded": (c_int, [c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                              _pf, _pf, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,
+                                              _pf, _pf, c_int, c_int, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,
                                               ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, c_int,
                                               c_void_p, c_size_t, c_void_p]),
     "gpa_lawler_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),

@@ -182,17 +182,20 @@ struct MrGeometry {
     int nbx_alloc, nby_alloc, can_prune;
     // split pass 2 (R1 > 0): stage-A radius / taps per phase, stage-B coarse radius, extended coarse rows, row shift of P1
     int R1, J1, H, NdE, row_shift;
+    // split pass 1 (R1y > 0): the same along axis 1, one anchor plane per call
+    int R1y, J1y, Hy, MdE, pitch_e, col_shift, rows_a;
     size_t plane_stride, p2_stride, pm_stride, a_stride;   // elements per plane
     double *wx_d, *wy_d;
     float2 *phx, *phy, *p1, *p2;
     float2 *a_st, *phx1, *carB, *derotB, *jB;    // split pass 2: stage-A output and the carrier tables
+    float2 *a_y, *carBy, *derotBy, *jBy;         // split pass 1: anchor plane (body / edge parts) and the carrier tables
     float* pmax;
     unsigned short* perm;
     int chunk;
 };
 
 static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax, int Ray, int Rb,
-                   int R1 = 0, int H = 0) {
+                   int R1 = 0, int H = 0, int R1y = 0, int Hy = 0) {
     GPA_REQUIRE(S == 2 || S == 4 || S == 8, "multirate stride must be 2, 4 or 8 (got %d)", S);
     GPA_REQUIRE(N % S == 0 && M % S == 0, "frame (%d x %d) is not divisible by the stride %d", N, M, S);
     GPA_REQUIRE(n_rows >= 1 && n_planes >= 1, "empty candidate set");
@@ -226,6 +229,18 @@ static int plan_mr(MrGeometry& g, int N, int M, int n_rows, int n_planes, int ca
         g.n_rows_filled = S * g.NdE + S * g.J1;
         g.a_stride = (size_t)2 * g.NdE * g.Md;
     }
+    g.R1y = R1y; g.Hy = Hy; g.J1y = 0; g.MdE = 0; g.pitch_e = 0; g.col_shift = Ray; g.rows_a = 0;
+    if (R1y > 0) {
+        GPA_REQUIRE(Hy >= 1 && 2 * Hy + 1 <= 23, "split pass 1: coarse radius %d out of range", Hy);
+        GPA_REQUIRE(g.Md >= 2 * (ceil_div(R1y, S) + 1) && R1y + S * (Hy + 1) <= M,
+                    "split pass 1: stage-A radius %d does not fit the frame", R1y);
+        g.J1y = ceil_div(2 * R1y + 1, S);
+        GPA_REQUIRE(S * g.J1y + kAhead <= kMaxTaps, "split pass 1: stage-A filter too long");
+        g.MdE = g.Md + 2 * Hy;
+        g.pitch_e = (int)align_up((size_t)g.MdE, 32);
+        g.col_shift = R1y + S * Hy;
+        g.rows_a = (int)align_up((size_t)g.n_rows_filled, 32);
+    }
     g.plane_stride = (size_t)g.n_alloc * g.pitch_d;
     g.p2_stride = (size_t)g.n_cand * g.Nd * g.Md;
     g.nbx_alloc = ceil_div(g.Nd, kWarps * kP) * (kWarps * kP / kPmB);
@@ -251,6 +266,12 @@ static size_t carve_mr(MrGeometry& g, void* ws, size_t ws_bytes, int chunk) {
         g.carB = a.take<float2>((size_t)g.n_cand * g.NdE);
         g.derotB = a.take<float2>((size_t)g.n_cand * g.Nd);
         g.jB = a.take<float2>((size_t)2 * g.n_cand);
+    }
+    if (g.R1y > 0) {
+        g.a_y = a.take<float2>((size_t)2 * g.rows_a * g.pitch_e);
+        g.carBy = a.take<float2>((size_t)g.n_planes * g.MdE);
+        g.derotBy = a.take<float2>((size_t)g.n_planes * g.Md);
+        g.jBy = a.take<float2>((size_t)2 * g.n_planes);
     }
     g.chunk = chunk;
     return a.off;
@@ -297,11 +318,60 @@ static int fill_interp(TapTable& t, const float* bx, const float* by, int Rb, in
     return GPA_OK;
 }
 
+// Split pass 1, anchor stage (once per call): the anchor plane n_planes / 2 filtered by G_1 at the full rate,
+// decimated, with its carrier masked to the frame body (part 0) and to the wrapped columns (part 1).
+template <int S>
+static int launch_anchor_y(const MrGeometry& g, const float* img, const TapTable& t1y, cudaStream_t st) {
+    MrPass1Params p;
+    p.img = img; p.phy = g.phy; p.p1 = g.a_y; p.plane_stride = (size_t)g.rows_a * g.pitch_e;
+    p.N = g.N; p.M = g.M; p.Md = g.MdE; p.pitch_d = g.pitch_e; p.n_rows_filled = g.n_rows_filled;
+    p.Rax = g.row_shift; p.Ray = g.col_shift; p.J = g.J1y; p.plane0 = g.n_planes / 2; p.pstep = 0;
+    p.count = 2; p.planes_per_cta = 2;
+    constexpr int W1 = 8;
+    const size_t n_samp1 = (size_t)S * (W1 * kP + g.J1y + kAhead + 1);
+    const size_t smem = (n_samp1 * 33 + 1) * sizeof(float) + 2 * n_samp1 * sizeof(float2);
+    GPA_REQUIRE(smem <= 227 * 1024, "split pass 1: stage-A filter too long for shared memory (%zu bytes)", smem);
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1<S, W1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_e, W1 * kP), 1);
+    KernelTimer timer("k_mr_pass1a", st);
+    k_mr_pass1<S, W1, true><<<grid, W1 * 32, smem, st>>>(p, t1y);
+    GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
 template <int S>
 static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, const TapTable& tx, const TapTable& tb,
-                     const TapTable& t2, int plane0, int pstep, int count, int cand_mode, unsigned long long* key,
-                     cudaStream_t st) {
-    {   // stage 1
+                     const TapTable& t2, const TapTable& t2y, int plane0, int pstep, int count, int cand_mode,
+                     unsigned long long* key, cudaStream_t st) {
+    if (g.R1y > 0) {   // stage 1, split: coarse-rate stage per plane from the anchor plane (launch_anchor_y ran once per call)
+        MrPass1bParams p;
+        p.A = g.a_y; p.a_part = (size_t)g.rows_a * g.pitch_e; p.carB = g.carBy; p.derotB = g.derotBy; p.jB = g.jBy;
+        p.p1 = g.p1; p.plane_stride = g.plane_stride;
+        p.n_rows = g.n_rows_filled; p.Md = g.Md; p.MdE = g.MdE; p.pitch_d = g.pitch_d; p.pitch_e = g.pitch_e;
+        p.H = g.Hy; p.EB = ceil_div(g.R1y, S) + 1; p.plane0 = plane0; p.pstep = pstep; p.count = count;
+        const int JB = 2 * g.Hy + 1;
+        const int TR = kWarps * kP + JB - 1;
+        const size_t smem = (size_t)(2 * TR * 33 + 2 * TR + 2 * kWarps * kP) * sizeof(float2);
+        const int tiles = ceil_div(g.n_rows_filled, 32) * ceil_div(g.pitch_d, kWarps * kP);
+        int zs = ceil_div(2 * 296, tiles);                 // >= ~2 waves of CTAs
+        if (zs > count) zs = count;
+        if (zs < 1) zs = 1;
+        p.planes_per_cta = ceil_div(count, zs);
+        dim3 grid(ceil_div(g.n_rows_filled, 32), ceil_div(g.pitch_d, kWarps * kP), ceil_div(count, p.planes_per_cta));
+        KernelTimer timer("k_mr_pass1b", st);
+#define GPA_P1B(JBV)                                                                                                    \
+    case JBV:                                                                                                           \
+        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_pass1b<JBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        k_mr_pass1b<JBV><<<grid, kWarps * 32, smem, st>>>(p, t2y);                                                      \
+        break;
+        switch (JB) {
+            GPA_P1B(13) GPA_P1B(15) GPA_P1B(17) GPA_P1B(19) GPA_P1B(21) GPA_P1B(23)
+            default:
+                set_error("split pass 1: unsupported coarse tap count %d", JB);
+                return GPA_ERR_INVALID;
+        }
+#undef GPA_P1B
+    } else {   // stage 1
         MrPass1Params p;
         p.img = img; p.phy = g.phy; p.p1 = g.p1; p.plane_stride = g.plane_stride;
         p.N = g.N; p.M = g.M; p.Md = g.Md; p.pitch_d = g.pitch_d; p.n_rows_filled = g.n_rows_filled;
@@ -445,13 +515,14 @@ extern "C" int gpa_set_pruning(int on) {
 }
 
 extern "C" int gpa_sweep_mr_workspace_bytes(int N, int M, int n_rows, int n_planes, int cand_mode, int S, int Rax,
-                                            int Ray, int Rb, int R1x, int H2x, int planes_in_flight, size_t* bytes) {
+                                            int Ray, int Rb, int R1x, int H2x, int R1y, int H2y, int planes_in_flight,
+                                            size_t* bytes) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x, R1y, H2y);
     if (rc) return rc;
     GPA_REQUIRE(bytes != nullptr, "bytes is null");
     GPA_REQUIRE(planes_in_flight >= 1 && planes_in_flight <= n_planes, "planes_in_flight out of range");
-    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 1024 + 4096;
+    *bytes = carve_mr(g, nullptr, 0, planes_in_flight) + (size_t)planes_in_flight * 1024 + 8192;
     return GPA_OK;
 }
 
@@ -460,10 +531,13 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
                                    int plane_end, int plane_step, int S, const float* taps_ax, int Rax, const float* taps_ay, int Ray,
                                    const float* taps_bx, const float* taps_by, int Rb, const float* taps_1x, int R1x,
                                    const float* taps_2x, int H2x, double sigma_a, double sigma_1,
+                                   const float* taps_1y, int R1y, const float* taps_2y, int H2y, double sigma_1y,
                                    unsigned long long* key, void* ws, size_t ws_bytes, void* stream) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x, R1y, H2y);
     if (rc) return rc;
+    GPA_REQUIRE(R1y == 0 || (taps_1y && taps_2y && sigma_1y > 0.0 && sigma_1y < sigma_a),
+                "split pass 1 needs both tap sets and 0 < sigma_1y < sigma_a");
     GPA_REQUIRE(R1x == 0 || (taps_1x && taps_2x && sigma_1 > 0.0 && sigma_1 < sigma_a),
                 "split pass 2 needs both tap sets and 0 < sigma_1 < sigma_a");
     if ((rc = check_common(img, wx_rows, wy_planes, n_rows, n_planes, cand_mode, plane_begin, plane_end, ws))) return rc;
@@ -484,6 +558,12 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
     std::memset(&t2, 0, sizeof(t2));
     if (split)
         for (int j = 0; j < 2 * H2x + 1; ++j) t2.g[j] = make_float2(taps_2x[j], taps_2x[j]);
+    TapTable t1y, t2y;
+    std::memset(&t2y, 0, sizeof(t2y));
+    if (g.R1y > 0) {
+        if ((rc = fill_polyphase(t1y, taps_1y, R1y, S, g.J1y))) return rc;
+        for (int j = 0; j < 2 * H2y + 1; ++j) t2y.g[j] = make_float2(taps_2y[j], taps_2y[j]);
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {   // carrier tables: same kernel as the direct path, padded-row layout of the decimating stage
         Geometry t;
@@ -504,12 +584,29 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
         k_build_split_tables<<<grid, 256, 0, st>>>(tp);
         GPA_CHECK_CUDA(cudaGetLastError());
     }
+    if (g.R1y > 0) {   // split pass 1: per-plane coarse carriers relative to the anchor plane, then the anchor stage
+        SplitTabParams tp;
+        tp.phx1 = nullptr; tp.carB = g.carBy; tp.derotB = g.derotBy; tp.jB = g.jBy; tp.wx_d = g.wy_d;
+        tp.wx0 = wy_planes[n_planes / 2];
+        const double s2sq = sigma_a * sigma_a - sigma_1y * sigma_1y;
+        tp.ratio = sigma_a * sigma_a / s2sq;
+        tp.cexp = 2.0 * 9.869604401089358 * sigma_a * sigma_a * sigma_1y * sigma_1y / s2sq;
+        tp.n_cand = n_planes; tp.N = M; tp.S = S; tp.H = g.Hy; tp.Nd = g.Md; tp.NdE = g.MdE; tp.n_alloc = 0;
+        tp.Rtot = g.col_shift;
+        dim3 grid(ceil_div(g.MdE, 256) < 8 ? ceil_div(g.MdE, 256) : 8, n_planes);     // no (n_cand + 1)-th block: phx1 is not built
+        k_build_split_tables<<<grid, 256, 0, st>>>(tp);
+        GPA_CHECK_CUDA(cudaGetLastError());
+        if (S == 2) rc = launch_anchor_y<2>(g, img, t1y, st);
+        else if (S == 4) rc = launch_anchor_y<4>(g, img, t1y, st);
+        else rc = launch_anchor_y<8>(g, img, t1y, st);
+        if (rc) return rc;
+    }
     for (int i0 = 0; i0 < total; i0 += chunk) {
         const int cnt = total - i0 < chunk ? total - i0 : chunk;
         const int p0 = plane_begin + i0 * plane_step;
-        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
-        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
-        else rc = launch_mr<8>(g, img, ty, tx, tb, t2, p0, plane_step, cnt, cand_mode, key, st);
+        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
+        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
+        else rc = launch_mr<8>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
         if (rc) break;
     }
     g_gossip.n = 0;      // one call per arming
@@ -518,12 +615,12 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
 
 static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes, int n_planes, int cand_mode,
                        int plane_begin, int plane_end, int plane_step, int S, int Rax, int Ray, const float* taps_bx,
-                       const float* taps_by, int Rb, int R1x, int H2x, const unsigned long long* key, double kref_x,
+                       const float* taps_by, int Rb, int R1x, int H2x, int R1y, int H2y, const unsigned long long* key, double kref_x,
                        double kref_y, int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx,
                        void* const* lockin_dst, void* const* grad_dst, int n_dst, int dst_rows, int write_zero, void* ws,
                        size_t ws_bytes, void* stream) {
     MrGeometry g;
-    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x);
+    int rc = plan_mr(g, N, M, n_rows, n_planes, cand_mode, S, Rax, Ray, Rb, R1x, H2x, R1y, H2y);
     if (rc) return rc;
     GPA_REQUIRE(wx_rows && wy_planes && ws && key && (lockin || n_dst > 0), "null pointer argument");
     GPA_REQUIRE(0 <= plane_begin && plane_begin <= plane_end && plane_end <= n_planes, "bad plane range");
@@ -611,12 +708,12 @@ static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const do
 extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
                                      int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
                                      int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
-                                     int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
+                                     int R1x, int H2x, int R1y, int H2y, const unsigned long long* key, double kref_x, double kref_y,
                                      int grad_mode, int out_f64, void* lockin, void* grad, void* w, int* kidx, void* ws,
                                      size_t ws_bytes, void* stream) {
     GPA_REQUIRE(lockin != nullptr, "null pointer argument");
     return finalize_mr(N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, plane_begin, plane_end, plane_step, S, Rax, Ray,
-                       taps_bx, taps_by, Rb, R1x, H2x, key, kref_x, kref_y, grad_mode, out_f64, lockin, grad, w, kidx,
+                       taps_bx, taps_by, Rb, R1x, H2x, R1y, H2y, key, kref_x, kref_y, grad_mode, out_f64, lockin, grad, w, kidx,
                        nullptr, nullptr, 0, 0, 0, ws, ws_bytes, stream);
 }
 
@@ -624,13 +721,13 @@ extern "C" int gpa_sweep_finalize_mr(int N, int M, const double* wx_rows, int n_
 extern "C" int gpa_sweep_finalize_mr_sharded(int N, int M, const double* wx_rows, int n_rows, const double* wy_planes,
                                              int n_planes, int cand_mode, int plane_begin, int plane_end, int plane_step,
                                              int S, int Rax, int Ray, const float* taps_bx, const float* taps_by, int Rb,
-                                             int R1x, int H2x, const unsigned long long* key, double kref_x, double kref_y,
+                                             int R1x, int H2x, int R1y, int H2y, const unsigned long long* key, double kref_x, double kref_y,
                                              int grad_mode, int out_f64, void* const* lockin_dst, void* const* grad_dst,
                                              int n_dst, int dst_rows, int write_zero, void* ws, size_t ws_bytes,
                                              void* stream) {
     GPA_REQUIRE(n_dst >= 1, "n_dst must be >= 1");
     return finalize_mr(N, M, wx_rows, n_rows, wy_planes, n_planes, cand_mode, plane_begin, plane_end, plane_step, S, Rax, Ray,
-                       taps_bx, taps_by, Rb, R1x, H2x, key, kref_x, kref_y, grad_mode, out_f64, nullptr, nullptr, nullptr,
+                       taps_bx, taps_by, Rb, R1x, H2x, R1y, H2y, key, kref_x, kref_y, grad_mode, out_f64, nullptr, nullptr, nullptr,
                        nullptr, lockin_dst, grad_dst, n_dst, dst_rows, write_zero, ws, ws_bytes, stream);
 }
 

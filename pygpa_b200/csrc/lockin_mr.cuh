@@ -32,7 +32,10 @@ struct MrPass1Params {
 // The image tile is plane independent, so it is staged ONCE per CTA as raw float samples
 // (transposed, pitch 33) and the CTA loops over `planes_per_cta` planes; per plane only the
 // carrier of the tile columns is staged (double buffered) and applied on the fly (2 FMUL/sample).
-template <int S, int WARPS>
+// ANCHOR (split pass 1): the two "planes" of the launch are the anchor plane prm.plane0 demodulated with its
+// carrier masked to the frame body (pl = 0) and to the columns that wrapped around the frame edge (pl = 1);
+// prm.Ray is then the column shift R_1 + S H and prm.Md / pitch_d describe the extended coarse axis.
+template <int S, int WARPS, bool ANCHOR = false>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
     extern __shared__ float smem_f[];
@@ -60,12 +63,18 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
     const int pl0 = blockIdx.z * prm.planes_per_cta;
     const int pl1 = min(pl0 + prm.planes_per_cta, prm.count);
     auto stage_carrier = [&](int pl, int slot) {
-        const float2* __restrict__ phy = prm.phy + (size_t)(prm.plane0 + pl * prm.pstep) * M;
+        const float2* __restrict__ phy = prm.phy + (size_t)(ANCHOR ? prm.plane0 : prm.plane0 + pl * prm.pstep) * M;
         float2* dst = car + slot * n_samp;
         for (int j = threadIdx.x; j < n_samp; j += WARPS * 32) {
             int c = cbase + j;
             if (c >= M) c %= M;
-            dst[j] = __ldg(phy + c);
+            float2 v = __ldg(phy + c);
+            if constexpr (ANCHOR) {
+                const int yu = S * m0 - prm.Ray + j;                 // unwrapped frame column of sample j
+                const bool body = yu >= 0 && yu < M;
+                if (body != (pl == 0)) v = make_float2(0.f, 0.f);
+            }
+            dst[j] = v;
         }
     };
     stage_carrier(pl0, 0);
@@ -99,6 +108,133 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
             }
         }
         __syncthreads();
+    }
+}
+
+// Split pass 1, coarse-rate stage (the y twin of k_mr_pass2b): all planes of a peak differ only in wy, so ONE
+// anchor plane A_y(r, e) (k_mr_pass1<.., ANCHOR>, body / wrapped-column parts) is filtered at the full rate and
+// every plane costs a JB-tap filter along the coarse axis:
+//   P1[wy](r, my) = c e^{2 pi i (dw - delta) S my} sum_j h[j] e^{2 pi i delta S (my + j - H)} (A_body + J A_edge)(r, my + j)
+// CTA: 32 padded rows (lane = row) x kWarps kP coarse output columns (warp w owns columns [w kP, w kP + kP)); the A tile is
+// staged once (transposed, pitch 33) and the CTA loops over its share of the chunk's planes.
+struct MrPass1bParams {
+    const float2* A;        // [2][n_rows][pitch_e]
+    size_t a_part;          // elements between the body and the edge part
+    const float2* carB;     // [n_planes][MdE]   indexed by GLOBAL plane
+    const float2* derotB;   // [n_planes][Md]
+    const float2* jB;       // [n_planes][2]
+    float2* p1;             // [chunk][n_alloc][pitch_d]
+    size_t plane_stride;
+    int n_rows, Md, MdE, pitch_d, pitch_e, H, EB, plane0, pstep, count, planes_per_cta;
+};
+
+template <int JB>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k_mr_pass1b(const MrPass1bParams prm, const __grid_constant__ TapTable taps) {
+    constexpr int TO = kWarps * kP;            // output columns per CTA
+    constexpr int TR = TO + JB - 1;            // A columns per CTA
+    constexpr int NT = kWarps * 32;
+    constexpr int SP = 33;
+    extern __shared__ float2 smem[];
+    float2* const tB = smem;                   // [TR][SP]
+    float2* const tE = tB + TR * SP;           // [TR][SP]
+    float2* const scar = tE + TR * SP;         // [2][TR]
+    float2* const sder = scar + 2 * TR;        // [2][TO]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32;
+    const int m0 = blockIdx.y * TO;
+    const int Md = prm.Md, MdE = prm.MdE;
+    const float2 zero = make_float2(0.f, 0.f);
+    const int lo_end = prm.H + prm.EB, hi_begin = Md + prm.H - prm.EB;     // A_edge is zero on columns [lo_end, hi_begin)
+    {
+        const bool cta_edge = m0 < lo_end || m0 + TR > hi_begin;
+        for (int rr = warp; rr < 32; rr += kWarps) {
+            const int row = r0 + rr;
+            const float2* __restrict__ Ab = prm.A + (size_t)row * prm.pitch_e + m0;
+            const float2* __restrict__ Ae = Ab + prm.a_part;
+            for (int j = lane; j < TR; j += 32) {
+                if (row < prm.n_rows && m0 + j < MdE) {
+                    cp_async8(tB + j * SP + rr, Ab + j);
+                    if (cta_edge) cp_async8(tE + j * SP + rr, Ae + j);
+                } else {
+                    tB[j * SP + rr] = zero;
+                    if (cta_edge) tE[j * SP + rr] = zero;
+                }
+            }
+        }
+        cp_async_commit();
+    }
+    const int pl0 = blockIdx.z * prm.planes_per_cta;
+    const int pl1 = min(pl0 + prm.planes_per_cta, prm.count);
+    auto stage = [&](int pl, int slot) {
+        const int plane = prm.plane0 + pl * prm.pstep;
+        for (int j = threadIdx.x; j < TR + TO; j += NT) {
+            if (j < TR) {
+                const int e = m0 + j;
+                if (e < MdE) cp_async8(scar + slot * TR + j, prm.carB + (size_t)plane * MdE + e);
+                else scar[slot * TR + j] = zero;
+            } else {
+                const int my = m0 + j - TR;
+                if (my < Md) cp_async8(sder + slot * TO + j - TR, prm.derotB + (size_t)plane * Md + my);
+                else sder[slot * TO + j - TR] = zero;
+            }
+        }
+        cp_async_commit();
+    };
+    if (pl0 < pl1) stage(pl0, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    const int e0 = m0 + warp * kP;                                   // first A column of this warp
+    const bool edge = e0 < lo_end || e0 + kP + JB - 1 > hi_begin;   // warp-uniform
+    const int e_mid = prm.H + Md / 2;
+    const float2* colB = tB + (warp * kP) * SP + lane;
+    const float2* colE = tE + (warp * kP) * SP + lane;
+    const int r = r0 + lane;
+    const int m = m0 + warp * kP;
+    float2 g[JB];
+#pragma unroll
+    for (int j = 0; j < JB; ++j) g[j] = taps.g[j];
+    int slot = 0;
+    for (int pl = pl0; pl < pl1; ++pl, slot ^= 1) {
+        if (pl + 1 < pl1) stage(pl + 1, slot ^ 1);
+        const float2* car = scar + slot * TR + warp * kP;
+        float2 acc[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) acc[p] = zero;
+        if (!edge) {
+#pragma unroll
+            for (int k = 0; k < kP + JB - 1; ++k) {
+                const float2 smp = cmul(colB[k * SP], car[k]);
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+                    if (k - p >= 0 && k - p < JB) acc[p] = __ffma2_rn(g[k - p], smp, acc[p]);
+            }
+        } else {
+            const int plane = prm.plane0 + pl * prm.pstep;
+            const float2 jlo = __ldg(prm.jB + 2 * plane), jhi = __ldg(prm.jB + 2 * plane + 1);
+#pragma unroll
+            for (int k = 0; k < kP + JB - 1; ++k) {
+                const float2 jj = (e0 + k < e_mid) ? jlo : jhi;
+                const float2 ed = cmul(colE[k * SP], jj);
+                const float2 bd = colB[k * SP];
+                const float2 smp = cmul(make_float2(bd.x + ed.x, bd.y + ed.y), car[k]);
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+                    if (k - p >= 0 && k - p < JB) acc[p] = __ffma2_rn(g[k - p], smp, acc[p]);
+            }
+        }
+        const float2* der = sder + slot * TO + warp * kP;
+        if (r < prm.n_rows) {
+            float2* out = prm.p1 + (size_t)pl * prm.plane_stride + (size_t)r * prm.pitch_d + m;
+#pragma unroll
+            for (int p = 0; p < kP; p += 2) {
+                const float2 v0 = cmul(acc[p], der[p]), v1 = cmul(acc[p + 1], der[p + 1]);
+                if (m + p + 1 < prm.pitch_d) *reinterpret_cast<float4*>(out + p) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                else if (m + p < prm.pitch_d) out[p] = v0;
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();      // the next plane's rows are complete; this one's are no longer read
     }
 }
 

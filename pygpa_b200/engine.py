@@ -125,7 +125,7 @@ class SweepPlan:
     """Geometry + scratch of one sweep call (candidate axes, taps, workspace)."""
 
     def __init__(self, shape, wx_rows, wy_planes, sigma, cand_mode=CAND_GRID, trunc=DEFAULT_TRUNC,
-                 planes_in_flight=None, device=None, method="auto", private_ws=False):
+                 planes_in_flight=None, device=None, method="auto", private_ws=False, split_y=True):
         self.device = device or require_cuda()
         self._private = bool(private_ws)       # own scratch: what argmax() leaves survives other plans' calls
         self._ws = None
@@ -154,8 +154,11 @@ class SweepPlan:
         # split pass 2 (anchor stage shared by the candidates of a plane) when the grid is narrow enough;
         # 'multirate-single' keeps every candidate's own full-rate pass 2
         self.split = None
+        self.split_y = None                     # the same along axis 1: one anchor plane + a coarse-rate stage per plane
         if self.mr is not None and cand_mode == CAND_GRID and method != "multirate-single":
             self.split = split_taps(self.n, self.mr, self.wx)
+            if split_y:
+                self.split_y = split_taps(self.m, self.mr, self.wy)
         if self.mr is not None:
             self.mr_in_flight, self.mr_ws_bytes = self._plan_mr(planes_in_flight)
             self.ws_bytes = max(self.ws_bytes, self.mr_ws_bytes)
@@ -196,13 +199,16 @@ class SweepPlan:
         return (_lib.as_pf(self.tx), self.rx, _lib.as_pf(self.ty), self.ry)
 
     def _split_geom(self):
-        return (self.split["R1"], self.split["H"]) if self.split else (0, 0)
+        gx = (self.split["R1"], self.split["H"]) if self.split else (0, 0)
+        gy = (self.split_y["R1"], self.split_y["H"]) if self.split_y else (0, 0)
+        return gx + gy
 
     def _split_args(self):
-        sp = self.split
-        if not sp:
-            return (None, 0, None, 0, 0.0, 0.0)
-        return (_lib.as_pf(sp["taps_1"]), sp["R1"], _lib.as_pf(sp["taps_2"]), sp["H"], float(self.mr["sigma_a"]), sp["sigma_1"])
+        sp, spy = self.split, self.split_y
+        sa = float(self.mr["sigma_a"])
+        ax = (_lib.as_pf(sp["taps_1"]), sp["R1"], _lib.as_pf(sp["taps_2"]), sp["H"], sa, sp["sigma_1"]) if sp else (None, 0, None, 0, sa, 0.0)
+        ay = (_lib.as_pf(spy["taps_1"]), spy["R1"], _lib.as_pf(spy["taps_2"]), spy["H"], spy["sigma_1"]) if spy else (None, 0, None, 0, 0.0)
+        return ax + ay
 
     def argmax(self, img_dev, key, plane_begin=0, plane_end=None, plane_step=1):
         """key (N, M) int64 CUDA tensor, updated in place with the candidates of planes
@@ -220,7 +226,7 @@ class SweepPlan:
                                                *self._split_args(), _ptr(key), _ptr(ws), ws.numel(), _stream()))
             n_local = -(-(plane_end - plane_begin) // plane_step)
             chunks = -(-n_local // self.mr_in_flight) if plane_end > plane_begin else 0
-            _count(2 + (6 if self.split else 4) * chunks + (1 if self.split and chunks else 0))
+            _count(2 + (6 if self.split else 4) * chunks + (1 if self.split and chunks else 0) + (2 if self.split_y and chunks else 0))
             return
         _lib.check(lib.gpa_sweep_argmax(_ptr(img_dev), *self._geom(), plane_begin, plane_end, *self._taps(),
                                         _ptr(key), _ptr(ws), ws.numel(), _stream()))

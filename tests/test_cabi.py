@@ -75,14 +75,19 @@ def test_split_pass2_geometry_is_validated_without_a_gpu():
     lib = _lib.load()
     nbytes, single = ctypes.c_size_t(0), ctypes.c_size_t(0)
     base = (2048, 2048, 41, 41, 0, 4, 43, 43, 20)
-    assert lib.gpa_sweep_mr_workspace_bytes(*base, 0, 0, 41, ctypes.byref(single)) == 0
-    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 7, 41, ctypes.byref(nbytes)) == 0
+    assert lib.gpa_sweep_mr_workspace_bytes(*base, 0, 0, 0, 0, 41, ctypes.byref(single)) == 0
+    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 7, 0, 0, 41, ctypes.byref(nbytes)) == 0
     extra = nbytes.value - single.value
+    nbytes_x = nbytes.value
     assert 41 * 2 * (512 + 14) * 512 * 8 <= extra <= 41 * (2 * (512 + 14) * 512 + 600 * 512) * 8
-    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 12, 41, ctypes.byref(nbytes)) == -1       # more than 23 coarse taps
+    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 12, 0, 0, 41, ctypes.byref(nbytes)) == -1       # more than 23 coarse taps
     assert b"coarse radius" in lib.gpa_last_error()
-    assert lib.gpa_sweep_mr_workspace_bytes(2048, 2048, 41, 41, 1, 4, 43, 43, 20, 43, 7, 41, ctypes.byref(nbytes)) == -1   # k-list
-    assert lib.gpa_sweep_mr_workspace_bytes(88, 88, 41, 41, 0, 4, 43, 43, 20, 43, 7, 41, ctypes.byref(nbytes)) == -1       # edge bands overlap
+    assert lib.gpa_sweep_mr_workspace_bytes(2048, 2048, 41, 41, 1, 4, 43, 43, 20, 43, 7, 0, 0, 41, ctypes.byref(nbytes)) == -1   # k-list
+    assert lib.gpa_sweep_mr_workspace_bytes(88, 88, 41, 41, 0, 4, 43, 43, 20, 43, 7, 0, 0, 41, ctypes.byref(nbytes)) == -1       # edge bands overlap
+    both = ctypes.c_size_t(0)
+    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 7, 43, 7, 41, ctypes.byref(both)) == 0          # + split pass 1
+    assert 2 * 2192 * 544 * 8 <= both.value - nbytes_x <= 2 * 2208 * 544 * 8 + 3 * 41 * 600 * 8 + 8192
+    assert lib.gpa_sweep_mr_workspace_bytes(*base, 43, 7, 43, 12, 41, ctypes.byref(both)) == -1
     r1, h, s1 = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
     assert lib.gpa_split_plan(2048, 3, 8.98, None, 0, ctypes.byref(r1), ctypes.byref(h), ctypes.byref(s1), None, None) == -1
 

@@ -41,6 +41,12 @@ def _interp(c, taps, r, s, axis, n):
     return out
 
 
+def _split_pass1(img, wys, mr, sp):
+    """All planes P1[iy] (N, Md) from ONE anchor plane: the split applied along axis 1 (k_mr_pass1<ANCHOR> +
+    k_mr_pass1b).  The rows are independent, so this is _split_pass2 on the transposed problem with a real input."""
+    return [p.T for p in _split_pass2(img.T.astype(complex), wys, mr, sp)]
+
+
 def _split_pass2(p1, wxs, mr, sp):
     """All candidates' coarse grids P2[ix] (Nd, Md) from one anchor stage."""
     n = p1.shape[0]
@@ -88,14 +94,20 @@ def test_multirate_split_argmax_matches_oracle(shape, sigma, r_k, n_grid):
     mr = _taps.multirate_taps(n, m, float(sigma))
     assert mr is not None
     sp = _taps.split_taps(n, mr, wxs)
-    assert sp is not None, "this configuration is meant to exercise the split pass 2"
+    spy = _taps.split_taps(m, mr, wys)
+    assert sp is not None and spy is not None, "this configuration is meant to exercise both split passes"
     S, ra, rb = mr["S"], mr["Ra_x"], mr["Rb"]
     best = np.zeros(shape)
     bidx = np.full(shape, -1)
     y = np.arange(m)
     worst_p2 = 0.0
+    p1s = _split_pass1(img, wys, mr, spy)
+    worst_p1 = 0.0
     for iy, wy in enumerate(wys):
-        p1 = _dec_filter(img * np.exp(2j * np.pi * wy * y)[None, :], mr["taps_ay"].astype(np.float64), ra, S, 1)   # (n, m/S)
+        p1 = p1s[iy]                                                                                             # (n, m/S)
+        if iy in (0, len(wys) // 2, len(wys) - 1):
+            single = _dec_filter(img * np.exp(2j * np.pi * wy * y)[None, :], mr["taps_ay"].astype(np.float64), ra, S, 1)
+            worst_p1 = max(worst_p1, np.abs(p1 - single).max() / np.abs(single).max())
         p2s = _split_pass2(p1, wxs, mr, sp)
         for ix, wx in enumerate(wxs):
             if iy == len(wys) // 2 and ix in (0, len(wxs) - 1):     # against the single-stage pass 2, border rows included
@@ -107,6 +119,7 @@ def test_multirate_split_argmax_matches_oracle(shape, sigma, r_k, n_grid):
             take = (a2 > best) | ((a2 == best) & (idx < bidx) & (a2 > 0))
             best[take] = a2[take]
             bidx[take] = idx
+    assert worst_p1 < 1e-5, f"split pass 1 differs from the single-stage pass 1 by {worst_p1:.2e}"
     assert worst_p2 < 1e-5, f"split pass 2 differs from the single-stage pass 2 by {worst_p2:.2e}"
     same = bidx == ref["kidx"]
     gap = (ref["amp1"] - ref["amp2"]) / np.maximum(ref["amp1"], 1e-300)

@@ -496,14 +496,18 @@ def test_split_pass2_matches_single_stage(shape, n_grid):
     for k in ks[:2]:
         wxs, wys = engine.grid_axes(k[0], k[1], kw, kstep)
         split = engine.SweepPlan(shape, wxs, wys, 10, device=dev, method="multirate")
+        xonly = engine.SweepPlan(shape, wxs, wys, 10, device=dev, method="multirate", split_y=False)
         single = engine.SweepPlan(shape, wxs, wys, 10, device=dev, method="multirate-single")
-        assert split.split is not None and single.split is None
+        assert split.split is not None and split.split_y is not None and single.split is None and single.split_y is None
+        assert xonly.split is not None and xonly.split_y is None
         a = split.run(d_img, k, want_w=True, out_f64=True)
         b = single.run(d_img, k, want_w=True, out_f64=True)
+        c = xonly.run(d_img, k, want_w=True, out_f64=True)
         ref = oracle.wfr_sweep(img, 10, k[0], k[1], kw, kstep, return_diag=True)
         gap = (ref["amp1"] - ref["amp2"]) / ref["amp1"]
-        for r in (a, b):
+        for r in (a, b, c):
             check_sweep({key: r[key].cpu().numpy() for key in ("lockin", "w", "grad")}, ref)
+        assert np.all(gap[(a["kidx"] != c["kidx"]).cpu().numpy()] < NEAR_TIE)
         differ = (a["kidx"] != b["kidx"]).cpu().numpy()
         assert np.all(gap[differ] < NEAR_TIE)
         amp_a = (a["key"] >> 32).to(torch.int32).view(torch.float32).cpu().numpy()

@@ -8,7 +8,7 @@ size, ng = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2048,
 cfg = synth.make_config('C3', size=size, n_grid=ng)
 img = engine.image_to_device(cfg['image'], dev)
 ks = cfg['ks']
-names = ("k_mr_pass1", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize")
+names = ("k_mr_pass1", "k_mr_pass1a", "k_mr_pass1b", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize")
 res = {}
 keys = {}
 for method in ("multirate", "multirate-single", "multirate"):
