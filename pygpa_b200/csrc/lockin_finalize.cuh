@@ -218,59 +218,71 @@ __device__ __forceinline__ void mr_finalize_pixel(const MrFinalizeParams& mp, Ta
     // like the frame; the reference never uses the values beyond the frame edge, they are ignored).
     // The three positions span at most two adjacent coarse cells, so a 12 x 12 coarse window holds
     // every sample: row i <-> coarse row cx0 - HL + i, column j <-> cy0 - HL + j.
-    auto fdiv = [](int a, int b) { return (a >= 0 ? a : a - b + 1) / b; };
-    int offx[3], phx_[3], offy[3];
-    const int cx0 = fdiv(x - 1, S), cy0 = fdiv(y - 1, S);
-    float gy[3][kMrW];          // y taps of the three y positions aligned to the 12-column window
+    // One pass over the window with packed FFMA2 (real tap x complex sample), 2 MACs per sample instead of 3:
+    //   a_i  = sum_j gy_c[j] P[i][j]   -> s(x-1, y), s(x+1, y) = sum_i gx_{m,p}[i] a_i
+    //   C[j] = sum_i gx_c[i] P[i][j]   -> s(x, y-1), s(x, y), s(x, y+1) = sum_j gy_{m,c,p}[j] C[j]
+    constexpr int LOG = S == 2 ? 1 : (S == 4 ? 2 : 3);
+    static_assert((1 << LOG) == S, "stride must be 2, 4 or 8");
+    int offx[3], phx_[3], offy[3], phy_[3];
+    const int cx0 = (x - 1) >> LOG, cy0 = (y - 1) >> LOG;          // floor division (arithmetic shift)
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-        const int cx = fdiv(x - 1 + e, S), cy = fdiv(y - 1 + e, S);
+        const int cx = (x - 1 + e) >> LOG, cy = (y - 1 + e) >> LOG;
         offx[e] = cx - cx0;
         phx_[e] = x - 1 + e - S * cx;
         offy[e] = cy - cy0;
-        const int phy_ = y - 1 + e - S * cy;
-#pragma unroll
-        for (int j = 0; j < kMrW; ++j) {
-            const int v = j - offy[e];
-            gy[e][j] = (v >= 0 && v < kMrW - 1) ? tap(S * kMrW + phy_ * kMrW + v) : 0.f;
-        }
+        phy_[e] = y - 1 + e - S * cy;
     }
+    auto ytap = [&](int e, int j) -> float {       // y tap of position e aligned to the 12-column window
+        const int v = j - offy[e];
+        return (v >= 0 && v < kMrW - 1) ? tap(S * kMrW + phy_[e] * kMrW + v) : 0.f;
+    };
+    float2 gyc[kMrW];
     int colj[kMrW];
 #pragma unroll
     for (int j = 0; j < kMrW; ++j) {
-        int c = (cy0 - kMrHL + j) % Md;
-        colj[j] = c < 0 ? c + Md : c;
+        const float g = ytap(1, j);
+        gyc[j] = make_float2(g, g);
+        int c = cy0 - kMrHL + j;                    // in [-6, Md + 5]: one conditional wrap (Md >= 12)
+        if (c < 0) c += Md;
+        else if (c >= Md) c -= Md;
+        colj[j] = c;
     }
+    float2 C[kMrW];
+#pragma unroll
+    for (int j = 0; j < kMrW; ++j) C[j] = make_float2(0.f, 0.f);
     float2 s_xm = make_float2(0.f, 0.f), s_0 = s_xm, s_xp = s_xm, s_ym = s_xm, s_yp = s_xm;
 #pragma unroll 1
     for (int i = 0; i < kMrW; ++i) {
-        int r = (cx0 - kMrHL + i) % Nd;
+        int r = cx0 - kMrHL + i;
         if (r < 0) r += Nd;
+        else if (r >= Nd) r -= Nd;
         const float2* __restrict__ prow = P + (size_t)r * Md;
-        float2 rv[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) rv[d] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < kMrW; ++j) {
-            const float2 smp = __ldg(prow + colj[j]);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                rv[d].x = fmaf(gy[d][j], smp.x, rv[d].x);
-                rv[d].y = fmaf(gy[d][j], smp.y, rv[d].y);
-            }
-        }
-        // x taps are warp-uniform (a warp shares x)
         float gx[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             const int w = i - offx[e];
             gx[e] = (w >= 0 && w < kMrW - 1) ? tap(phx_[e] * kMrW + w) : 0.f;
         }
-        s_xm.x = fmaf(gx[0], rv[1].x, s_xm.x); s_xm.y = fmaf(gx[0], rv[1].y, s_xm.y);
-        s_0.x = fmaf(gx[1], rv[1].x, s_0.x);   s_0.y = fmaf(gx[1], rv[1].y, s_0.y);
-        s_xp.x = fmaf(gx[2], rv[1].x, s_xp.x); s_xp.y = fmaf(gx[2], rv[1].y, s_xp.y);
-        s_ym.x = fmaf(gx[1], rv[0].x, s_ym.x); s_ym.y = fmaf(gx[1], rv[0].y, s_ym.y);
-        s_yp.x = fmaf(gx[1], rv[2].x, s_yp.x); s_yp.y = fmaf(gx[1], rv[2].y, s_yp.y);
+        const float2 gxc = make_float2(gx[1], gx[1]);
+        float2 smp[kMrW];
+#pragma unroll
+        for (int j = 0; j < kMrW; ++j) smp[j] = __ldg(prow + colj[j]);
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kMrW; ++j) {
+            a = __ffma2_rn(gyc[j], smp[j], a);
+            C[j] = __ffma2_rn(gxc, smp[j], C[j]);
+        }
+        s_xm = __ffma2_rn(make_float2(gx[0], gx[0]), a, s_xm);
+        s_xp = __ffma2_rn(make_float2(gx[2], gx[2]), a, s_xp);
+    }
+#pragma unroll
+    for (int j = 0; j < kMrW; ++j) {
+        const float gm = ytap(0, j), gp = ytap(2, j);
+        s_0 = __ffma2_rn(gyc[j], C[j], s_0);
+        s_ym = __ffma2_rn(make_float2(gm, gm), C[j], s_ym);
+        s_yp = __ffma2_rn(make_float2(gp, gp), C[j], s_yp);
     }
     finalize_store<T2>(prm, pix, x, y, idx, row, plane, s_0, s_xm, s_xp, s_ym, s_yp);
 }
