@@ -468,6 +468,8 @@ class HostSweep:
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=self._seg_bytes)
             name[0] = self._shm.name
+            if self.world > 1:
+                _touch_interleaved(self._shm.buf, self._seg_bytes)
         if self.world > 1:
             dist.broadcast_object_list(name, src=0, group=group)
         if self.rank != 0:
@@ -565,6 +567,27 @@ class HostSweep:
         if self.rank == 0:
             self._shm.unlink()
         self._shm = None
+
+
+def _touch_interleaved(buf, nbytes):
+    """First-touch the pages of the shared result segment with the NUMA interleave policy, so that the GPUs of both
+    sockets write their rows into local memory half of the time instead of all funnelling into rank 0's node
+    (8 GPUs x PCIe gen5 otherwise queue behind one socket's memory controllers and the inter-socket link).
+    Best effort: without NUMA (or without the syscall) the pages are simply touched."""
+    import platform
+    arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+    libc = None
+    try:
+        if platform.machine() == "x86_64":
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(0xFFFF)                    # nodes 0..15; absent nodes are ignored by the kernel
+            if libc.syscall(238, 3, ctypes.byref(mask), 17) != 0:     # set_mempolicy(MPOL_INTERLEAVE, ...)
+                libc = None
+    except Exception:
+        libc = None
+    arr[::4096] = 0
+    if libc is not None:
+        libc.syscall(238, 0, None, 0)                        # back to MPOL_DEFAULT
 
 
 _sweeps = {}
