@@ -242,7 +242,8 @@ def run_ours(args, cfg):
         plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=world > 1))
     taps = 2 * plans[0].rx + 1
     transport = os.environ.get("GPA_TRANSPORT", "auto")
-    sweep = gdist.ShardedSweep(plans, ks, dst=0, transport=transport, gossip=os.environ.get("GPA_GOSSIP", "1") != "0") if world > 1 else None
+    sweep = gdist.ShardedSweep(plans, ks, dst=0, transport=transport, gossip=os.environ.get("GPA_GOSSIP", "1") != "0",
+                                two_phase=os.environ.get("GPA_TWO_PHASE", "0") == "1") if world > 1 else None
     # N > 1, frame stream: the caller's stream does not join the per-peak streams between frames (exactly like the single
     # stream of N = 1, nothing synchronises between the K steps), so the exchange tail of frame t overlaps frame t + 1;
     # multi_gpu.frame_latency_ms is the time of ONE isolated frame
@@ -382,6 +383,7 @@ def run_ours(args, cfg):
                 "frame_latency_ms": frame_latency_ms,
                 "pipelined_frames": bool(pipelined),
                 "threshold_gossip": bool(sweep.gossip),
+                "two_phase_sweep": bool(getattr(sweep, "two_phase", False)),
                 "exposed_tail_ms": max(max(r[p]["total_ms"] for p in range(len(ks))) - max(r[p]["argmax_ms"] for p in range(len(ks))) for r in every),
                 "k_key_merge_ms_per_step_rank0": kernels["k_key_merge"][0] / args.steps,
                 "check": check,

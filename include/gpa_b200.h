@@ -461,6 +461,18 @@ int gpa_key_to_w(const unsigned long long* key, size_t n, size_t comp_stride, co
  * (64-bit max over NVLink, tagged with the epoch: stale frames never match, nothing is ever reset).  Any published
  * value is a lower bound of the block's final winners, so results stay bit-identical to the unpruned sweep. */
 int gpa_sweep_arm_gossip(void* const* hint_ptrs /*host*/, int n_ranks, unsigned int epoch);
+/* Two-phase variant (call right after gpa_sweep_arm_gossip, same ordering of the ranks: entry 0 = this rank).  The next
+ * gpa_sweep_argmax_mr then (1) publishes, per tile of k_mr_interp, the largest bound any of its planes reaches into row
+ * `rank` of every rank's table best_ptrs[r] (float [n_ranks][tiles]), (2) after a flag barrier sweeps ONLY the tiles where
+ * it holds the globally most promising plane — the one CTA per tile a single GPU would run first, unpruned — and
+ * (3) after a second flag barrier everything else, against the thresholds phase (2) published through the gossip arrays.
+ * Without it every rank starts every tile unpruned: W unpruned plane sweeps per tile instead of one.
+ * flag_slots_a / _b: this rank's slot in every rank's flag array for the two barriers; wait_a / _b: this rank's own
+ * n_ranks slots (device); epoch as gpa_peer_signal; *status, timeout_s as gpa_peer_wait.  Applies only when the call
+ * sweeps its planes in one resident chunk. */
+int gpa_sweep_arm_two_phase(void* const* best_ptrs /*host*/, void* const* flag_slots_a /*host*/, void* const* flag_slots_b /*host*/,
+                            const unsigned long long* wait_a, const unsigned long long* wait_b, int rank,
+                            unsigned long long epoch, double timeout_s, int* status);
 /* gpa_sweep_finalize_mr for one rank's share of the planes with owner-writes: pixel (x, y) of a winner
  * this rank owns is stored to lockin_dst[x / dst_rows] and grad_dst[x / dst_rows] (host arrays of n_dst
  * device pointers to full (N, M) / (N, M, 2) arrays, local or peer-mapped; all pixels go to entry 0 when

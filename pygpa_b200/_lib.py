@@ -91,6 +91,8 @@ SIGNATURES = {
     "gpa_host_unregister": (c_int, [c_void_p]),
     "gpa_key_merge": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_size_t, c_void_p]),
     "gpa_sweep_arm_gossip": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.c_uint]),
+    "gpa_sweep_arm_two_phase": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                                        c_int, ctypes.c_ulonglong, c_double, c_void_p]),
     "gpa_key_to_w": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gpa_sweep_finalize_mr_sharded": (c_int, [c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                               _pf, _pf, c_int, c_int, c_int, c_int, c_int, c_void_p, c_double, c_double, c_int, c_int,

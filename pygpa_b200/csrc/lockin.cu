@@ -174,6 +174,16 @@ struct GossipArm {
     unsigned long long* hint[GPA_MAX_PEERS];
     int n = 0;
     unsigned epoch = 0;
+    // two-phase sweep (optional): tables of the tiles' best bounds, flag slots of the two barriers
+    bool two_phase = false;
+    unsigned long long epoch64 = 0;
+    int rank = 0;
+    float* best[GPA_MAX_PEERS];
+    void* flag_a[GPA_MAX_PEERS];
+    void* flag_b[GPA_MAX_PEERS];
+    const unsigned long long *wait_a = nullptr, *wait_b = nullptr;
+    int* status = nullptr;
+    double timeout_s = 20.0;
 };
 static thread_local GossipArm g_gossip;
 
@@ -342,7 +352,7 @@ static int launch_anchor_y(const MrGeometry& g, const float* img, const TapTable
 template <int S>
 static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, const TapTable& tx, const TapTable& tb,
                      const TapTable& t2, const TapTable& t2y, int plane0, int pstep, int count, int cand_mode,
-                     unsigned long long* key, cudaStream_t st) {
+                     unsigned long long* key, cudaStream_t st, bool whole_share) {
     if (g.R1y > 0) {   // stage 1, split: coarse-rate stage per plane from the anchor plane (launch_anchor_y ran once per call)
         MrPass1bParams p;
         p.A = g.a_y; p.a_part = (size_t)g.rows_a * g.pitch_e; p.carB = g.carBy; p.derotB = g.derotBy; p.jB = g.jBy;
@@ -472,23 +482,49 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         p.n_hint = p.prune ? g_gossip.n : 0;
         p.epoch = g_gossip.epoch;
         for (int r = 0; r < GPA_MAX_PEERS; ++r) p.hint[r] = r < g_gossip.n ? g_gossip.hint[r] : nullptr;
+        // two-phase sharded sweep: only when this launch covers the rank's whole share (one chunk)
+        const bool two_phase = p.prune && p.n_hint > 1 && g_gossip.two_phase && whole_share;
+        p.phase = 0; p.best_all = nullptr; p.rank = g_gossip.rank; p.world = g_gossip.n; p.z0 = 0;
         if (p.prune) {
             dim3 tg(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX));
+            OrderShare share;
+            share.n = two_phase ? g_gossip.n : 0;
+            share.rank = g_gossip.rank;
+            for (int r = 0; r < GPA_MAX_PEERS; ++r) share.best[r] = r < share.n ? g_gossip.best[r] : nullptr;
             KernelTimer timer("k_mr_order", st);
-            k_mr_order<S><<<tg, 256, 0, st>>>(g.pmax, g.n_cand, count, p.nbx, p.nby, g.nbx_alloc, g.nby_alloc, g.perm);
+            k_mr_order<S><<<tg, 256, 0, st>>>(g.pmax, g.n_cand, count, p.nbx, p.nby, g.nbx_alloc, g.nby_alloc, g.perm, share);
         }
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
         const size_t smem = (size_t)(2 * CX * CY + 2 * CY * (kMrTX + 1)) * sizeof(float2);
         dim3 grid(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX), count);
-        KernelTimer timer("k_mr_interp", st);
-        if (g.n_cand <= 256) {
-            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            k_mr_interp<S, 8><<<grid, 256, smem, st>>>(p, tb);
-        } else {
-            GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            k_mr_interp<S, 16><<<grid, 256, smem, st>>>(p, tb);
+        auto launch_interp = [&](dim3 gr) -> int {
+            KernelTimer timer("k_mr_interp", st);
+            if (g.n_cand <= 256) {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                k_mr_interp<S, 8><<<gr, 256, smem, st>>>(p, tb);
+            } else {
+                GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                k_mr_interp<S, 16><<<gr, 256, smem, st>>>(p, tb);
+            }
+            return GPA_OK;
+        };
+        int rc = GPA_OK;
+        if (two_phase) {
+            // barrier 1: every rank has published the best bounds of its tiles (k_mr_order above)
+            if ((rc = gpa_peer_signal(g_gossip.flag_a, g_gossip.n, g_gossip.epoch64, st)) ||
+                (rc = gpa_peer_wait(g_gossip.wait_a, g_gossip.n, g_gossip.epoch64, g_gossip.timeout_s, g_gossip.status, st)))
+                return rc;
+            p.best_all = g_gossip.best[0];          // entry 0 is this rank's own table
+            p.phase = 1;
+            if ((rc = launch_interp(dim3(grid.x, grid.y, 1)))) return rc;
+            // barrier 2: the globally most promising plane of every tile has been swept and its bounds published
+            if ((rc = gpa_peer_signal(g_gossip.flag_b, g_gossip.n, g_gossip.epoch64, st)) ||
+                (rc = gpa_peer_wait(g_gossip.wait_b, g_gossip.n, g_gossip.epoch64, g_gossip.timeout_s, g_gossip.status, st)))
+                return rc;
+            p.phase = 2;
         }
+        if ((rc = launch_interp(grid))) return rc;
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
@@ -506,6 +542,25 @@ extern "C" int gpa_sweep_arm_gossip(void* const* hint_ptrs, int n_ranks, unsigne
     }
     g_gossip.n = n_ranks;
     g_gossip.epoch = epoch;
+    g_gossip.two_phase = false;
+    return GPA_OK;
+}
+
+extern "C" int gpa_sweep_arm_two_phase(void* const* best_ptrs, void* const* flag_slots_a, void* const* flag_slots_b,
+                                       const unsigned long long* wait_a, const unsigned long long* wait_b, int rank,
+                                       unsigned long long epoch, double timeout_s, int* status) {
+    GPA_REQUIRE(g_gossip.n > 1, "gpa_sweep_arm_two_phase follows gpa_sweep_arm_gossip with n_ranks > 1");
+    GPA_REQUIRE(best_ptrs && flag_slots_a && flag_slots_b && wait_a && wait_b && status, "null pointer argument");
+    GPA_REQUIRE(rank >= 0 && rank < g_gossip.n && timeout_s > 0, "bad rank / timeout");
+    for (int r = 0; r < g_gossip.n; ++r) {
+        GPA_REQUIRE(best_ptrs[r] && flag_slots_a[r] && flag_slots_b[r], "null table / flag slot");
+        g_gossip.best[r] = static_cast<float*>(best_ptrs[r]);
+        g_gossip.flag_a[r] = flag_slots_a[r];
+        g_gossip.flag_b[r] = flag_slots_b[r];
+    }
+    g_gossip.wait_a = wait_a; g_gossip.wait_b = wait_b; g_gossip.rank = rank; g_gossip.epoch64 = epoch;
+    g_gossip.timeout_s = timeout_s; g_gossip.status = status;
+    g_gossip.two_phase = true;
     return GPA_OK;
 }
 
@@ -604,12 +659,14 @@ extern "C" int gpa_sweep_argmax_mr(const float* img, int N, int M, const double*
     for (int i0 = 0; i0 < total; i0 += chunk) {
         const int cnt = total - i0 < chunk ? total - i0 : chunk;
         const int p0 = plane_begin + i0 * plane_step;
-        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
-        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
-        else rc = launch_mr<8>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st);
+        const bool whole = cnt == total;
+        if (S == 2) rc = launch_mr<2>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st, whole);
+        else if (S == 4) rc = launch_mr<4>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st, whole);
+        else rc = launch_mr<8>(g, img, ty, tx, tb, t2, t2y, p0, plane_step, cnt, cand_mode, key, st, whole);
         if (rc) break;
     }
     g_gossip.n = 0;      // one call per arming
+    g_gossip.two_phase = false;
     return rc;
 }
 

@@ -651,6 +651,12 @@ struct MrInterpParams {
     unsigned long long* hint[GPA_MAX_PEERS];
     int n_hint;
     unsigned epoch;
+    // Two-phase sharded sweep (phase != 0): best_all[r * tiles + tile] = largest bound any plane of rank r reaches in the tile
+    // (k_mr_order, exchanged over peer memory).  Phase 1 runs only the z = 0 CTA (the rank's most promising plane) of the tiles
+    // where this rank holds the GLOBALLY most promising plane — unpruned, exactly the CTA a single GPU would run first — and
+    // publishes its block bounds to every rank; phase 2 runs everything else against those thresholds.
+    const float* best_all;
+    int phase, rank, world, z0;
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
@@ -668,9 +674,15 @@ constexpr int kMaxPruneCand = 2048;   // candidates per plane that the survivor 
 // inside the tile (max over candidates and over the tile's coarse-window blocks of pmax), most
 // promising first.  CTA (tile, z) of k_mr_interp then handles plane perm[tile][z], so the z = 0 wave
 // already records near-final winners in `key` and every later CTA prunes against tight thresholds.
+struct OrderShare {            // two-phase sharded sweep: where to publish the tile's best bound (row `rank` of every rank's table)
+    float* best[GPA_MAX_PEERS];
+    int n, rank;
+};
+
 template <int S>
 __global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax, int n_cand, int count, int nbx, int nby,
-                                                  int nbx_alloc, int nby_alloc, unsigned short* __restrict__ perm) {
+                                                  int nbx_alloc, int nby_alloc, unsigned short* __restrict__ perm,
+                                                  const OrderShare share) {
     constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
     __shared__ float bound[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -704,6 +716,10 @@ __global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax
         int rank = 0;
         for (int q = 0; q < count; ++q) rank += (bound[q] > b) || (bound[q] == b && q < pl);
         perm[(size_t)tile * count + rank] = (unsigned short)pl;
+        if (rank == 0 && share.n > 0) {        // this plane leads the tile: tell every rank how promising it is
+            const size_t slot = (size_t)share.rank * (gridDim.x * gridDim.y) + tile;
+            for (int r = 0; r < share.n; ++r) share.best[r][slot] = b;
+        }
     }
 }
 
@@ -730,6 +746,16 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     float2* const p3t0 = smem + 2 * CX * CY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
+    if (prm.phase != 0 && blockIdx.z == 0) {
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x, tiles = gridDim.x * gridDim.y;
+        const float mine = prm.best_all[(size_t)prm.rank * tiles + tile];
+        bool global_best = true;
+        for (int r = 0; r < prm.world; ++r) {
+            const float v = prm.best_all[(size_t)r * tiles + tile];
+            if (v > mine || (v == mine && r < prm.rank)) global_best = false;
+        }
+        if ((prm.phase == 1) != global_best) return;      // phase 1: only the global best; phase 2: every other first CTA
+    }
     // with pruning every tile visits the planes in its own order, most promising first (k_mr_order)
     const int pl = prm.prune ? (int)prm.perm[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * prm.count + blockIdx.z]
                              : (int)blockIdx.z;

@@ -109,7 +109,7 @@ def merge_payload(tensors, group=None):
 # ----------------------------------------------------------------------------------------------
 # the sharded sweep
 # ----------------------------------------------------------------------------------------------
-_PH_ARGMAX, _PH_MERGED, _PH_DELIVERED = 0, 1, 2
+_PH_ARGMAX, _PH_MERGED, _PH_DELIVERED, _PH_BOUNDS, _PH_WAVE0 = 0, 1, 2, 3, 4
 _FLAG_BYTES = 4096
 
 
@@ -129,7 +129,7 @@ class ShardedSweep:
     this rank ((0, 0) on a rank that is not a destination)."""
 
     def __init__(self, plans, krefs, group=None, dst=0, out_f64=False, want_w=False, transport="auto", timeout_s=20.0,
-                 gossip=True):
+                 gossip=True, two_phase=False):
         from . import _lib
         self.plans, self.krefs, self.group = list(plans), [tuple(map(float, k)) for k in krefs], group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -174,7 +174,7 @@ class ShardedSweep:
         cb, rb = (16, 8) if self.out_f64 else (8, 4)
         if transport == "peer":
             from .peer import PeerArena
-            if 3 * P * 64 > 2048:
+            if 5 * P * 64 > 2048:
                 raise ValueError("too many peaks for the flag block")
             off_key = _FLAG_BYTES
             off_lock = off_key + P * n * m * 8
@@ -184,9 +184,18 @@ class ShardedSweep:
             blk = 8 * self.plans[0].mr["S"]
             self._hint_n = (n // blk) * (m // blk) if all(p.mr["S"] * 8 == blk for p in self.plans) and n % blk == 0 and m % blk == 0 else 0
             self.gossip = bool(gossip) and world > 1 and self._hint_n > 0
-            total = off_hint + (-(-P * self._hint_n * 8 // 256) * 256 if self.gossip else 0)
+            off_best = off_hint + (-(-P * self._hint_n * 8 // 256) * 256 if self.gossip else 0)
+            # two-phase sweep (gpa_sweep_arm_two_phase; OFF by default: measured on 8 GPUs it gains nothing over the plain
+            # gossip — 3.144 vs 3.140 ms per C3 step — because block-minimum bounds of single planes stay ~0.1-0.5 % below
+            # the key-based thresholds of one GPU and the two extra flag barriers per peak cost what the better start saves):
+            # per peak a float table [world][tiles of k_mr_interp (64 x 128 pixels)]
+            self._tiles = (-(-n // 64)) * (-(-m // 128))
+            # every rank must take part in the two flag barriers of every peak: only when no share is empty
+            everybody = all(hi > lo for r in range(world) for lo, hi, _st in shard_units_interleaved(self.n_peaks, counts, world, r))
+            self.two_phase = self.gossip and bool(two_phase) and everybody and self.ranges is inter
+            total = off_best + (-(-P * world * self._tiles * 4 // 256) * 256 if self.two_phase else 0)
             self.arena = PeerArena(total, group=group, device=self.dev)
-            self._off = {"key": off_key, "lockin": off_lock, "grad": off_grad, "hint": off_hint}
+            self._off = {"key": off_key, "lockin": off_lock, "grad": off_grad, "hint": off_hint, "best": off_best}
             self.keys = self.arena.tensor(off_key, (P, n, m), torch.int64)
             self.lockin = self.arena.tensor(off_lock, (P, n, m), torch.complex128 if self.out_f64 else torch.complex64)
             self.grad = self.arena.tensor(off_grad, (P, n, m, 2), torch.float64 if self.out_f64 else torch.float32)
@@ -328,6 +337,15 @@ class ShardedSweep:
                     order = [rank] + [r for r in everyone if r != rank]
                     hp = (ctypes.c_void_p * world)(*[self.arena.addr(r, self._off["hint"] + p * self._hint_n * 8) for r in order])
                     _lib.check(lib.gpa_sweep_arm_gossip(hp, world, self.epoch & 0xFFFFFFFF))
+                    if self.two_phase:
+                        vp = ctypes.c_void_p * world
+                        bp = vp(*[self.arena.addr(r, self._off["best"] + p * world * self._tiles * 4) for r in order])
+                        fa = vp(*[self.arena.addr(r, self._flag_off(_PH_BOUNDS, p, rank)) for r in order])
+                        fb = vp(*[self.arena.addr(r, self._flag_off(_PH_WAVE0, p, rank)) for r in order])
+                        _lib.check(lib.gpa_sweep_arm_two_phase(
+                            bp, fa, fb, ctypes.c_void_p(self.arena.addr(rank, self._flag_off(_PH_BOUNDS, p))),
+                            ctypes.c_void_p(self.arena.addr(rank, self._flag_off(_PH_WAVE0, p))), rank, self.epoch,
+                            self.timeout_s, engine._ptr(self._status)))
                 plan.argmax(img_dev, self.keys[p], lo, hi, step)
             self._mark(p, "argmax")
             if world > 1:

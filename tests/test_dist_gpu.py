@@ -46,8 +46,10 @@ def _worker(rank, world, port, img, ks, kw, kstep, sigma, out_dir):
             plans.append(engine.SweepPlan(d_img.shape, wxs, wys, sigma, device=dev, private_ws=True))
         single = [p.run(d_img, k, want_w=True) for p, k in zip(plans, ks)]
         single = [{k_: (v.clone() if v is not None else None) for k_, v in o.items()} for o in single]
-        for transport, dst in (("peer", 0), ("peer", "rows"), ("collective", None), ("collective", 0)):
-            sw = gdist.ShardedSweep(plans, ks, dst=dst, want_w=True, transport=transport, timeout_s=5.0)
+        for transport, dst in (("peer", 0), ("peer", "rows"), ("peer2", 0), ("collective", None), ("collective", 0)):
+            # "peer2": the two-phase variant of the threshold exchange (gpa_sweep_arm_two_phase)
+            sw = gdist.ShardedSweep(plans, ks, dst=dst, want_w=True, transport=transport.rstrip("2"), timeout_s=5.0,
+                                    two_phase=transport == "peer2")
             for rep in range(3):        # epochs: the flags are never reset
                 outs = sw(d_img, join=rep != 1)     # a frame stream may skip the join between frames
             torch.cuda.synchronize()
@@ -77,7 +79,7 @@ def test_two_gpu_sharded_sweep_bit_identical(tmp_path):
             assert all(res.values()), f"{transport} dst={dst} peak {p} rank {r} rows {rows}: {res}"
             seen.add((transport, dst, r))
     # rank 0 checked every configuration, rank 1 its row slice
-    assert {("peer", "0", 0), ("peer", "rows", 0), ("peer", "rows", 1), ("collective", "None", 0),
+    assert {("peer", "0", 0), ("peer", "rows", 0), ("peer", "rows", 1), ("peer2", "0", 0), ("collective", "None", 0),
             ("collective", "None", 1), ("collective", "0", 0)} <= seen
 
 
