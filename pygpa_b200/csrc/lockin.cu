@@ -115,11 +115,7 @@ static int launch_pass1(const Geometry& g, const float* img, const TapTable& ty,
     p.N = g.N; p.M = g.M; p.pitch = g.pitch; p.n_rows_filled = g.N + 2 * g.Rx;
     p.Rx = g.Rx; p.Ry = g.Ry; p.T = g.Ty; p.plane0 = plane0;
     const size_t smem = (size_t)(kTile + g.Ty + kAhead) * 33 * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(ceil_div(p.n_rows_filled, 32), ceil_div(g.pitch, kTile), count);
     KernelTimer timer("k_pass1", st);
     k_pass1<<<grid, kWarps * 32, smem, st>>>(p, ty);
@@ -139,11 +135,7 @@ static int launch_pass2(const Geometry& g, const TapTable& tx, int plane0, int c
         p.n_cand = 1; p.row_c = 0; p.row_p = 1; p.idx_c = 0; p.idx_p = 1;
     }
     const size_t smem = (size_t)(kTile + g.Tx + kAhead) * kLanes * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(g.pitch / kLanes, ceil_div(g.N, kTile), count);
     KernelTimer timer(MODE == kArgmax ? "k_pass2_argmax" : "k_pass2_store", st);
     k_pass2<MODE><<<grid, kWarps * 32, smem, st>>>(p, tx);
@@ -929,11 +921,7 @@ extern "C" int gpa_wfr4_sweep(const float* img, int N, int M, const double* klis
     TapTable tx, ty;
     if ((rc = fill_taps(tx, taps_x, Rx)) || (rc = fill_taps(ty, taps_y, Ry))) return rc;
     if ((rc = build_tables(g, klist_x, klist_y, st))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(k_pass2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     for (int p0 = 0; p0 < K; p0 += chunk) {
         const int cnt = K - p0 < chunk ? K - p0 : chunk;
         if ((rc = launch_pass1(g, img, ty, p0, cnt, st))) return rc;
