@@ -148,6 +148,9 @@ int gpa_sweep_argmax(const float* img, int N, int M,
  * bound cannot beat the winners already recorded in `key` (exact branch and bound: results are
  * bit-identical with it on or off; it only changes how much work is done).  On by default. */
 int gpa_set_pruning(int on);
+/* Coarse-tile staging of k_mr_interp: TMA box loads (cp.async.bulk.tensor + mbarrier) for the tiles whose coarse window does
+ * not wrap around the frame (default on), per-element cp.async gathers otherwise / when off.  Results are identical. */
+int gpa_set_tma(int on);
 
 /* Split pass 2 (R1x > 0; candidate grids only).  All candidates of a plane share their full-rate
  * filtering: G_a = G_1 * G_2 (sigma_a^2 = sigma_1^2 + sigma_2^2), the plane is demodulated by the

@@ -1,5 +1,6 @@
 // Shared helpers for libgpa_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>

@@ -160,6 +160,19 @@ static int check_common(const float* img, const double* wx_rows, const double* w
 // multirate host side
 // ---------------------------------------------------------------------------------------------
 static int g_prune_enabled = 1;
+static int g_tma_enabled = 1;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled load_encode_tiled() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(fn);
+}
 
 // threshold gossip of a k-grid sharded sweep: armed by gpa_sweep_arm_gossip, consumed by the next gpa_sweep_argmax_mr
 struct GossipArm {
@@ -488,16 +501,34 @@ static int launch_mr(const MrGeometry& g, const float* img, const TapTable& ty, 
         }
         if (cand_mode == GPA_CAND_GRID) { p.idx_c = g.n_planes; p.idx_p = 1; } else { p.idx_c = 0; p.idx_p = 1; }
         constexpr int CX = kMrTX / S + kMrW - 2, CY = kMrTY / S + kMrW - 2;
-        const size_t smem = (size_t)(2 * CX * CY + 2 * CY * (kMrTX + 1)) * sizeof(float2);
+        constexpr size_t ctile = ((size_t)CX * (CY + 2) * 8 + 127) / 128 * 128;  // bytes per coarse buffer (TMA box: CY + 2 columns, 128-byte aligned)
+        const size_t smem = 2 * ctile + (size_t)(2 * CY * (kMrTX + 1)) * sizeof(float2);
+        // P2 as a 3-D tensor (2 Md floats, Nd, candidates x planes) for the TMA box loads of the interior tiles
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        p.use_tma = 0;
+        if (g_tma_enabled && (size_t)g.Md * 8 % 16 == 0 && (long long)count * g.n_cand < (1LL << 31)) {
+            static PFN_encodeTiled encode = load_encode_tiled();
+            if (encode != nullptr) {
+                const cuuint64_t dims[3] = {(cuuint64_t)2 * g.Md, (cuuint64_t)g.Nd, (cuuint64_t)count * g.n_cand};
+                const cuuint64_t strides[2] = {(cuuint64_t)g.Md * 8, (cuuint64_t)g.Nd * g.Md * 8};
+                const cuuint32_t box[3] = {2 * (CY + 2), CX, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)g.p2, dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                p.use_tma = cr == CUDA_SUCCESS;
+            }
+        }
         dim3 grid(ceil_div(g.M, kMrTY), ceil_div(g.N, kMrTX), count);
         auto launch_interp = [&](dim3 gr) -> int {
             KernelTimer timer("k_mr_interp", st);
             if (g.n_cand <= 256) {
                 GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                k_mr_interp<S, 8><<<gr, 256, smem, st>>>(p, tb);
+                k_mr_interp<S, 8><<<gr, 256, smem, st>>>(p, tb, tmap);
             } else {
                 GPA_CHECK_CUDA(cudaFuncSetAttribute(k_mr_interp<S, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                k_mr_interp<S, 16><<<gr, 256, smem, st>>>(p, tb);
+                k_mr_interp<S, 16><<<gr, 256, smem, st>>>(p, tb, tmap);
             }
             return GPA_OK;
         };
@@ -553,6 +584,11 @@ extern "C" int gpa_sweep_arm_two_phase(void* const* best_ptrs, void* const* flag
     g_gossip.wait_a = wait_a; g_gossip.wait_b = wait_b; g_gossip.rank = rank; g_gossip.epoch64 = epoch;
     g_gossip.timeout_s = timeout_s; g_gossip.status = status;
     g_gossip.two_phase = true;
+    return GPA_OK;
+}
+
+extern "C" int gpa_set_tma(int on) {
+    g_tma_enabled = on != 0;
     return GPA_OK;
 }
 

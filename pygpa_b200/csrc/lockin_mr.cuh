@@ -657,7 +657,31 @@ struct MrInterpParams {
     // publishes its block bounds to every rank; phase 2 runs everything else against those thresholds.
     const float* best_all;
     int phase, rank, world, z0;
+    int use_tma;           // the coarse tiles of interior CTAs come as one TMA box per candidate (tmap = P2 as a 3-D tensor)
 };
+
+// ---- TMA / mbarrier helpers (cp.async.bulk.tensor: SASS UTMALDG) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, unsigned long long* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                   "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -730,7 +754,7 @@ __global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax
 //   atomicMax per pixel.  IB = bits per packed winner index (8 when n_cand <= 256, else 16).
 template <int S, int IB>
 __global__ void __launch_bounds__(256, 2)
-k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
+k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, const __grid_constant__ CUtensorMap tmap) {
     constexpr int CX = kMrTX / S + kMrW - 2;        // coarse rows / columns held per candidate
     constexpr int CY = kMrTY / S + kMrW - 2;
     constexpr int NS = kP / S + kMrW - 2;           // coarse samples per 16 outputs
@@ -741,9 +765,14 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     constexpr int Q3 = S < 4 ? 8 : S;               // outputs per x-interpolation task (whole cells)
     constexpr int NS3 = Q3 / S + kMrW - 2;
     constexpr int N3 = CY * (kMrTX / Q3);           // x-interpolation tasks per candidate
-    extern __shared__ float2 smem[];
-    // smem: two coarse tiles [CX][CY] (cp.async targets), two x-interpolated tiles [CY][P3P]
-    float2* const p3t0 = smem + 2 * CX * CY;
+    extern __shared__ __align__(128) float2 smem[];
+    // smem: two coarse tiles [CX][CY] (cp.async / TMA targets, 128-byte aligned), two x-interpolated tiles [CY][P3P]
+    // TMA boxes must start on a 16-byte boundary of the global tensor: the window's first column c_lo = y0 / S - 5 is odd, so
+    // the box starts one column earlier and is CYB = CY + 2 columns wide (inner extent a multiple of 16 bytes)
+    constexpr int CYB = CY + 2;
+    constexpr int CTILE = (CX * CYB * 8 + 127) / 128 * 16;     // float2 elements between the two coarse buffers
+    float2* const p3t0 = smem + 2 * CTILE;
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y0 = blockIdx.x * kMrTY, x0 = blockIdx.y * kMrTX;
     if (prm.phase != 0 && blockIdx.z == 0) {
@@ -945,19 +974,43 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
         taskmask[e] = m;
     }
     const float2* __restrict__ src = prm.p2 + (size_t)pl * prm.n_cand * Nd * Md;
+    // Interior tiles (no circular wrap inside the coarse window): ONE thread issues one TMA box [CX][CY] per candidate and
+    // the tile's arrival is tracked by an mbarrier; tiles on the frame border keep the per-element cp.async gather (wrap).
+    const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
+    const bool tma = prm.use_tma && r_lo >= 0 && c_lo >= 1 && ((c_lo - 1) & 1) == 0 && r_lo + CX <= Nd && c_lo - 1 + CYB <= Md;     // CTA-uniform
+    const int cpitch = tma ? CYB : CY, coff = tma ? 1 : 0;     // layout of the staged coarse tile
+    if (tma && threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     auto fetch = [&](int i) {
+        if (tma) {
+            if (i < n_live && threadIdx.x == 0) {
+                mbar_expect_tx(&s_bar[i & 1], CX * CYB * 8);
+                tma_load_3d(smem + (i & 1) * CTILE, &tmap, &s_bar[i & 1], 2 * (c_lo - 1), r_lo, pl * prm.n_cand + cand_of(i));
+            }
+            return;
+        }
         if (i < n_live) {
             const float2* __restrict__ g = src + (size_t)cand_of(i) * Nd * Md;
-            float2* dst = smem + (i & 1) * CX * CY;
+            float2* dst = smem + (i & 1) * CTILE;
 #pragma unroll
             for (int e = 0; e < PER; ++e)
                 if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
         }
         cp_async_commit();
     };
+    auto landed = [&](int i) {          // tile i is in shared memory (for this thread; the CTA barrier that follows covers the rest)
+        if (tma) {
+            if (i < n_live) mbar_wait(&s_bar[i & 1], (unsigned)(i >> 1) & 1u);
+        } else {
+            cp_async_wait_all();
+        }
+    };
     // along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy], tasks of Q3 outputs
     auto interp_x = [&](int c) {
-        const float2* p2c = smem + (c & 1) * CX * CY;
+        const float2* p2c = smem + (c & 1) * CTILE;
         float2* p3t = p3t0 + (c & 1) * CY * P3P;
         const unsigned live = prune ? s_mask[c] : 0xffffffffu;
 #pragma unroll
@@ -967,7 +1020,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
             const int cy = t % CY, xb = t / CY;
             float2 smp[NS3], acc[Q3];
 #pragma unroll
-            for (int i = 0; i < NS3; ++i) smp[i] = p2c[(xb * (Q3 / S) + i) * CY + cy];
+            for (int i = 0; i < NS3; ++i) smp[i] = p2c[(xb * (Q3 / S) + i) * cpitch + cy + coff];
             interp_block<S, Q3>(acc, smp, taps, 0);
 #pragma unroll
             for (int p = 0; p < Q3; ++p) p3t[cy * P3P + xb * Q3 + p] = acc[p];
@@ -976,14 +1029,16 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps) {
     // Software pipeline over candidates, ONE barrier per candidate: in phase c every thread
     // interpolates candidate c+1 along x (into the other p3t buffer) and candidate c along y (+ arg-max),
     // while cp.async brings in the coarse tile of candidate c+2.
+    __syncthreads();              // mbarrier initialisation visible before the first TMA / wait
     fetch(0);
     fetch(1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (tma) landed(0);
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
     if (n_live > 0) interp_x(0);
     for (int i = 0; i < n_live; ++i) {
         const int c = cand_of(i);
-        cp_async_wait_all();
+        landed(i + 1);
         __syncthreads();          // tile i+1 landed, p3t[i] complete, buffers of phase i-1 released
         fetch(i + 2);
         if (i + 1 < n_live) interp_x(i + 1);

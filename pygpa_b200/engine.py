@@ -52,6 +52,11 @@ def set_pruning(on):
     _lib.check(_lib.load().gpa_set_pruning(int(bool(on))))
 
 
+def set_tma(on):
+    """Toggle the TMA box loads of the interpolation kernel's coarse tiles (default on; results are identical)."""
+    _lib.check(_lib.load().gpa_set_tma(int(bool(on))))
+
+
 def release_workspaces():
     _workspaces.clear()
 

@@ -115,6 +115,25 @@ def test_multirate_and_direct_forms_agree(shape, sigma, stride):
     assert torch.equal(chunked["key"], res["multirate"]["key"])
 
 
+def test_tma_and_cp_async_tile_loads_agree():
+    """The coarse tiles of k_mr_interp arrive by TMA box loads (interior tiles) or per-element cp.async gathers (tiles whose
+    window wraps around the frame, or TMA off): the keys must be bit-identical."""
+    cfg = synth.make_config('C2', size=512, n_grid=13)
+    dev = engine.require_cuda()
+    img = engine.image_to_device(cfg["image"], dev)
+    k = cfg["ks"][1]
+    wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+    plan = engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, method="multirate")
+    a = plan.run(img, k)
+    engine.set_tma(False)
+    try:
+        b = plan.run(img, k)
+    finally:
+        engine.set_tma(True)
+    assert torch.equal(a["key"], b["key"])
+    assert torch.equal(torch.view_as_real(a["lockin"]), torch.view_as_real(b["lockin"]))
+
+
 def test_pruning_is_exact():
     """Branch-and-bound pruning of the multirate arg-max must not change a single key bit, on a
     structured frame (where it removes most candidates) and on pure noise (where it removes few)."""
