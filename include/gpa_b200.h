@@ -337,6 +337,10 @@ int gpa_fit_plane_huber(const double* img, int n, int m, double f_scale, int max
  * iteration, as the reference).  *iterations (host, optional) receives the iteration count and
  * forces a stream synchronisation.
  * ------------------------------------------------------------------------------------------ */
+/* K2 row transforms of the DCT: 1 (default) = pipelined kernels (persistent CTAs, the next pair of rows arrives by
+ * cp.async.bulk while the current pair is transformed), 0 = one CTA per pair of rows.  Results are bit-identical. */
+int gpa_set_dct_pipeline(int on);
+
 /* Device mirrors of the reference's solver helpers, all float64:
  *   gpa_dctn           scipy.fft.dctn / idctn (type 2, norm=None) of an (N, M) array — the transform pair of solvePoisson
  *                      and solvePoisson_precomped (phase_unwrap.py:81-103); ws as gpa_unwrap_workspace_bytes(N, M)

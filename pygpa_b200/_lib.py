@@ -38,6 +38,7 @@ SIGNATURES = {
                                  _pf, c_int, _pf, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_set_pruning": (c_int, [c_int]),
     "gpa_set_tma": (c_int, [c_int]),
+    "gpa_set_dct_pipeline": (c_int, [c_int]),
     "gpa_sweep_mr_workspace_bytes": (c_int, [c_int] * 14 + [ctypes.POINTER(c_size_t)]),
     "gpa_sweep_argmax_mr": (c_int, [c_void_p, c_int, c_int, _pd, c_int, _pd, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _pf, c_int, _pf, c_int, _pf, _pf, c_int, _pf, c_int, _pf, c_int, c_double, c_double,

@@ -37,6 +37,14 @@ GPA_HD inline void lsq_solve2(const double (&a0)[DM], const double (&a1)[DM],
     const bool swap = n1 > n0;   // column pivoting: the larger column first
     const double f2 = swap ? n1 : n0;
     if (!(f2 > 0.0)) return;
+    // pivot column c and the other column o, selected ONCE (the selects inside the three loops below used to cost more
+    // issue slots than the arithmetic)
+    double c[DM], o[DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) {
+        c[i] = swap ? a1[i] : a0[i];
+        o[i] = swap ? a0[i] : a1[i];
+    }
     // Gram-Schmidt with the UNNORMALISED pivot column c (R = [[f, g], [0, h]], f^2 = |c|^2, g = c.o / f, h^2 = |o - (c.o / f^2) c|^2):
     // the generic pixel costs two divisions and no square root, which keeps this streaming kernel on the HBM roofline
     // instead of the fp64 divide / square-root pipe (r1: 0.33 of the HBM peak with the normalised form).
@@ -47,10 +55,9 @@ GPA_HD inline void lsq_solve2(const double (&a0)[DM], const double (&a1)[DM],
 #pragma unroll
     for (int i = 0; i < DM; ++i) {
         if (i < d) {
-            const double c = swap ? a1[i] : a0[i];
-            co = fma(c, swap ? a0[i] : a1[i], co);
+            co = fma(c[i], o[i], co);
 #pragma unroll
-            for (int k = 0; k < NRHS; ++k) cy[k] = fma(c, y[k][i], cy[k]);
+            for (int k = 0; k < NRHS; ++k) cy[k] = fma(c[i], y[k][i], cy[k]);
         }
     }
     const double gs = co * inv_f2;            // g / f
@@ -60,7 +67,7 @@ GPA_HD inline void lsq_solve2(const double (&a0)[DM], const double (&a1)[DM],
 #pragma unroll
     for (int i = 0; i < DM; ++i) {
         if (i < d) {
-            const double e = (swap ? a0[i] : a1[i]) - gs * (swap ? a1[i] : a0[i]);
+            const double e = o[i] - gs * c[i];
             h2 = fma(e, e, h2);
 #pragma unroll
             for (int k = 0; k < NRHS; ++k) z2h[k] = fma(e, y[k][i], z2h[k]);

@@ -24,28 +24,41 @@ struct LsqParams {
     int use_matrix;
 };
 
-template <int DM>
+// DIFF / WRAP / MEANS / MATRIX are the launch-uniform switches of LsqParams as template parameters, FULL = (d == DM): the
+// kernel body has no uniform branches left, so ALL of a pixel's loads (DM sources, DM forward neighbours, DM weights) are
+// issued back to back before the first one is consumed.  With the runtime switches the compiler kept every load inside its
+// branch — four serialised DRAM round trips per thread, 59 % of the stall samples on long_scoreboard at 0.45 of the HBM rate
+// (profiles/r02f_k_lstsq_ncu_summary.json).
+template <int DM, bool FULL, bool DIFF, bool WRAP, bool MEANS, bool MATRIX>
 __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= p.n || c >= p.m) return;
-    double b[DM];
+    const int d = FULL ? DM : p.d;
     const long long o = p.base + (long long)r * p.rs + (long long)c * p.cs;
+    double s0[DM], s1[DM], w[DM];
 #pragma unroll
     for (int i = 0; i < DM; ++i) {
-        if (i < p.d) {
-            double v = p.src[o + i * p.ps];
-            if (p.doff) v = p.src[o + i * p.ps + p.doff] - v;
-            if (p.do_wrap) v = wrap_pi(v);
-            if (p.means) v -= p.means[i];
-            b[i] = v;
+        s0[i] = s1[i] = w[i] = 0.0;
+        if (i < d) {
+            s0[i] = p.src[o + i * p.ps];
+            if (DIFF) s1[i] = p.src[o + i * p.ps + p.doff];
+            if (!MATRIX) w[i] = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
         }
     }
+    double b[DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) {
+        double v = DIFF ? s1[i] - s0[i] : s0[i];
+        if (WRAP) v = wrap_pi(v);
+        if (MEANS && i < d) v -= p.means[i];
+        b[i] = v;
+    }
     double x0 = 0.0, x1 = 0.0;
-    if (p.use_matrix) {
+    if (MATRIX) {
 #pragma unroll
         for (int i = 0; i < DM; ++i) {
-            if (i < p.d) {
+            if (i < d) {
                 x0 = fma(p.P[0][i], b[i], x0);
                 x1 = fma(p.P[1][i], b[i], x1);
             }
@@ -54,20 +67,36 @@ __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
         double a0[DM], a1[DM], y[1][DM], x[1][2];
 #pragma unroll
         for (int i = 0; i < DM; ++i) {
-            if (i < p.d) {
-                const double w = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
-                a0[i] = w * p.K[i][0];
-                a1[i] = w * p.K[i][1];
-                y[0][i] = w * b[i];
-            }
+            a0[i] = w[i] * p.K[i][0];
+            a1[i] = w[i] * p.K[i][1];
+            y[0][i] = w[i] * b[i];
         }
-        lsq_solve2<1, DM>(a0, a1, y, p.d, x);
+        lsq_solve2<1, DM>(a0, a1, y, d, x);
         x0 = x[0][0];
         x1 = x[0][1];
     }
     const size_t np = (size_t)p.n * p.m;
     p.out[(size_t)r * p.m + c] = x0;
     p.out[np + (size_t)r * p.m + c] = x1;
+}
+
+template <int DM, bool FULL>
+static void launch_lstsq(const LsqParams& p, dim3 grid, cudaStream_t st) {
+    const bool diff = p.doff != 0, wrap = p.do_wrap != 0, means = p.means != nullptr, matrix = p.use_matrix != 0;
+    // the combinations the entry point can produce: plain (+ means) with either solver, wrapped differences / pre-differences
+    if (diff) {            // GPA_LSQ_SRC_DIFF0 / DIFF1: always wrapped, never mean-subtracted
+        if (matrix) k_lstsq<DM, FULL, true, true, false, true><<<grid, 256, 0, st>>>(p);
+        else k_lstsq<DM, FULL, true, true, false, false><<<grid, 256, 0, st>>>(p);
+    } else if (wrap) {     // GPA_LSQ_SRC_PREDIFF0 / PREDIFF1
+        if (matrix) k_lstsq<DM, FULL, false, true, false, true><<<grid, 256, 0, st>>>(p);
+        else k_lstsq<DM, FULL, false, true, false, false><<<grid, 256, 0, st>>>(p);
+    } else if (means) {    // GPA_LSQ_SRC_PLAIN with the per-plane mean removed
+        if (matrix) k_lstsq<DM, FULL, false, false, true, true><<<grid, 256, 0, st>>>(p);
+        else k_lstsq<DM, FULL, false, false, true, false><<<grid, 256, 0, st>>>(p);
+    } else {
+        if (matrix) k_lstsq<DM, FULL, false, false, false, true><<<grid, 256, 0, st>>>(p);
+        else k_lstsq<DM, FULL, false, false, false, false><<<grid, 256, 0, st>>>(p);
+    }
 }
 
 // per-plane mean of a (d, n) array, deterministic two-stage reduction
@@ -182,8 +211,9 @@ extern "C" int gpa_lstsq_u(const double* src, int src_kind, const double* w, int
     {
         KernelTimer t("k_lstsq", st);
         dim3 grid(ceil_div(p.m, 64), ceil_div(p.n, 4));
-        if (d <= 3) k_lstsq<3><<<grid, 256, 0, st>>>(p);
-        else k_lstsq<kMaxD><<<grid, 256, 0, st>>>(p);
+        if (d == 3) launch_lstsq<3, true>(p, grid, st);
+        else if (d < 3) launch_lstsq<3, false>(p, grid, st);
+        else launch_lstsq<kMaxD, false>(p, grid, st);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;

@@ -17,6 +17,7 @@
 // the second forward pass and <r, z> into the last inverse pass.
 #include "common.cuh"
 #include "fft_device.cuh"
+#include "dct_pipe.cuh"
 
 #include <utility>
 
@@ -251,6 +252,151 @@ __global__ void __launch_bounds__(512, MAXB >= 2 ? 1 : 2) k_idct2_rows_pow2(cons
             a.partial[row] = sa;
             if (two) a.partial[row + 1] = sb;
         }
+        UwScalars* sc = a.sc;
+        finish_reduction(&sc->ticket[kTicketBeta], a.partial, a.rows, red, [sc](double s) { sc_beta(sc, s); });
+    }
+}
+
+// ---- pipelined forms (dct_pipe.cuh): persistent CTAs of n / 8 threads, pair p = blockIdx.x, blockIdx.x + gridDim.x, ...
+template <int LOGN>
+__global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN - 3)) k_dct2_rows_pipe(const DctArgs a) {
+    if (a.sc->done) return;
+    constexpr int n = 1 << LOGN, T = n >> 3;
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    __shared__ unsigned long long mbar;
+    double* const stage = reinterpret_cast<double*>(dp_smem);                  // rows 2b | 2b + 1 as they lie in memory
+    double2* const buf = reinterpret_cast<double2*>(dp_smem + 2 * n * sizeof(double));
+    double2* const t8 = buf + n + n / 8;
+    const int tid = threadIdx.x, pairs = (a.rows + 1) >> 1, G = gridDim.x;
+    auto row_bytes = [&](int pair) -> unsigned { return (2 * pair + 1 < a.rows ? 2u : 1u) * n * (unsigned)sizeof(double); };
+    if (tid == 0) {
+        dp_mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i <= n / 8; i += T) t8[i] = a.tw[i];
+    const double2 mk0 = a.mk[tid];                       // e^{-i pi tid/2n}; position tid + m n/8 needs mk0 e^{-i pi m/16}
+    __syncthreads();
+    int pair = blockIdx.x;
+    if (tid == 0 && pair < pairs) dp_bulk_load(stage, a.in + (size_t)2 * pair * n, row_bytes(pair), &mbar);
+    unsigned parity = 0;
+    for (; pair < pairs; pair += G) {
+        const int row = 2 * pair;
+        const bool two = row + 1 < a.rows;
+        dp_mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        // Makhoul order: v[p] = x[2p] (p < n/2), x[2(n-1-p)+1] (p >= n/2); rows a, b in the real / imaginary part
+        auto get = [&](int m) -> double2 {
+            const int p = tid + m * T;
+            const int src = m < 4 ? 2 * p : 2 * (n - 1 - p) + 1;
+            return make_double2(stage[src], two ? stage[n + src] : 0.0);
+        };
+        const int next = pair + G;
+        dp_fft<LOGN>(buf, t8, tid, get, [] { __syncthreads(); }, [&] {
+            if (tid == 0 && next < pairs) dp_bulk_load(stage, a.in + (size_t)2 * next * n, row_bytes(next), &mbar);
+        });
+        double* __restrict__ ya = a.out + (size_t)row * n;
+        double* __restrict__ yb = ya + n;
+        const double cra = a.fuse_scale ? a.cos_row[row] : 0.0;
+        const double crb = a.fuse_scale && two ? a.cos_row[row + 1] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = tid + q * T;
+            const double2 w = zmul(mk0, dp_rot16(q)), zk = buf[dp_pad(k)], zn = buf[dp_pad(k ? n - k : 0)];
+            const double sx = zk.x + zn.x, sy = zk.y - zn.y;      // Z[k] + conj Z[n-k]
+            const double dx = zk.x - zn.x, dy = zk.y + zn.y;      // Z[k] - conj Z[n-k]
+            double ra = w.x * sx - w.y * sy;                      // Re(w (Z + conj Z'))
+            double rb = w.x * dy + w.y * dx;                      // Im(w (Z - conj Z'))
+            if (a.fuse_scale) {
+                const double ck = a.cos_col[k];
+                ra /= (k == 0 && row == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
+                rb /= 2.0 * (ck + crb - 2.0);
+            }
+            ya[k] = ra;
+            if (two) yb[k] = rb;
+        }
+    }
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN - 3)) k_idct2_rows_pipe(const DctArgs a) {
+    if (a.sc->done) return;
+    constexpr int n = 1 << LOGN, T = n >> 3;
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    __shared__ unsigned long long mbar;
+    __shared__ double red[32];
+    double* const stage = reinterpret_cast<double*>(dp_smem);
+    double2* const buf = reinterpret_cast<double2*>(dp_smem + 2 * n * sizeof(double));
+    double2* const t8 = buf + n + n / 8;
+    const int tid = threadIdx.x, pairs = (a.rows + 1) >> 1, G = gridDim.x;
+    auto row_bytes = [&](int pair) -> unsigned { return (2 * pair + 1 < a.rows ? 2u : 1u) * n * (unsigned)sizeof(double); };
+    if (tid == 0) {
+        dp_mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i <= n / 8; i += T) t8[i] = a.tw[i];
+    const double2 mk0 = a.mk[tid];                       // e^{-i pi tid/2n}; position tid + m n/8 needs mk0 e^{-i pi m/16}
+    __syncthreads();
+    int pair = blockIdx.x;
+    if (tid == 0 && pair < pairs) dp_bulk_load(stage, a.in + (size_t)2 * pair * n, row_bytes(pair), &mbar);
+    unsigned parity = 0;
+    const double inv = 1.0 / (double)n;
+    for (; pair < pairs; pair += G) {
+        const int row = 2 * pair;
+        const bool two = row + 1 < a.rows;
+        dp_mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        // FFT input at k: conj(V_a) - i conj(V_b), V[k] = e^{+i pi k/2n} (y[k] - i y[n-k]) / 2     (as k_idct2_rows_pow2)
+        auto get = [&](int m) -> double2 {
+            const int k = tid + m * T;
+            const double2 w = zmul(mk0, dp_rot16(m));      // e^{-i pi k/2n} = (c, -s)
+            const double ak = stage[k], ank = k ? stage[n - k] : 0.0;
+            const double bk = two ? stage[n + k] : 0.0, bnk = (two && k) ? stage[2 * n - k] : 0.0;
+            const double re_a = 0.5 * (w.x * ak - w.y * ank), im_a = 0.5 * (-w.y * ak - w.x * ank);
+            const double re_b = 0.5 * (w.x * bk - w.y * bnk), im_b = 0.5 * (-w.y * bk - w.x * bnk);
+            return make_double2(re_a - im_b, -im_a - re_b);
+        };
+        const int next = pair + G;
+        dp_fft<LOGN>(buf, t8, tid, get, [] { __syncthreads(); }, [&] {
+            if (tid == 0 && next < pairs) dp_bulk_load(stage, a.in + (size_t)2 * next * n, row_bytes(next), &mbar);
+        });
+        double* __restrict__ xa = a.out + (size_t)row * n;
+        double* __restrict__ xb = xa + n;
+        double dot_a = 0.0, dot_b = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                      // two batches of 8 loads in flight (16 at once spill at 80 registers)
+            double da[4], db[4];
+            if (a.dot_with) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = tid + (4 * h + q) * T;
+                    da[q] = a.dot_with[(size_t)row * n + j];
+                    db[q] = two ? a.dot_with[(size_t)(row + 1) * n + j] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = tid + (4 * h + q) * T;
+                const int src = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
+                const double2 f = buf[dp_pad(src)];
+                const double va = f.x * inv, vb = -f.y * inv;
+                xa[j] = va;
+                if (two) xb[j] = vb;
+                if (a.dot_with) {
+                    dot_a = fma(va, da[q], dot_a);
+                    if (two) dot_b = fma(vb, db[q], dot_b);
+                }
+            }
+        }
+        if (a.dot_with) {
+            const double sa = block_sum(dot_a, red);
+            const double sb = block_sum(dot_b, red);
+            if (tid == 0) {
+                a.partial[row] = sa;
+                if (two) a.partial[row + 1] = sb;
+            }
+        }
+    }
+    if (a.dot_with) {
         UwScalars* sc = a.sc;
         finish_reduction(&sc->ticket[kTicketBeta], a.partial, a.rows, red, [sc](double s) { sc_beta(sc, s); });
     }
@@ -607,9 +753,40 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     return a.off;
 }
 
+static bool g_dct_pipe = true;      // pipelined row / column kernels (gpa_set_dct_pipeline)
+
+template <int INVERSE, int LOGN>
+static int launch_rows_pipe(const DctArgs& a, cudaStream_t st) {
+    auto kern = INVERSE ? k_idct2_rows_pipe<LOGN> : k_dct2_rows_pipe<LOGN>;
+    constexpr int n = 1 << LOGN, threads = n / 8;
+    const size_t smem = dp_rows_smem_bytes(n);
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int per_sm[2] = {0, 0}, sms = 0;        // occupancy of this instantiation (same on every B200)
+    if (!per_sm[INVERSE]) {
+        int dev = 0, v = 0;
+        GPA_CHECK_CUDA(cudaGetDevice(&dev));
+        GPA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GPA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, threads, smem));
+        per_sm[INVERSE] = v > 0 ? v : 1;
+    }
+    const int pairs = (a.rows + 1) / 2;
+    const int slots = sms * per_sm[INVERSE];
+    kern<<<pairs < slots ? pairs : slots, threads, smem, st>>>(a);
+    return GPA_OK;
+}
+
 template <int INVERSE>
 static int launch_rows(const AxisTables& ax, DctArgs a, cudaStream_t st) {
     a.tw = ax.tw; a.mk = ax.mk; a.ct = ax.ct; a.n = ax.n; a.bs = ax.bs;
+    if (g_dct_pipe && ax.pow2 && !ax.bs.L && ax.n >= 256 && ax.n <= 4096 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0) {
+        switch (ax.n) {
+            case 256: return launch_rows_pipe<INVERSE, 8>(a, st);
+            case 512: return launch_rows_pipe<INVERSE, 9>(a, st);
+            case 1024: return launch_rows_pipe<INVERSE, 10>(a, st);
+            case 2048: return launch_rows_pipe<INVERSE, 11>(a, st);
+            default: return launch_rows_pipe<INVERSE, 12>(a, st);
+        }
+    }
     if (ax.pow2 || ax.bs.L) {
         // one radix-8 butterfly per thread, two for the longest transforms (at most 512 threads)
         const int len = ax.bs.L ? ax.bs.L : ax.n;
@@ -746,6 +923,12 @@ extern "C" int gpa_dctn(const double* in, int N, int M, int inverse, double* out
     if ((rc = inverse ? launch_rows<1>(u.axN, a, st) : launch_rows<0>(u.axN, a, st))) return rc;
     transpose(u.z, out, M, N, u.sc, st);
     GPA_CHECK_CUDA(cudaGetLastError());
+    return GPA_OK;
+}
+
+/* K2 row transforms: pipelined kernels (bulk-copy prefetch, persistent CTAs; default) or the one-CTA-per-row-pair kernels. */
+extern "C" int gpa_set_dct_pipeline(int on) {
+    g_dct_pipe = on != 0;
     return GPA_OK;
 }
 
