@@ -29,59 +29,75 @@ struct LsqParams {
 // issued back to back before the first one is consumed.  With the runtime switches the compiler kept every load inside its
 // branch — four serialised DRAM round trips per thread, 59 % of the stall samples on long_scoreboard at 0.45 of the HBM rate
 // (profiles/r02f_k_lstsq_ncu_summary.json).
+// A thread solves kLsqPPT pixels, 64 columns apart (a CTA covers 4 rows x 64 kLsqPPT columns): with DM = 3 two pixels per
+// thread double the loads in flight per warp at 72 registers; the general DM = 8 form keeps one.
+template <int DM>
+struct LsqShape { static constexpr int PPT = DM <= 3 ? 2 : 1; };
+
 template <int DM, bool FULL, bool DIFF, bool WRAP, bool MEANS, bool MATRIX>
 __global__ void __launch_bounds__(256) k_lstsq(const LsqParams p) {
-    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    constexpr int kLsqPPT = LsqShape<DM>::PPT;
+    const int c0 = blockIdx.x * (64 * kLsqPPT) + (threadIdx.x & 63);
     const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= p.n || c >= p.m) return;
+    if (r >= p.n) return;
     const int d = FULL ? DM : p.d;
-    const long long o = p.base + (long long)r * p.rs + (long long)c * p.cs;
-    double s0[DM], s1[DM], w[DM];
+    double s0[kLsqPPT][DM], s1[kLsqPPT][DM], w[kLsqPPT][DM];
 #pragma unroll
-    for (int i = 0; i < DM; ++i) {
-        s0[i] = s1[i] = w[i] = 0.0;
-        if (i < d) {
-            s0[i] = p.src[o + i * p.ps];
-            if (DIFF) s1[i] = p.src[o + i * p.ps + p.doff];
-            if (!MATRIX) w[i] = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
-        }
-    }
-    double b[DM];
-#pragma unroll
-    for (int i = 0; i < DM; ++i) {
-        double v = DIFF ? s1[i] - s0[i] : s0[i];
-        if (WRAP) v = wrap_pi(v);
-        if (MEANS && i < d) v -= p.means[i];
-        b[i] = v;
-    }
-    double x0 = 0.0, x1 = 0.0;
-    if (MATRIX) {
+    for (int q = 0; q < kLsqPPT; ++q) {
+        const int c = c0 + 64 * q;
+        const long long o = p.base + (long long)r * p.rs + (long long)c * p.cs;
 #pragma unroll
         for (int i = 0; i < DM; ++i) {
-            if (i < d) {
-                x0 = fma(p.P[0][i], b[i], x0);
-                x1 = fma(p.P[1][i], b[i], x1);
+            s0[q][i] = s1[q][i] = w[q][i] = 0.0;
+            if (i < d && c < p.m) {
+                s0[q][i] = p.src[o + i * p.ps];
+                if (DIFF) s1[q][i] = p.src[o + i * p.ps + p.doff];
+                if (!MATRIX) w[q][i] = p.w[(long long)i * p.wn * p.wm + (long long)r * p.wm + c];
             }
         }
-    } else {
-        double a0[DM], a1[DM], y[1][DM], x[1][2];
-#pragma unroll
-        for (int i = 0; i < DM; ++i) {
-            a0[i] = w[i] * p.K[i][0];
-            a1[i] = w[i] * p.K[i][1];
-            y[0][i] = w[i] * b[i];
-        }
-        lsq_solve2<1, DM>(a0, a1, y, d, x);
-        x0 = x[0][0];
-        x1 = x[0][1];
     }
     const size_t np = (size_t)p.n * p.m;
-    p.out[(size_t)r * p.m + c] = x0;
-    p.out[np + (size_t)r * p.m + c] = x1;
+#pragma unroll
+    for (int q = 0; q < kLsqPPT; ++q) {
+        const int c = c0 + 64 * q;
+        if (c >= p.m) continue;
+        double b[DM];
+#pragma unroll
+        for (int i = 0; i < DM; ++i) {
+            double v = DIFF ? s1[q][i] - s0[q][i] : s0[q][i];
+            if (WRAP) v = wrap_pi(v);
+            if (MEANS && i < d) v -= p.means[i];
+            b[i] = v;
+        }
+        double x0 = 0.0, x1 = 0.0;
+        if (MATRIX) {
+#pragma unroll
+            for (int i = 0; i < DM; ++i) {
+                if (i < d) {
+                    x0 = fma(p.P[0][i], b[i], x0);
+                    x1 = fma(p.P[1][i], b[i], x1);
+                }
+            }
+        } else {
+            double a0[DM], a1[DM], y[1][DM], x[1][2];
+#pragma unroll
+            for (int i = 0; i < DM; ++i) {
+                a0[i] = w[q][i] * p.K[i][0];
+                a1[i] = w[q][i] * p.K[i][1];
+                y[0][i] = w[q][i] * b[i];
+            }
+            lsq_solve2<1, DM>(a0, a1, y, d, x);
+            x0 = x[0][0];
+            x1 = x[0][1];
+        }
+        p.out[(size_t)r * p.m + c] = x0;
+        p.out[np + (size_t)r * p.m + c] = x1;
+    }
 }
 
 template <int DM, bool FULL>
-static void launch_lstsq(const LsqParams& p, dim3 grid, cudaStream_t st) {
+static void launch_lstsq(const LsqParams& p, cudaStream_t st) {
+    const dim3 grid(ceil_div(p.m, 64 * LsqShape<DM>::PPT), ceil_div(p.n, 4));
     const bool diff = p.doff != 0, wrap = p.do_wrap != 0, means = p.means != nullptr, matrix = p.use_matrix != 0;
     // the combinations the entry point can produce: plain (+ means) with either solver, wrapped differences / pre-differences
     if (diff) {            // GPA_LSQ_SRC_DIFF0 / DIFF1: always wrapped, never mean-subtracted
@@ -210,10 +226,9 @@ extern "C" int gpa_lstsq_u(const double* src, int src_kind, const double* w, int
     }
     {
         KernelTimer t("k_lstsq", st);
-        dim3 grid(ceil_div(p.m, 64), ceil_div(p.n, 4));
-        if (d == 3) launch_lstsq<3, true>(p, grid, st);
-        else if (d < 3) launch_lstsq<3, false>(p, grid, st);
-        else launch_lstsq<kMaxD, false>(p, grid, st);
+        if (d == 3) launch_lstsq<3, true>(p, st);
+        else if (d < 3) launch_lstsq<3, false>(p, st);
+        else launch_lstsq<kMaxD, false>(p, st);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
