@@ -40,6 +40,20 @@ __device__ __forceinline__ void dp_bulk_load(void* smem_dst, const void* gsrc, u
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 }
 
+// 2-D tensor-map boxes (cp.async.bulk.tensor; SASS UTMALDG / UTMASTG): coordinates (c0 = innermost)
+__device__ __forceinline__ void dp_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, unsigned long long* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                   "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void dp_tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void dp_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ int dp_pad(int p) { return p + (p >> 3); }
 
 // e^{-2 pi i t/n}, t < n/2, from the shared-memory table t8[m] = e^{-2 pi i m/n}, m <= n/8 (first octant; the other octants by
@@ -76,9 +90,10 @@ __device__ __forceinline__ double2 dp_rot16(const int m) {
 
 // radix-8 Stockham stages NS, 8 NS, ... of an n = 2^LOGN point FFT held in the padded buffer; n / 8 threads (tid = index in
 // the group), one butterfly per thread.  FIRST: the inputs come from get(p) instead of the buffer (no twiddles at NS = 1).
-template <int LOGN, int NS, bool FIRST, typename Get, typename Sync, typename Hook>
+// idx(p) = position of element p in the buffer (dp_pad(p) for one FFT per CTA, 2 dp_pad(p) + g for two interleaved FFTs).
+template <int LOGN, int NS, bool FIRST, typename Get, typename Sync, typename Hook, typename Idx>
 __device__ __forceinline__ void dp_stage8(double2* __restrict__ buf, const double2* __restrict__ t8, const int tid, Get get,
-                                          Sync sync, Hook after_first_read) {
+                                          Sync sync, Hook after_first_read, Idx idx) {
     constexpr int n = 1 << LOGN, e = n >> 3;
     if constexpr (NS < n) {
         double2 u[8];
@@ -88,7 +103,7 @@ __device__ __forceinline__ void dp_stage8(double2* __restrict__ buf, const doubl
             for (int i = 0; i < 8; ++i) u[i] = get(i);        // position tid + i n/8
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] = buf[dp_pad(j + i * e)];
+            for (int i = 0; i < 8; ++i) u[i] = buf[idx(j + i * e)];
         }
         if constexpr (NS > 1) {
             constexpr int tstep = e / NS;                // e^{-2 pi i q k/(8 NS)} = tw[q k n/(8 NS)]
@@ -108,18 +123,18 @@ __device__ __forceinline__ void dp_stage8(double2* __restrict__ buf, const doubl
         const int j0 = ((j - k) << 3) + k;
         dft8(u);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) buf[dp_pad(j0 + i * NS)] = u[i];
+        for (int i = 0; i < 8; ++i) buf[idx(j0 + i * NS)] = u[i];
         sync();
-        dp_stage8<LOGN, NS * 8, false>(buf, t8, tid, get, sync, after_first_read);
+        dp_stage8<LOGN, NS * 8, false>(buf, t8, tid, get, sync, after_first_read, idx);
     }
 }
 
 // buf (padded) <- FFT_n of the input sequence; n / 8 threads; get(m) returns the thread's input at position tid + m n/8,
 // m = 0..7 (every head stage reads exactly these eight).  after_first_read() runs once every thread has consumed
 // its inputs (the staging buffer may be refilled from then on).  On return buf is visible to all threads of the group.
-template <int LOGN, typename Get, typename Sync, typename Hook>
+template <int LOGN, typename Get, typename Sync, typename Hook, typename Idx>
 __device__ __forceinline__ void dp_fft(double2* __restrict__ buf, const double2* __restrict__ t8, const int tid, Get get,
-                                       Sync sync, Hook after_first_read) {
+                                       Sync sync, Hook after_first_read, Idx idx) {
     constexpr int n = 1 << LOGN, T = n >> 3;
     constexpr int R0 = 1 << (LOGN % 3);
     if constexpr (R0 == 2) {                             // one radix-2 stage (ns = 1: twiddles are 1), 4 butterflies per thread
@@ -135,11 +150,11 @@ __device__ __forceinline__ void dp_fft(double2* __restrict__ buf, const double2*
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = tid + q * T;
-            buf[dp_pad(2 * j)] = zadd(a[q], b[q]);
-            buf[dp_pad(2 * j + 1)] = zsub(a[q], b[q]);
+            buf[idx(2 * j)] = zadd(a[q], b[q]);
+            buf[idx(2 * j + 1)] = zsub(a[q], b[q]);
         }
         sync();
-        dp_stage8<LOGN, 2, false>(buf, t8, tid, get, sync, after_first_read);
+        dp_stage8<LOGN, 2, false>(buf, t8, tid, get, sync, after_first_read, idx);
     } else if constexpr (R0 == 4) {                      // one radix-4 stage, 2 butterflies per thread
         constexpr int quarter = n >> 2;
         double2 v[2][4];
@@ -156,16 +171,20 @@ __device__ __forceinline__ void dp_fft(double2* __restrict__ buf, const double2*
             const int j = tid + q * T;
             dft4(v[q][0], v[q][1], v[q][2], v[q][3]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) buf[dp_pad(4 * j + i)] = v[q][i];
+            for (int i = 0; i < 4; ++i) buf[idx(4 * j + i)] = v[q][i];
         }
         sync();
-        dp_stage8<LOGN, 4, false>(buf, t8, tid, get, sync, after_first_read);
+        dp_stage8<LOGN, 4, false>(buf, t8, tid, get, sync, after_first_read, idx);
     } else {
-        dp_stage8<LOGN, 1, true>(buf, t8, tid, get, sync, after_first_read);
+        dp_stage8<LOGN, 1, true>(buf, t8, tid, get, sync, after_first_read, idx);
     }
 }
 
 // staging (two raw rows) | padded FFT buffer | first-octant twiddles
+// column strips: two interleaved padded FFT buffers (the raw strip of 4 columns lands in the same memory) | twiddles
+constexpr size_t dp_cols_smem_bytes(int n) {
+    return (size_t)2 * (n + n / 8) * sizeof(double2) + (size_t)(n / 8 + 1) * sizeof(double2);
+}
 constexpr size_t dp_rows_smem_bytes(int n) {
     return (size_t)2 * n * sizeof(double) + (size_t)(n + n / 8) * sizeof(double2) + (size_t)(n / 8 + 1) * sizeof(double2);
 }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
         const int next = pair + G;
         dp_fft<LOGN>(buf, t8, tid, get, [] { __syncthreads(); }, [&] {
             if (tid == 0 && next < pairs) dp_bulk_load(stage, a.in + (size_t)2 * next * n, row_bytes(next), &mbar);
-        });
+        }, [](int p) { return dp_pad(p); });
         double* __restrict__ ya = a.out + (size_t)row * n;
         double* __restrict__ yb = ya + n;
         const double cra = a.fuse_scale ? a.cos_row[row] : 0.0;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
         const int next = pair + G;
         dp_fft<LOGN>(buf, t8, tid, get, [] { __syncthreads(); }, [&] {
             if (tid == 0 && next < pairs) dp_bulk_load(stage, a.in + (size_t)2 * next * n, row_bytes(next), &mbar);
-        });
+        }, [](int p) { return dp_pad(p); });
         double* __restrict__ xa = a.out + (size_t)row * n;
         double* __restrict__ xb = xa + n;
         double dot_a = 0.0, dot_b = 0.0;
@@ -550,6 +550,128 @@ __global__ void __launch_bounds__(MAXB == 1 ? 1024 : 512, 1) k_poisson_cols(cons
     }
 }
 
+// Pipelined column stage of the Poisson solve: z <- idct_0(dct_0(z) / scale), in place (same arithmetic as k_poisson_cols).
+// A CTA of n / 4 threads owns a strip of FOUR columns = one 32-byte sector per row: the strip arrives as TMA boxes
+// (cp.async.bulk.tensor.2d, 256 rows x 4 columns each) in the row-major layout [row][4], which IS two interleaved complex
+// sequences — (column 0, column 1) and (column 2, column 3) of a row form the double2 elements 2 row + g of the FFTs g = 0, 1
+// (two real columns per complex FFT, as in the row kernels).  Thread (j, g) = (tid >> 1, tid & 1) runs butterfly j of FFT g, so
+// a warp's shared-memory accesses interleave the two FFTs and stay conflict-free in the padded layout 2 pad(p) + g.  The head
+// stage of the forward FFT reads the raw strip through the Makhoul permutation; everything else happens in place; the
+// result goes back as TMA box stores.  Persistent CTAs (two per SM at n = 2048, running in different phases) take the
+// strips round-robin.  Columns beyond M are zero-filled by the loads and clipped by the stores.
+struct ColPipeArgs {
+    int N, M;
+    const double2 *tw, *mk;
+    const double *cos_k, *cos_c;   // cos(pi k / M), k < N ; cos(pi c / N), c < M      (phase_unwrap.py:109, swapped on purpose)
+    const UwScalars* sc;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(1 << (LOGN - 2), LOGN >= 12 ? 1 : 1 << (12 - LOGN) > 16 ? 16 : 1 << (12 - LOGN))
+k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tmap) {
+    if (a.sc->done) return;
+    constexpr int n = 1 << LOGN, T = n >> 3, half = n >> 1;
+    constexpr int BOXR = n < 256 ? n : 256;                 // rows per TMA box
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    __shared__ unsigned long long mbar;
+    double2* const buf = reinterpret_cast<double2*>(dp_smem);
+    double2* const t8 = buf + 2 * (n + n / 8);
+    const int tid = threadIdx.x, g = tid & 1, j = tid >> 1;
+    const int units = (a.M + 3) >> 2;
+    if (tid == 0) {
+        dp_mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i <= n / 8; i += 2 * T) t8[i] = a.tw[i];
+    const double2 mk0 = a.mk[j];
+    __syncthreads();
+    auto idx = [g](int p) { return 2 * dp_pad(p) + g; };
+    auto sync = [] { __syncthreads(); };
+    auto noop = [] {};
+    unsigned parity = 0;
+    const double inv = 1.0 / (double)n;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int c0 = 4 * unit;
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous strip's stores have read the buffer
+            dp_mbar_expect_tx(&mbar, (unsigned)(n * 4 * sizeof(double)));
+#pragma unroll 1
+            for (int b = 0; b < n / BOXR; ++b) dp_tma_load_2d(dp_smem + (size_t)b * BOXR * 32, &tmap, &mbar, c0, b * BOXR);
+        }
+        dp_mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        // ---- forward FFT of the permuted columns: v[p] = x[2p] (p < n/2), x[2(n-1-p)+1] (p >= n/2)
+        dp_fft<LOGN>(buf, t8, j, [&](int m) -> double2 {
+            const int p = j + m * T;
+            const int src = m < 4 ? 2 * p : 2 * (n - 1 - p) + 1;
+            return buf[2 * src + g];
+        }, sync, noop, idx);
+        // ---- DCT-II epilogue, Poisson scale, DCT-III prologue on the pairs (k, n - k)
+        {
+            const int ca = c0 + 2 * g, cb = ca + 1;              // the two columns of this FFT (axis-1 frequencies J)
+            const double cra = ca < a.M ? a.cos_c[ca] : 0.0, crb = cb < a.M ? a.cos_c[cb] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int k = j + q * T;                         // q = 4: k = n/2 (thread j = 0 only)
+                if (q == 4 && j != 0) break;
+                const int kn = k ? n - k : 0;
+                const double2 zk = buf[idx(k)], zn = buf[idx(kn)];
+                const double2 wk = q == 4 ? make_double2(0.70710678118654752440084436210485, -0.70710678118654752440084436210485)
+                                          : zmul(mk0, dp_rot16(q));           // e^{-i pi k/2n}
+                const double2 wn = make_double2(-wk.y, -wk.x);             // e^{-i pi (n-k)/2n} = -i conj(wk)
+                double ra_k = wk.x * (zk.x + zn.x) - wk.y * (zk.y - zn.y);
+                double rb_k = wk.x * (zk.y + zn.y) + wk.y * (zk.x - zn.x);
+                const double ck = __ldg(a.cos_k + k);
+                ra_k /= (k == 0 && ca == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
+                rb_k /= 2.0 * (ck + crb - 2.0);
+                double ra_n = 0.0, rb_n = 0.0;
+                if (k != 0) {
+                    if (k == half) {
+                        ra_n = ra_k; rb_n = rb_k;
+                    } else {      // forward coefficients at n - k: Z and its conjugate partner swap roles
+                        ra_n = wn.x * (zn.x + zk.x) - wn.y * (zn.y - zk.y);
+                        rb_n = wn.x * (zn.y + zk.y) + wn.y * (zn.x - zk.x);
+                        const double cn = __ldg(a.cos_k + kn);
+                        ra_n /= 2.0 * (cn + cra - 2.0);
+                        rb_n /= 2.0 * (cn + crb - 2.0);
+                    }
+                }
+                {
+                    const double re_a = 0.5 * (wk.x * ra_k - wk.y * ra_n), im_a = 0.5 * (-wk.y * ra_k - wk.x * ra_n);
+                    const double re_b = 0.5 * (wk.x * rb_k - wk.y * rb_n), im_b = 0.5 * (-wk.y * rb_k - wk.x * rb_n);
+                    buf[idx(k)] = make_double2(re_a - im_b, -im_a - re_b);
+                }
+                if (k != 0 && k != half) {
+                    const double re_a = 0.5 * (wn.x * ra_n - wn.y * ra_k), im_a = 0.5 * (-wn.y * ra_n - wn.x * ra_k);
+                    const double re_b = 0.5 * (wn.x * rb_n - wn.y * rb_k), im_b = 0.5 * (-wn.y * rb_n - wn.x * rb_k);
+                    buf[idx(kn)] = make_double2(re_a - im_b, -im_a - re_b);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- inverse transform (forward FFT of the conjugated input), in place
+        dp_fft<LOGN>(buf, t8, j, [&](int m) -> double2 { return buf[idx(j + m * T)]; }, sync, noop, idx);
+        // ---- x[r] = Re / -Im of F[perm(r)] / n, back into the row-major strip, then out by TMA
+        double2 f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = j + q * T;
+            f[q] = buf[idx((r & 1) ? n - 1 - (r >> 1) : (r >> 1))];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) buf[2 * (j + q * T) + g] = make_double2(f[q].x * inv, -f[q].y * inv);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes visible to the TMA store
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll 1
+            for (int b = 0; b < n / BOXR; ++b) dp_tma_store_2d(&tmap, dp_smem + (size_t)b * BOXR * 32, c0, b * BOXR);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete before the CTA retires
+}
+
 __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
                             const UwScalars* sc) {
     if (sc->done) return;
@@ -720,7 +842,21 @@ struct UwPlan {
     double *cosI, *cosJ;      // cos(pi I / M), I < N ; cos(pi J / N), J < M   (phase_unwrap.py:109, swapped on purpose)
     UwScalars* sc;
     int npart;
+    CUtensorMap tmap_z;       // z as a 2-D tensor (M, N) for the pipelined column stage; valid if cols_pipe
+    int cols_pipe;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_uwEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_uwEncodeTiled uw_load_encode_tiled() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<PFN_uwEncodeTiled>(fn);
+}
 
 static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     Arena a(ws, ws_bytes);
@@ -750,10 +886,51 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     u.cosI = a.take<double>(N);
     u.cosJ = a.take<double>(M);
     u.sc = a.take<UwScalars>(1);
+    u.cols_pipe = 0;
     return a.off;
 }
 
 static bool g_dct_pipe = true;      // pipelined row / column kernels (gpa_set_dct_pipeline)
+
+// describe u.z for the TMA boxes of k_poisson_cols_pipe (strips of 4 columns x 256 rows); leaves cols_pipe = 0 when the
+// shape does not qualify (the one-CTA-per-strip kernel or the transposing path then runs)
+static void plan_cols_pipe(UwPlan& u) {
+    u.cols_pipe = 0;
+    const int N = u.N, M = u.M;
+    if (!g_dct_pipe || !u.axN.pow2 || N < 256 || N > 4096 || M % 2 != 0 || M < 4) return;
+    static PFN_uwEncodeTiled encode = uw_load_encode_tiled();
+    if (encode == nullptr) return;
+    std::memset(&u.tmap_z, 0, sizeof(u.tmap_z));
+    const cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)M * sizeof(double)};
+    const cuuint32_t box[2] = {4, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&u.tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)u.z, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    u.cols_pipe = cr == CUDA_SUCCESS;
+}
+
+template <int LOGN>
+static int launch_cols_pipe(const UwPlan& u, cudaStream_t st) {
+    constexpr int n = 1 << LOGN, threads = n / 4;
+    const size_t smem = dp_cols_smem_bytes(n);
+    auto kern = k_poisson_cols_pipe<LOGN>;
+    GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int per_sm = 0, sms = 0;
+    if (!per_sm) {
+        int dev = 0, v = 0;
+        GPA_CHECK_CUDA(cudaGetDevice(&dev));
+        GPA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GPA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, threads, smem));
+        per_sm = v > 0 ? v : 1;
+    }
+    ColPipeArgs c;
+    c.N = u.N; c.M = u.M; c.tw = u.axN.tw; c.mk = u.axN.mk; c.cos_k = u.cosI; c.cos_c = u.cosJ; c.sc = u.sc;
+    const int units = (u.M + 3) / 4, slots = sms * per_sm;
+    kern<<<units < slots ? units : slots, threads, smem, st>>>(c, u.tmap_z);
+    return GPA_OK;
+}
 
 template <int INVERSE, int LOGN>
 static int launch_rows_pipe(const DctArgs& a, cudaStream_t st) {
@@ -824,6 +1001,18 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
     KernelTimer timer("uw_poisson_solve", st);
     a.in = u.r; a.out = u.z; a.rows = N;                                   // rows along axis 1
     if ((rc = launch_rows<0>(u.axM, a, st))) return rc;
+    if (u.cols_pipe) {                    // pipelined fused column stage (TMA strips of 4 columns)
+        switch (N) {
+            case 256: rc = launch_cols_pipe<8>(u, st); break;
+            case 512: rc = launch_cols_pipe<9>(u, st); break;
+            case 1024: rc = launch_cols_pipe<10>(u, st); break;
+            case 2048: rc = launch_cols_pipe<11>(u, st); break;
+            default: rc = launch_cols_pipe<12>(u, st); break;
+        }
+        if (rc) return rc;
+        a.in = u.z; a.out = u.t; a.rows = N; a.dot_with = u.r; a.partial = u.partial;
+        return launch_rows<1>(u.axM, a, st);                               // t = z_k, partial = <r, z> rows
+    }
     if (u.axN.pow2 && M % 2 == 0) {       // fused column stage: z <- idct_0(dct_0(z) / scale) in one pass over the array
         ColArgs c;
         c.z = u.z; c.N = N; c.M = M; c.tw = u.axN.tw; c.mk = u.axN.mk; c.cos_k = u.cosI; c.cos_c = u.cosJ; c.sc = u.sc;
@@ -992,6 +1181,7 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t nm = (size_t)N * M;
+    plan_cols_pipe(u);
     {
         int rc = build_uw_tables(u, st);
         if (rc) return rc;
