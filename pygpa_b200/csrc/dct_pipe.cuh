@@ -56,17 +56,33 @@ __device__ __forceinline__ void dp_mbar_expect_tx(unsigned long long* bar, unsig
 
 __device__ __forceinline__ int dp_pad(int p) { return p + (p >> 3); }
 
-// e^{-2 pi i t/n}, t < n/2, from the shared-memory table t8[m] = e^{-2 pi i m/n}, m <= n/8 (first octant; the other octants by
-// reflection about pi/4 and a rotation by -i).  The global twiddle table missed the (small, next to 3 x 70 KB of shared memory)
-// L1 most of the time: 40 % of the stall samples of the first pipelined version were long_scoreboard on these loads.
+// Twiddles: one compact shared-memory table per radix-8 stage, tws[off(NS) + k] = e^{-2 pi i k/(8 NS)}, k < NS — a thread of
+// stage NS reads entry k = tid & (NS - 1), so a warp's reads are contiguous (conflict-free) — and w2 = w1^2, w4 = w2^2 by
+// squaring.  (History: the global twiddle table missed the small L1 next to 3 x 70 KB of shared memory, 40 % of the stall
+// samples on long_scoreboard; one table of the first octant indexed by k, 2k, 4k times the stage's step made 2- to 8-way
+// bank conflicts and lifted the shared-memory pipe from 40 % to 56 % busy.)  sum of NS over the stages < n / 7 entries.
 template <int LOGN>
-__device__ __forceinline__ double2 dp_tw(const double2* __restrict__ t8, const int t) {
-    constexpr int Q = 1 << (LOGN - 2), E = 1 << (LOGN - 3);
-    const int r = t & (Q - 1);
-    const bool refl = r > E;
-    const double2 v = t8[refl ? Q - r : r];
-    const double2 w = refl ? make_double2(-v.y, -v.x) : v;
-    return (t & Q) ? make_double2(w.y, -w.x) : w;
+__host__ __device__ constexpr int dp_tw_first() { return (LOGN % 3) ? 1 << (LOGN % 3) : 8; }
+template <int LOGN>
+__host__ __device__ constexpr int dp_tw_off(int NS) {
+    int off = 0;
+    for (int ns = dp_tw_first<LOGN>(); ns < NS; ns <<= 3) off += ns;
+    return off;
+}
+template <int LOGN>
+__host__ __device__ constexpr int dp_tw_entries() { return dp_tw_off<LOGN>(1 << LOGN); }
+
+// all threads of the CTA: fill the stage tables from the global table tw[t] = e^{-2 pi i t/n}
+template <int LOGN>
+__device__ __forceinline__ void dp_tw_fill(double2* __restrict__ tws, const double2* __restrict__ tw, int tid, int nthr) {
+    constexpr int n = 1 << LOGN;
+    int off = 0;
+#pragma unroll
+    for (int ns = dp_tw_first<LOGN>(); ns < n; ns <<= 3) {
+        const int step = n / (8 * ns);
+        for (int k = tid; k < ns; k += nthr) tws[off + k] = tw[k * step];
+        off += ns;
+    }
 }
 
 // e^{-i pi m/16}, m = 0..7: mk[tid + m n/8] = mk[tid] e^{-i pi m/16} (mk[k] = e^{-i pi k/2n}), so a thread keeps ONE Makhoul
@@ -106,8 +122,8 @@ __device__ __forceinline__ void dp_stage8(double2* __restrict__ buf, const doubl
             for (int i = 0; i < 8; ++i) u[i] = buf[idx(j + i * e)];
         }
         if constexpr (NS > 1) {
-            constexpr int tstep = e / NS;                // e^{-2 pi i q k/(8 NS)} = tw[q k n/(8 NS)]
-            const double2 w1 = dp_tw<LOGN>(t8, k * tstep), w2 = dp_tw<LOGN>(t8, 2 * k * tstep), w4 = dp_tw<LOGN>(t8, 4 * k * tstep);
+            const double2 w1 = t8[dp_tw_off<LOGN>(NS) + k];          // e^{-2 pi i k/(8 NS)}; w_q = w1^q
+            const double2 w2 = zmul(w1, w1), w4 = zmul(w2, w2);
             const double2 w3 = zmul(w1, w2), w5 = zmul(w1, w4), w6 = zmul(w2, w4);
             const double2 w7 = zmul(w3, w4);
             u[1] = zmul(u[1], w1);
@@ -183,10 +199,10 @@ __device__ __forceinline__ void dp_fft(double2* __restrict__ buf, const double2*
 // staging (two raw rows) | padded FFT buffer | first-octant twiddles
 // column strips: two interleaved padded FFT buffers (the raw strip of 4 columns lands in the same memory) | twiddles
 constexpr size_t dp_cols_smem_bytes(int n) {
-    return (size_t)2 * (n + n / 8) * sizeof(double2) + (size_t)(n / 8 + 1) * sizeof(double2);
+    return (size_t)2 * (n + n / 8) * sizeof(double2) + (size_t)(n / 7 + 1) * sizeof(double2);
 }
 constexpr size_t dp_rows_smem_bytes(int n) {
-    return (size_t)2 * n * sizeof(double) + (size_t)(n + n / 8) * sizeof(double2) + (size_t)(n / 8 + 1) * sizeof(double2);
+    return (size_t)2 * n * sizeof(double) + (size_t)(n + n / 8) * sizeof(double2) + (size_t)(n / 7 + 1) * sizeof(double2);
 }
 
 }  // namespace gpa

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
         dp_mbar_init(&mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i <= n / 8; i += T) t8[i] = a.tw[i];
+    dp_tw_fill<LOGN>(t8, a.tw, tid, T);
     const double2 mk0 = a.mk[tid];                       // e^{-i pi tid/2n}; position tid + m n/8 needs mk0 e^{-i pi m/16}
     __syncthreads();
     int pair = blockIdx.x;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
     }
 }
 
-template <int LOGN>
+template <int LOGN, bool DOT>
 __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN - 3)) k_idct2_rows_pipe(const DctArgs a) {
     if (a.sc->done) return;
     constexpr int n = 1 << LOGN, T = n >> 3;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
         dp_mbar_init(&mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i <= n / 8; i += T) t8[i] = a.tw[i];
+    dp_tw_fill<LOGN>(t8, a.tw, tid, T);
     const double2 mk0 = a.mk[tid];                       // e^{-i pi tid/2n}; position tid + m n/8 needs mk0 e^{-i pi m/16}
     __syncthreads();
     int pair = blockIdx.x;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                      // two batches of 8 loads in flight (16 at once spill at 80 registers)
             double da[4], db[4];
-            if (a.dot_with) {
+            if (DOT) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int j = tid + (4 * h + q) * T;
@@ -381,13 +381,13 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
                 const double va = f.x * inv, vb = -f.y * inv;
                 xa[j] = va;
                 if (two) xb[j] = vb;
-                if (a.dot_with) {
+                if (DOT) {
                     dot_a = fma(va, da[q], dot_a);
                     if (two) dot_b = fma(vb, db[q], dot_b);
                 }
             }
         }
-        if (a.dot_with) {
+        if (DOT) {
             const double sa = block_sum(dot_a, red);
             const double sb = block_sum(dot_b, red);
             if (tid == 0) {
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
             }
         }
     }
-    if (a.dot_with) {
+    if (DOT) {
         UwScalars* sc = a.sc;
         finish_reduction(&sc->ticket[kTicketBeta], a.partial, a.rows, red, [sc](double s) { sc_beta(sc, s); });
     }
@@ -563,7 +563,11 @@ struct ColPipeArgs {
     int N, M;
     const double2 *tw, *mk;
     const double *cos_k, *cos_c;   // cos(pi k / M), k < N ; cos(pi c / N), c < M      (phase_unwrap.py:109, swapped on purpose)
-    const UwScalars* sc;
+    UwScalars* sc;
+    // <r, z> of the PCG without another pass over the arrays: the DCT-II is orthogonal up to the weights
+    // sum_n x[n] y[n] = X[0] Y[0] / 4n + sum_{k>0} X[k] Y[k] / 2n per axis, and this kernel holds both dctn(r) (before the
+    // Poisson scale) and dctn(z) (after it) in registers.  partial = one value per CTA (null: not wanted).
+    double* partial;
 };
 
 template <int LOGN>
@@ -574,15 +578,18 @@ k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tma
     constexpr int BOXR = n < 256 ? n : 256;                 // rows per TMA box
     extern __shared__ __align__(128) unsigned char dp_smem[];
     __shared__ unsigned long long mbar;
+    __shared__ double red[32];
     double2* const buf = reinterpret_cast<double2*>(dp_smem);
     double2* const t8 = buf + 2 * (n + n / 8);
     const int tid = threadIdx.x, g = tid & 1, j = tid >> 1;
+    double dot = 0.0;
+    const double wi0 = 0.25 / (double)n, wi1 = 0.5 / (double)n, wj0 = 0.25 / (double)a.M, wj1 = 0.5 / (double)a.M;
     const int units = (a.M + 3) >> 2;
     if (tid == 0) {
         dp_mbar_init(&mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i <= n / 8; i += 2 * T) t8[i] = a.tw[i];
+    dp_tw_fill<LOGN>(t8, a.tw, tid, 2 * T);
     const double2 mk0 = a.mk[j];
     __syncthreads();
     auto idx = [g](int p) { return 2 * dp_pad(p) + g; };
@@ -610,6 +617,7 @@ k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tma
         {
             const int ca = c0 + 2 * g, cb = ca + 1;              // the two columns of this FFT (axis-1 frequencies J)
             const double cra = ca < a.M ? a.cos_c[ca] : 0.0, crb = cb < a.M ? a.cos_c[cb] : 0.0;
+            const double wja = ca < a.M ? (ca == 0 ? wj0 : wj1) : 0.0, wjb = cb < a.M ? wj1 : 0.0;
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const int k = j + q * T;                         // q = 4: k = n/2 (thread j = 0 only)
@@ -622,8 +630,12 @@ k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tma
                 double ra_k = wk.x * (zk.x + zn.x) - wk.y * (zk.y - zn.y);
                 double rb_k = wk.x * (zk.y + zn.y) + wk.y * (zk.x - zn.x);
                 const double ck = __ldg(a.cos_k + k);
-                ra_k /= (k == 0 && ca == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
-                rb_k /= 2.0 * (ck + crb - 2.0);
+                {
+                    const double ua = ra_k, ub = rb_k;
+                    ra_k /= (k == 0 && ca == 0) ? 1.0 : 2.0 * (ck + cra - 2.0);
+                    rb_k /= 2.0 * (ck + crb - 2.0);
+                    dot = fma(k == 0 ? wi0 : wi1, fma(wja * ua, ra_k, wjb * ub * rb_k), dot);
+                }
                 double ra_n = 0.0, rb_n = 0.0;
                 if (k != 0) {
                     if (k == half) {
@@ -632,8 +644,10 @@ k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tma
                         ra_n = wn.x * (zn.x + zk.x) - wn.y * (zn.y - zk.y);
                         rb_n = wn.x * (zn.y + zk.y) + wn.y * (zn.x - zk.x);
                         const double cn = __ldg(a.cos_k + kn);
+                        const double ua = ra_n, ub = rb_n;
                         ra_n /= 2.0 * (cn + cra - 2.0);
                         rb_n /= 2.0 * (cn + crb - 2.0);
+                        dot = fma(wi1, fma(wja * ua, ra_n, wjb * ub * rb_n), dot);
                     }
                 }
                 {
@@ -670,6 +684,12 @@ k_poisson_cols_pipe(const ColPipeArgs a, const __grid_constant__ CUtensorMap tma
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // stores complete before the CTA retires
+    if (a.partial) {
+        const double s = block_sum(dot, red);
+        if (tid == 0) a.partial[blockIdx.x] = s;
+        UwScalars* sc = a.sc;
+        finish_reduction(&sc->ticket[kTicketBeta], a.partial, gridDim.x, red, [sc](double t) { sc_beta(sc, t); });
+    }
 }
 
 __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
@@ -927,14 +947,16 @@ static int launch_cols_pipe(const UwPlan& u, cudaStream_t st) {
     }
     ColPipeArgs c;
     c.N = u.N; c.M = u.M; c.tw = u.axN.tw; c.mk = u.axN.mk; c.cos_k = u.cosI; c.cos_c = u.cosJ; c.sc = u.sc;
+    c.partial = u.partial;
     const int units = (u.M + 3) / 4, slots = sms * per_sm;
     kern<<<units < slots ? units : slots, threads, smem, st>>>(c, u.tmap_z);
     return GPA_OK;
 }
 
-template <int INVERSE, int LOGN>
+template <int INVERSE, int LOGN, bool DOT = false>
 static int launch_rows_pipe(const DctArgs& a, cudaStream_t st) {
-    auto kern = INVERSE ? k_idct2_rows_pipe<LOGN> : k_dct2_rows_pipe<LOGN>;
+    if (INVERSE && !DOT && a.dot_with) return launch_rows_pipe<INVERSE, LOGN, true>(a, st);
+    auto kern = INVERSE ? (DOT ? k_idct2_rows_pipe<LOGN, true> : k_idct2_rows_pipe<LOGN, false>) : k_dct2_rows_pipe<LOGN>;
     constexpr int n = 1 << LOGN, threads = n / 8;
     const size_t smem = dp_rows_smem_bytes(n);
     GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1010,8 +1032,8 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
             default: rc = launch_cols_pipe<12>(u, st); break;
         }
         if (rc) return rc;
-        a.in = u.z; a.out = u.t; a.rows = N; a.dot_with = u.r; a.partial = u.partial;
-        return launch_rows<1>(u.axM, a, st);                               // t = z_k, partial = <r, z> rows
+        a.in = u.z; a.out = u.t; a.rows = N;                               // <r, z> came out of the column stage
+        return launch_rows<1>(u.axM, a, st);                               // t = z_k
     }
     if (u.axN.pow2 && M % 2 == 0) {       // fused column stage: z <- idct_0(dct_0(z) / scale) in one pass over the array
         ColArgs c;
