@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "fft_device.cuh"
 #include "dct_pipe.cuh"
+#include "lsq_device.cuh"
 
 #include <utility>
 
@@ -34,12 +35,8 @@ struct UwScalars {
 
 enum { kTicketInit = 0, kTicketBeta = 1, kTicketAlpha = 2, kTicketStop = 3 };
 
-__device__ __forceinline__ double wrap_pi_d(double v) {
-    const double two_pi = 2.0 * kPi;
-    double t = (v + kPi) / two_pi;
-    t -= floor(t);
-    return t * two_pi - kPi;
-}
+// (v + pi) mod 2 pi - pi (phase_unwrap.py:135-138): the division-free form shared with K3 (lsq_device.cuh)
+__device__ __forceinline__ double wrap_pi_d(double v) { return wrap_pi(v); }
 
 // sum over the CTA (any multiple of 32 threads up to 1024); sh needs 32 doubles
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -125,6 +122,9 @@ struct DctArgs {
     const double* dot_with;
     double* partial;
     UwScalars* sc;
+    // fused direction update of the PCG (pipelined inverse pass only): instead of storing the result z to `out`,
+    // p <- z + beta p (p <- z in the first iteration), beta from sc (complete before this kernel starts)   (phase_unwrap.py:188-196)
+    double* p_update;
 };
 
 // <r, z> is complete: k += 1, beta = rz / rz_prev (phase_unwrap.py:188-193)
@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
     }
 }
 
-template <int LOGN, bool DOT>
+// MODE 0: out = idct rows; 1: + partial sums of <out, dot_with>; 2: p_update <- out + beta p_update instead of storing out
+template <int LOGN, int MODE>
 __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN - 3)) k_idct2_rows_pipe(const DctArgs a) {
     if (a.sc->done) return;
     constexpr int n = 1 << LOGN, T = n >> 3;
@@ -340,6 +341,9 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
     if (tid == 0 && pair < pairs) dp_bulk_load(stage, a.in + (size_t)2 * pair * n, row_bytes(pair), &mbar);
     unsigned parity = 0;
     const double inv = 1.0 / (double)n;
+    constexpr bool DOT = MODE == 1, PUPD = MODE == 2;
+    const double beta = PUPD ? a.sc->beta : 0.0;
+    const bool first = PUPD ? a.sc->k == 1 : true;
     for (; pair < pairs; pair += G) {
         const int row = 2 * pair;
         const bool two = row + 1 < a.rows;
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
         dp_fft<LOGN>(buf, t8, tid, get, [] { __syncthreads(); }, [&] {
             if (tid == 0 && next < pairs) dp_bulk_load(stage, a.in + (size_t)2 * next * n, row_bytes(next), &mbar);
         }, [](int p) { return dp_pad(p); });
-        double* __restrict__ xa = a.out + (size_t)row * n;
+        double* __restrict__ xa = (PUPD ? a.p_update : a.out) + (size_t)row * n;
         double* __restrict__ xb = xa + n;
         double dot_a = 0.0, dot_b = 0.0;
 #pragma unroll
@@ -373,12 +377,24 @@ __global__ void __launch_bounds__(1 << (LOGN - 3), LOGN == 12 ? 1 : 768 >> (LOGN
                     db[q] = two ? a.dot_with[(size_t)(row + 1) * n + j] : 0.0;
                 }
             }
+            if (PUPD && !first) {                          // the old direction, 8 loads in flight
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = tid + (4 * h + q) * T;
+                    da[q] = xa[j];
+                    db[q] = two ? xb[j] : 0.0;
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int j = tid + (4 * h + q) * T;
                 const int src = (j & 1) ? n - 1 - (j >> 1) : (j >> 1);
                 const double2 f = buf[dp_pad(src)];
-                const double va = f.x * inv, vb = -f.y * inv;
+                double va = f.x * inv, vb = -f.y * inv;
+                if (PUPD && !first) {
+                    va = fma(beta, da[q], va);
+                    vb = fma(beta, db[q], vb);
+                }
                 xa[j] = va;
                 if (two) xb[j] = vb;
                 if (DOT) {
@@ -730,35 +746,37 @@ constexpr int kUwRows = 32;     // rows per CTA of the stencil kernels (4 rows x
 __global__ void __launch_bounds__(256) k_uw_setup(const SetupArgs a) {
     __shared__ double red[32];
     const int N = a.N, M = a.M;
-    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     double rsq = 0.0;
-    auto bx = [&](int rr, int cc) -> double {      // wrapped difference along axis 1 at (rr, cc), cc < M-1
+    auto bx_ = [&](int rr, int cc) -> double {      // wrapped difference along axis 1 at (rr, cc), cc < M-1
         const double d = a.psi ? a.psi[(size_t)rr * M + cc + 1] - a.psi[(size_t)rr * M + cc]
                                : a.dx[(size_t)rr * (M - 1) + cc];
         return wrap_pi_d(d);
     };
-    auto by = [&](int rr, int cc) -> double {      // along axis 0 at (rr, cc), rr < N-1
+    auto by_ = [&](int rr, int cc) -> double {     // along axis 0 at (rr, cc), rr < N-1
         const double d = a.psi ? a.psi[(size_t)(rr + 1) * M + cc] - a.psi[(size_t)rr * M + cc]
                                : a.dy[(size_t)rr * M + cc];
         return wrap_pi_d(d);
     };
-    for (int it = 0; it < kUwRows / 4; ++it) {
-        const int r = blockIdx.y * kUwRows + it * 4 + (threadIdx.x >> 6);
+    const int tiles_x = (M + 63) >> 6, n_sub = tiles_x * ((N + 3) >> 2);     // sub-tiles of 4 rows x 64 columns, round-robin
+    for (int t = blockIdx.x + blockIdx.y * gridDim.x; t < n_sub; t += gridDim.x * gridDim.y) {
+        const int by = t / tiles_x, bx = t - by * tiles_x;
+        const int c = bx * 64 + (threadIdx.x & 63);
+        const int r = by * 4 + (threadIdx.x >> 6);
         if (r < N && c < M) {
             const size_t i = (size_t)r * M + c;
             double v = 0.0;
             if (c < M - 1) {
                 const double w = edge_w(a.weight, i, i + 1);
                 a.wwx[(size_t)r * (M - 1) + c] = w;
-                v += w * bx(r, c);
+                v += w * bx_(r, c);
             }
-            if (c > 0) v -= edge_w(a.weight, i - 1, i) * bx(r, c - 1);
+            if (c > 0) v -= edge_w(a.weight, i - 1, i) * bx_(r, c - 1);
             if (r < N - 1) {
                 const double w = edge_w(a.weight, i, i + M);
                 a.wwy[i] = w;
-                v += w * by(r, c);
+                v += w * by_(r, c);
             }
-            if (r > 0) v -= edge_w(a.weight, i - M, i) * by(r - 1, c);
+            if (r > 0) v -= edge_w(a.weight, i - M, i) * by_(r - 1, c);
             a.r[i] = v;
             a.phi[i] = 0.0;
             rsq = fma(v, v, rsq);
@@ -794,10 +812,14 @@ __global__ void __launch_bounds__(256) k_uw_apply_q(const double* __restrict__ p
                                                     double* __restrict__ partial, int N, int M, UwScalars* sc) {
     if (sc->done) return;
     __shared__ double red[32];
-    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    // sub-tiles of 4 rows x 64 columns, taken round-robin by a grid that fills the machine exactly once (a grid of one CTA
+    // per 32 x 64 pixels was 1.73 waves at 2048^2: the second wave ran 73 % full)
+    const int tiles_x = (M + 63) >> 6, n_sub = tiles_x * ((N + 3) >> 2);
     double pq = 0.0;
-    for (int it = 0; it < kUwRows / 4; ++it) {
-        const int r = blockIdx.y * kUwRows + it * 4 + (threadIdx.x >> 6);
+    for (int t = blockIdx.x + blockIdx.y * gridDim.x; t < n_sub; t += gridDim.x * gridDim.y) {
+        const int by = t / tiles_x, bx = t - by * tiles_x;
+        const int c = bx * 64 + (threadIdx.x & 63);
+        const int r = by * 4 + (threadIdx.x >> 6);
         if (r < N && c < M) {
             const size_t i = (size_t)r * M + c;
             const double pc = p[i];
@@ -864,6 +886,7 @@ struct UwPlan {
     int npart;
     CUtensorMap tmap_z;       // z as a 2-D tensor (M, N) for the pipelined column stage; valid if cols_pipe
     int cols_pipe;
+    int fuse_p;               // the last inverse row pass also updates the search direction p (needs cols_pipe: beta is known)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -907,6 +930,7 @@ static size_t carve_unwrap(UwPlan& u, void* ws, size_t ws_bytes, int N, int M) {
     u.cosJ = a.take<double>(M);
     u.sc = a.take<UwScalars>(1);
     u.cols_pipe = 0;
+    u.fuse_p = 0;
     return a.off;
 }
 
@@ -929,6 +953,7 @@ static void plan_cols_pipe(UwPlan& u) {
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     u.cols_pipe = cr == CUDA_SUCCESS;
+    u.fuse_p = u.cols_pipe && u.axM.pow2 && M >= 256 && M <= 4096;       // the row pass along axis 1 is a pipelined kernel too
 }
 
 template <int LOGN>
@@ -953,10 +978,11 @@ static int launch_cols_pipe(const UwPlan& u, cudaStream_t st) {
     return GPA_OK;
 }
 
-template <int INVERSE, int LOGN, bool DOT = false>
+template <int INVERSE, int LOGN, int MODE = 0>
 static int launch_rows_pipe(const DctArgs& a, cudaStream_t st) {
-    if (INVERSE && !DOT && a.dot_with) return launch_rows_pipe<INVERSE, LOGN, true>(a, st);
-    auto kern = INVERSE ? (DOT ? k_idct2_rows_pipe<LOGN, true> : k_idct2_rows_pipe<LOGN, false>) : k_dct2_rows_pipe<LOGN>;
+    if (INVERSE && MODE == 0 && a.dot_with) return launch_rows_pipe<INVERSE, LOGN, 1>(a, st);
+    if (INVERSE && MODE == 0 && a.p_update) return launch_rows_pipe<INVERSE, LOGN, 2>(a, st);
+    auto kern = INVERSE ? k_idct2_rows_pipe<LOGN, MODE> : k_dct2_rows_pipe<LOGN>;
     constexpr int n = 1 << LOGN, threads = n / 8;
     const size_t smem = dp_rows_smem_bytes(n);
     GPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1033,6 +1059,7 @@ static int poisson_solve(const UwPlan& u, cudaStream_t st) {
         }
         if (rc) return rc;
         a.in = u.z; a.out = u.t; a.rows = N;                               // <r, z> came out of the column stage
+        if (u.fuse_p) a.p_update = u.p;                                    // p = z_k + beta p instead of t = z_k
         return launch_rows<1>(u.axM, a, st);                               // t = z_k
     }
     if (u.axN.pow2 && M % 2 == 0) {       // fused column stage: z <- idct_0(dct_0(z) / scale) in one pass over the array
@@ -1211,7 +1238,17 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
     dim3 g2(ceil_div(M, 64), ceil_div(N, kUwRows));
     const int n2 = g2.x * g2.y;
     GPA_REQUIRE(n2 <= u.npart && N <= u.npart && M <= u.npart, "frame too large for the reduction scratch");
-    const int g1 = (int)((nm + 2047) / 2048 < 4096 ? (nm + 2047) / 2048 : 4096);
+    // streaming / stencil kernels: grid-stride loops under a grid that fills the machine exactly once (8 CTAs of 256 threads per SM)
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        GPA_CHECK_CUDA(cudaGetDevice(&dev));
+        GPA_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int wave = sms * 8;
+    const int g1 = (int)((nm + 255) / 256 < (size_t)wave ? (nm + 255) / 256 : wave);
+    const int n_sub = ceil_div(M, 64) * ceil_div(N, 4);
+    const int gq = n_sub < wave ? n_sub : wave;
     {
         SetupArgs s;
         s.psi = psi; s.dx = dx; s.dy = dy; s.weight = weight;
@@ -1219,7 +1256,7 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
         s.sc = u.sc; s.kmax = kmax;
         KernelTimer timer("uw_setup", st);
         GPA_CHECK_CUDA(cudaMemsetAsync(u.sc, 0, sizeof(UwScalars), st));     // done = 0, tickets = 0
-        k_uw_setup<<<g2, 256, 0, st>>>(s);
+        k_uw_setup<<<gq, 256, 0, st>>>(s);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     // The reference always runs at least one iteration (k is tested after the update), so kmax <= 1
@@ -1233,8 +1270,8 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
             KernelTimer timer("uw_vector_ops", st);
             // (fusing p = z + beta p into the stencil kernel was measured SLOWER on B200: 0.115 vs 0.097 ms per iteration at
             // 2048^2 — the stencil is LSU- / latency-bound, not DRAM-bound, and the fused form doubles its loads)
-            k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
-            k_uw_apply_q<<<g2, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
+            if (!u.fuse_p) k_uw_update_p<<<g1, 256, 0, st>>>(u.t, u.p, nm, u.sc);
+            k_uw_apply_q<<<gq, 256, 0, st>>>(u.p, u.wwx, u.wwy, u.q, u.partial, N, M, u.sc);
             k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
         }
         GPA_CHECK_CUDA(cudaGetLastError());
