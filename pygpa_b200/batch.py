@@ -21,8 +21,13 @@ __all__ = ["FramePipeline", "shard_frames", "process_frames"]
 class FramePipeline:
     """Plans (candidate axes, taps, scratch) for one frame shape, reused for every frame."""
 
-    def __init__(self, shape, kvecs, sigma=None, kwscale=2.5, ksteps=3, n_grid=None, device=None):
+    def __init__(self, shape, kvecs, sigma=None, kwscale=2.5, ksteps=3, n_grid=None, device=None, streams=1):
+        """streams > 1: `submit` spreads consecutive frames over that many CUDA streams (each with its own scratch), so the
+        kernels of one frame that cannot fill the GPU (1024^2 frames: FFT strips, spline prefilter, reductions) overlap
+        with another frame's."""
         self.device = device or engine.require_cuda()
+        self._streams = [torch.cuda.Stream(self.device) for _ in range(streams)] if streams > 1 else []
+        self._turn = 0
         self.kvecs = np.asarray(kvecs, dtype=np.float64)
         norms = np.linalg.norm(self.kvecs, axis=1)
         self.kw = float(norms.mean() / kwscale)
@@ -55,6 +60,28 @@ class FramePipeline:
             # frame is resampled, as undistort_image(frame, -u) does (zeros outside the frame, geometric_phase_analysis.py:973)
             out["corrected"] = solvers.undistort(solvers.to_device_f64(arr, self.device), -u)
         return out
+
+
+    def submit(self, frame, undistort=True):
+        """Like calling the pipeline, but on the next stream of the pool (round-robin).  The returned tensors are complete
+        after `join()` (or a synchronisation of the device)."""
+        if not self._streams:
+            return self(frame, undistort)
+        caller = torch.cuda.current_stream(self.device)
+        s = self._streams[self._turn % len(self._streams)]
+        self._turn += 1
+        s.wait_stream(caller)                      # the frame may have been produced on the caller's stream
+        with torch.cuda.stream(s):
+            res = self(frame, undistort)
+        for v in res.values():
+            v.record_stream(caller)
+        return res
+
+    def join(self):
+        """Make the caller's stream wait for everything submitted so far."""
+        caller = torch.cuda.current_stream(self.device)
+        for s in self._streams:
+            caller.wait_stream(s)
 
 
 def shard_frames(n_frames, world, rank):

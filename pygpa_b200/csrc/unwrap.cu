@@ -1306,7 +1306,9 @@ extern "C" int gpa_unwrap_pcg(const double* psi, const double* dx, const double*
             k_uw_update_xr<<<g1, 256, 0, st>>>(phi, u.r, u.p, u.q, u.partial, nm, u.sc);
         }
         GPA_CHECK_CUDA(cudaGetLastError());
-        if ((k & 7) == 7 && k + 1 < iters) {                 // stop enqueueing once converged
+        // stop enqueueing once converged — only for long runs: a host synchronisation stalls the caller's pipeline (the
+        // adaptive chain calls this with kmax = 10 twice per frame), and converged iterations exit at once anyway
+        if ((k & 7) == 7 && k + 1 < iters && iters > 16) {
             GPA_CHECK_CUDA(cudaMemcpyAsync(&done_host, &u.sc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
             GPA_CHECK_CUDA(cudaStreamSynchronize(st));
             if (done_host) break;

@@ -37,13 +37,20 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def _ws_key(device):
+    return (device, torch.cuda.current_stream(device).cuda_stream)
+
+
 def workspace(nbytes, device):
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
-    ws = _workspaces.get(device)
+    """Grow-only scratch buffer per (device, current stream) — the C ABI never allocates.  Every entry point enqueues on
+    the current torch stream, so work issued on two streams never shares scratch, and a buffer is only ever replaced by the
+    stream that uses it (the caching allocator recycles it in that stream's order)."""
+    key = _ws_key(device)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        _workspaces[device] = None
+        _workspaces[key] = None
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -98,7 +105,7 @@ def _plan_planes(n, m, n_rows, n_planes, rx, ry, device, planes_in_flight):
         return nbytes.value
     if planes_in_flight is None:
         free, _total = torch.cuda.mem_get_info(device)
-        cached = _workspaces.get(device)
+        cached = _workspaces.get(_ws_key(device))
         budget = int(0.6 * free) + (cached.numel() if cached is not None else 0)
         base, full = need(1), need(n_planes)
         if full <= budget or n_planes == 1:
@@ -180,7 +187,7 @@ class SweepPlan:
         p = planes_in_flight
         if p is None:
             free, _total = torch.cuda.mem_get_info(self.device)
-            cached = _workspaces.get(self.device)
+            cached = _workspaces.get(_ws_key(self.device))
             budget = int(0.6 * free) + (cached.numel() if cached is not None else 0)
             base, full = need(1), need(self.wy.size)
             if full <= budget or self.wy.size == 1:
