@@ -21,13 +21,20 @@ __all__ = ["FramePipeline", "shard_frames", "process_frames"]
 class FramePipeline:
     """Plans (candidate axes, taps, scratch) for one frame shape, reused for every frame."""
 
-    def __init__(self, shape, kvecs, sigma=None, kwscale=2.5, ksteps=3, n_grid=None, device=None, streams=1):
+    def __init__(self, shape, kvecs, sigma=None, kwscale=2.5, ksteps=3, n_grid=None, device=None, streams=1, graphs=False):
         """streams > 1: `submit` spreads consecutive frames over that many CUDA streams (each with its own scratch), so the
         kernels of one frame that cannot fill the GPU (1024^2 frames: FFT strips, spline prefilter, reductions) overlap
-        with another frame's."""
+        with another frame's.
+        graphs: `submit` captures the whole per-frame chain (~250 launches) into one CUDA graph per stream on its second
+        use and replays it afterwards — the host then spends microseconds per frame instead of milliseconds.  Frames must
+        be CUDA tensors of one shape and dtype; the returned tensors of a stream are overwritten by that stream's next
+        frame (copy them out first)."""
         self.device = device or engine.require_cuda()
-        self._streams = [torch.cuda.Stream(self.device) for _ in range(streams)] if streams > 1 else []
+        self._streams = [torch.cuda.Stream(self.device) for _ in range(max(1, streams))] if (streams > 1 or graphs) else []
         self._turn = 0
+        self._graphs = bool(graphs)
+        self._slots = [None] * len(self._streams)       # per stream: dict(graph, static_in, out, undistort) once captured
+        self._warm = [0] * len(self._streams)
         self.kvecs = np.asarray(kvecs, dtype=np.float64)
         norms = np.linalg.norm(self.kvecs, axis=1)
         self.kw = float(norms.mean() / kwscale)
@@ -68,14 +75,36 @@ class FramePipeline:
         if not self._streams:
             return self(frame, undistort)
         caller = torch.cuda.current_stream(self.device)
-        s = self._streams[self._turn % len(self._streams)]
+        slot_i = self._turn % len(self._streams)
+        s = self._streams[slot_i]
         self._turn += 1
         s.wait_stream(caller)                      # the frame may have been produced on the caller's stream
+        if self._graphs and isinstance(frame, torch.Tensor) and frame.is_cuda:
+            slot = self._slots[slot_i]
+            if slot is None and self._warm[slot_i] >= 1:
+                slot = self._slots[slot_i] = self._capture(s, frame, undistort)
+            if slot is not None and slot["undistort"] == undistort and slot["static_in"].shape == frame.shape \
+                    and slot["static_in"].dtype == frame.dtype:
+                with torch.cuda.stream(s):
+                    slot["static_in"].copy_(frame)
+                    slot["graph"].replay()
+                return slot["out"]
         with torch.cuda.stream(s):
-            res = self(frame, undistort)
+            res = self(frame, undistort)           # eager (also the warm-up that sizes this stream's scratch before a capture)
+        self._warm[slot_i] += 1
         for v in res.values():
             v.record_stream(caller)
         return res
+
+    def _capture(self, stream, frame, undistort):
+        static_in = torch.empty_like(frame)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            static_in.copy_(frame)
+        stream.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            out = self(static_in, undistort)
+        return {"graph": graph, "static_in": static_in, "out": out, "undistort": undistort}
 
     def join(self):
         """Make the caller's stream wait for everything submitted so far."""
