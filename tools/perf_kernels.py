@@ -17,7 +17,8 @@ reps = 5
 for _ in range(reps): plan.run(img, k)
 torch.cuda.synchronize(); lib.gpa_profile_enable(0)
 tot, n = ctypes.c_double(0), ctypes.c_int(0); total = 0
-for name in ("k_mr_pass1", "k_mr_pass2", "k_mr_interp", "k_pass1", "k_pass2_argmax", "k_finalize", "k_mr_finalize"):
+for name in ("k_mr_pass1", "k_mr_pass1a", "k_mr_pass1b", "k_mr_pass2", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_pass1",
+             "k_pass2_argmax", "k_finalize", "k_mr_finalize"):
     lib.gpa_profile_read(name.encode(), ctypes.byref(tot), ctypes.byref(n), 0)
     if n.value: print(f"{name:16s} {tot.value / reps:8.3f} ms/peak ({n.value // reps} launches)"); total += tot.value / reps
 print("sum", round(total, 3), "ms/peak; units/peak", size * size * ng * ng / 1e9, "G")
