@@ -798,7 +798,9 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
     static_assert(SBX >= 1 && SBY >= 1 && kMrTX / S % kPmB == 0 && kMrTY / S % kPmB == 0, "tile must hold whole bound blocks");
     static_assert(kMrHL <= kPmB, "the interpolation halo must stay within one neighbouring bound block");
     __shared__ int s_blk[SBX][SBY];       // smallest recorded winner (float bits, >= 0) per bound block of the tile
-    __shared__ int s_cnt;
+    __shared__ int s_cnt, s_needboot;
+    __shared__ int s_boot[SBX * SBY];     // bootstrap: per bound block the candidate with the largest bound (bound bits | candidate)
+    __shared__ int s_new[SBX][SBY];       // block minima of this plane's best so far
     __shared__ unsigned short s_list[kMaxPruneCand];
     __shared__ unsigned s_mask[kMaxPruneCand];      // per survivor: bound blocks of the tile in which it can still win
     static_assert(SBX * SBY <= 32, "one mask bit per bound block of the tile");
@@ -844,82 +846,18 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
             }
             __syncthreads();
         }
-        {
-            // survivor search, all 8 warps: warp w tests candidates [32 w, 32 w + 32), [32 w + 256, ...) and writes its survivors
-            // in candidate order through a CTA-wide prefix over the per-(round, warp) counts — the list comes out in exactly
-            // the order the serial search of warp 0 produced (it took ~10 % of a pruned CTA's life)
-            __shared__ int s_wcnt[(kMaxPruneCand + 255) / 256][8];
-            float thr[SBX][SBY];
-#pragma unroll
+        // bootstrap (below) is needed when a bound block of the tile has pixels but no recorded winner yet: the tile's
+        // first plane, which would otherwise sweep all candidates unpruned
+        if (threadIdx.x == 0) {
+            int nb = 0;
             for (int i = 0; i < SBX; ++i)
-#pragma unroll
-                for (int j = 0; j < SBY; ++j) thr[i][j] = __int_as_float(s_blk[i][j]);
-            const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;      // window: one block around the tile's blocks
-            constexpr int MAXR = (kMaxPruneCand + 255) / 256;
-            unsigned keep_bits[MAXR];      // per round: this lane's mask (0 = dropped)
-            const int rounds = (prm.n_cand + 255) / 256;
-#pragma unroll
-            for (int rd = 0; rd < MAXR; ++rd) {
-                keep_bits[rd] = 0u;
-                if (rd < rounds) {
-                    const int c = rd * 256 + warp * 32 + lane;
-                    unsigned bits = 0u;
-                    if (c < prm.n_cand) {
-                        const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
-                        float m[SBX + 2][SBY + 2];
-#pragma unroll
-                        for (int i = 0; i < SBX + 2; ++i) {
-                            int wx = (bx0 + i) % prm.nbx;
-                            if (wx < 0) wx += prm.nbx;
-#pragma unroll
-                            for (int j = 0; j < SBY + 2; ++j) {
-                                int wy = (by0 + j) % prm.nby;
-                                if (wy < 0) wy += prm.nby;
-                                m[i][j] = __ldg(pm + wx * prm.nby_alloc + wy);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < SBX; ++i)
-#pragma unroll
-                            for (int j = 0; j < SBY; ++j) {
-                                float mm = 0.f;
-#pragma unroll
-                                for (int di = 0; di < 3; ++di)
-#pragma unroll
-                                    for (int dj = 0; dj < 3; ++dj) mm = fmaxf(mm, m[i + di][j + dj]);
-                                if (!(mm * 1.0002f < thr[i][j])) bits |= 1u << (i * SBY + j);
-                            }
-                    }
-                    keep_bits[rd] = bits;
-                    const unsigned bal = __ballot_sync(0xffffffffu, bits != 0u);
-                    if (lane == 0) s_wcnt[rd][warp] = __popc(bal);
-                }
-            }
-            __syncthreads();
-            int cnt = 0;
-#pragma unroll
-            for (int rd = 0; rd < MAXR; ++rd) {
-                if (rd < rounds) {
-                    int before = cnt;
-                    for (int w = 0; w < 8; ++w) {
-                        const int n_w = s_wcnt[rd][w];
-                        if (w < warp) before += n_w;
-                        cnt += n_w;
-                    }
-                    const bool keep = keep_bits[rd] != 0u;
-                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                    if (keep) {
-                        const int pos = before + __popc(bal & ((1u << lane) - 1u));
-                        s_list[pos] = (unsigned short)(rd * 256 + warp * 32 + lane);
-                        s_mask[pos] = keep_bits[rd];
-                    }
-                }
-            }
-            if (threadIdx.x == 0) s_cnt = cnt;
+                for (int j = 0; j < SBY; ++j) nb |= s_blk[i][j] == 0;
+            s_needboot = nb;
         }
+        if (threadIdx.x < SBX * SBY) s_boot[threadIdx.x] = 0;
         __syncthreads();
-        n_live = s_cnt;
     }
+    const bool boot = prune && s_needboot != 0;
     auto cand_of = [&](int i) -> int { return prune ? (int)s_list[i] : i; };
     // this thread's share of the coarse tile: fixed (row, col) offsets, wrapped once
     int off[PER];
@@ -984,17 +922,18 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    int gb = 0;        // tiles staged by earlier passes: buffer choice and mbarrier parity continue across the passes
     auto fetch = [&](int i) {
         if (tma) {
             if (i < n_live && threadIdx.x == 0) {
-                mbar_expect_tx(&s_bar[i & 1], CX * CYB * 8);
-                tma_load_3d(smem + (i & 1) * CTILE, &tmap, &s_bar[i & 1], 2 * (c_lo - 1), r_lo, pl * prm.n_cand + cand_of(i));
+                mbar_expect_tx(&s_bar[(gb + i) & 1], CX * CYB * 8);
+                tma_load_3d(smem + ((gb + i) & 1) * CTILE, &tmap, &s_bar[(gb + i) & 1], 2 * (c_lo - 1), r_lo, pl * prm.n_cand + cand_of(i));
             }
             return;
         }
         if (i < n_live) {
             const float2* __restrict__ g = src + (size_t)cand_of(i) * Nd * Md;
-            float2* dst = smem + (i & 1) * CTILE;
+            float2* dst = smem + ((gb + i) & 1) * CTILE;
 #pragma unroll
             for (int e = 0; e < PER; ++e)
                 if (off[e] >= 0) cp_async8(dst + threadIdx.x + e * 256, g + off[e]);
@@ -1003,15 +942,15 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
     };
     auto landed = [&](int i) {          // tile i is in shared memory (for this thread; the CTA barrier that follows covers the rest)
         if (tma) {
-            if (i < n_live) mbar_wait(&s_bar[i & 1], (unsigned)(i >> 1) & 1u);
+            if (i < n_live) mbar_wait(&s_bar[(gb + i) & 1], (unsigned)((gb + i) >> 1) & 1u);
         } else {
             cp_async_wait_all();
         }
     };
     // along x: p3t[cy][x] = sum_w tbx[x % S][w] p2c[x / S + w][cy], tasks of Q3 outputs
     auto interp_x = [&](int c) {
-        const float2* p2c = smem + (c & 1) * CTILE;
-        float2* p3t = p3t0 + (c & 1) * CY * P3P;
+        const float2* p2c = smem + ((gb + c) & 1) * CTILE;
+        float2* p3t = p3t0 + ((gb + c) & 1) * CY * P3P;
         const unsigned live = prune ? s_mask[c] : 0xffffffffu;
 #pragma unroll
         for (int e = 0; e < PER3; ++e) {
@@ -1026,10 +965,141 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
             for (int p = 0; p < Q3; ++p) p3t[cy * P3P + xb * Q3 + p] = acc[p];
         }
     };
+    // block minima of this plane's best so far -> s_new (all threads; ends with a barrier)
+    auto block_min_of_best = [&]() {
+        constexpr int BPX = kPmB * S;
+        __syncthreads();                    // every warp is past its last use of the lists
+        if (threadIdx.x < SBX * SBY) s_new[threadIdx.x / SBY][threadIdx.x % SBY] = 0x7f7fffff;
+        __syncthreads();
+        constexpr int SPANX = BPX < 32 ? BPX : 32;       // lanes (rows) of a warp inside one bound-block row
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int x = x0 + lane + 32 * h;
+            float mn = 3.4028234e38f;
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const int y = y0 + wcol[h] * kP + p;
+                if (x < prm.N && y < prm.M) mn = fminf(mn, best[h][p]);
+            }
+#pragma unroll
+            for (int o = SPANX / 2; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (lane % SPANX == 0) atomicMin(&s_new[(lane + 32 * h) / BPX][(wcol[h] * kP) / BPX], __float_as_int(mn));
+        }
+        __syncthreads();
+    };
+    // Two passes when the tile has no recorded winners yet (its first plane): pass 0 sweeps only the candidate with the
+    // largest bound of every bound block (<= SBX SBY candidates), its results become the block thresholds, and pass 1 is
+    // the regular pruned sweep against them — instead of all candidates unpruned (a first-plane CTA cost 2.6 x an
+    // average one; on a k-grid sharded over 8 GPUs one plane in five is a first plane).  Exact like the pruning itself:
+    // the thresholds are amplitudes of candidates of this very plane.
+    __syncthreads();              // mbarrier initialisation visible before the first TMA / wait
+    for (int pass = boot ? 0 : 1; pass < 2; ++pass) {
+    if (prune) {
+        // survivor search, all 8 warps: warp w tests candidates [32 w, 32 w + 32), [32 w + 256, ...) and writes its survivors
+        // in candidate order through a CTA-wide prefix over the per-(round, warp) counts — the list comes out in exactly
+        // the order the serial search of warp 0 produced (it took ~10 % of a pruned CTA's life)
+        __shared__ int s_wcnt[(kMaxPruneCand + 255) / 256][8];
+        float thr[SBX][SBY];
+#pragma unroll
+        for (int i = 0; i < SBX; ++i)
+#pragma unroll
+            for (int j = 0; j < SBY; ++j) thr[i][j] = __int_as_float(s_blk[i][j]);
+        const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;      // window: one block around the tile's blocks
+        constexpr int MAXR = (kMaxPruneCand + 255) / 256;
+        unsigned keep_bits[MAXR];      // per round: this lane's mask (0 = dropped)
+        const int rounds = (prm.n_cand + 255) / 256;
+#pragma unroll
+        for (int rd = 0; rd < MAXR; ++rd) {
+            keep_bits[rd] = 0u;
+            if (rd < rounds) {
+                const int c = rd * 256 + warp * 32 + lane;
+                unsigned bits = 0u;
+                float bnd[SBX * SBY];
+#pragma unroll
+                for (int b = 0; b < SBX * SBY; ++b) bnd[b] = 0.f;
+                if (c < prm.n_cand) {
+                    const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
+                    float m[SBX + 2][SBY + 2];
+#pragma unroll
+                    for (int i = 0; i < SBX + 2; ++i) {
+                        int wx = (bx0 + i) % prm.nbx;
+                        if (wx < 0) wx += prm.nbx;
+#pragma unroll
+                        for (int j = 0; j < SBY + 2; ++j) {
+                            int wy = (by0 + j) % prm.nby;
+                            if (wy < 0) wy += prm.nby;
+                            m[i][j] = __ldg(pm + wx * prm.nby_alloc + wy);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < SBX; ++i)
+#pragma unroll
+                        for (int j = 0; j < SBY; ++j) {
+                            float mm = 0.f;
+#pragma unroll
+                            for (int di = 0; di < 3; ++di)
+#pragma unroll
+                                for (int dj = 0; dj < 3; ++dj) mm = fmaxf(mm, m[i + di][j + dj]);
+                            if (!(mm * 1.0002f < thr[i][j])) bits |= 1u << (i * SBY + j);
+                            bnd[i * SBY + j] = mm;
+                        }
+                }
+                if (pass == 0) {      // bootstrap pass: only the best-bounded candidate of every block is wanted
+#pragma unroll
+                    for (int b = 0; b < SBX * SBY; ++b) {
+                        const unsigned k32 = c < prm.n_cand ? ((__float_as_uint(bnd[b]) & 0xfffff800u) | (unsigned)c) : 0u;
+                        const unsigned best_k = __reduce_max_sync(0xffffffffu, k32);
+                        if (lane == 0) atomicMax(&s_boot[b], (int)(best_k & 0x7fffffffu));
+                    }
+                    bits = 0u;
+                }
+                keep_bits[rd] = bits;
+                const unsigned bal = __ballot_sync(0xffffffffu, bits != 0u);
+                if (lane == 0) s_wcnt[rd][warp] = __popc(bal);
+            }
+        }
+        __syncthreads();
+        int cnt = 0;
+#pragma unroll
+        for (int rd = 0; rd < MAXR; ++rd) {
+            if (rd < rounds) {
+                int before = cnt;
+                for (int w = 0; w < 8; ++w) {
+                    const int n_w = s_wcnt[rd][w];
+                    if (w < warp) before += n_w;
+                    cnt += n_w;
+                }
+                const bool keep = keep_bits[rd] != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+                    s_list[pos] = (unsigned short)(rd * 256 + warp * 32 + lane);
+                    s_mask[pos] = keep_bits[rd];
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            if (pass == 0) {      // the (distinct) bootstrap candidates, alive everywhere
+                cnt = 0;
+                for (int b = 0; b < SBX * SBY; ++b) {
+                    const unsigned short cb = (unsigned short)(s_boot[b] & 0x7ff);
+                    bool dup = false;
+                    for (int k = 0; k < cnt; ++k) dup |= s_list[k] == cb;
+                    if (!dup) {
+                        s_list[cnt] = cb;
+                        s_mask[cnt] = 0xffffffffu;
+                        ++cnt;
+                    }
+                }
+            }
+            s_cnt = cnt;
+        }
+        __syncthreads();
+        n_live = s_cnt;
+    }
     // Software pipeline over candidates, ONE barrier per candidate: in phase c every thread
     // interpolates candidate c+1 along x (into the other p3t buffer) and candidate c along y (+ arg-max),
     // while cp.async brings in the coarse tile of candidate c+2.
-    __syncthreads();              // mbarrier initialisation visible before the first TMA / wait
     fetch(0);
     fetch(1);
     if (tma) landed(0);
@@ -1043,7 +1113,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
         fetch(i + 2);
         if (i + 1 < n_live) interp_x(i + 1);
         // ---- along y in registers + arg-max: thread = (x = lane + 32 h, 16 columns of block wcol[h])
-        const float2* p3t = p3t0 + (i & 1) * CY * P3P;
+        const float2* p3t = p3t0 + ((gb + i) & 1) * CY * P3P;
         const unsigned cr = (unsigned)c * (IB == 8 ? 0x01010101u : 0x00010001u);
         const unsigned live = prune ? s_mask[i] : 0xffffffffu;
 #pragma unroll
@@ -1065,6 +1135,16 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
         }
     }
     cp_async_wait_all();
+    gb += n_live;
+    if (pass == 0) {              // the bootstrap candidates' amplitudes are the thresholds of the real sweep
+        block_min_of_best();
+        if (threadIdx.x < SBX * SBY) {
+            const int i = threadIdx.x / SBY, j = threadIdx.x % SBY;
+            if (s_new[i][j] != 0x7f7fffff) s_blk[i][j] = max(s_blk[i][j] == 0x7f7fffff ? 0 : s_blk[i][j], s_new[i][j]);
+        }
+        __syncthreads();
+    }
+    }       // pass
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int x = x0 + lane + 32 * h;
@@ -1084,25 +1164,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
         // Publish what this CTA learned: min over a bound block of max(old winner, this plane's best) >= max(old block
         // minimum, block minimum of this plane's best) is a lower bound of the final winners of the block.
         constexpr int BPX = kPmB * S;
-        __shared__ int s_new[SBX][SBY];
-        __syncthreads();                    // every warp is past its last use of s_blk / s_mask
-        if (threadIdx.x < SBX * SBY) s_new[threadIdx.x / SBY][threadIdx.x % SBY] = 0x7f7fffff;
-        __syncthreads();
-        constexpr int SPANX = BPX < 32 ? BPX : 32;       // lanes (rows) of a warp inside one bound-block row
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int x = x0 + lane + 32 * h;
-            float mn = 3.4028234e38f;
-#pragma unroll
-            for (int p = 0; p < kP; ++p) {
-                const int y = y0 + wcol[h] * kP + p;
-                if (x < prm.N && y < prm.M) mn = fminf(mn, best[h][p]);
-            }
-#pragma unroll
-            for (int o = SPANX / 2; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            if (lane % SPANX == 0) atomicMin(&s_new[(lane + 32 * h) / BPX][(wcol[h] * kP) / BPX], __float_as_int(mn));
-        }
-        __syncthreads();
+        block_min_of_best();
         if (threadIdx.x < SBX * SBY) {
             const int i = threadIdx.x / SBY, j = threadIdx.x % SBY;
             const int gbx = x0 / BPX + i, gby = y0 / BPX + j;
