@@ -752,8 +752,9 @@ static int finalize_mr(int N, int M, const double* wx_rows, int n_rows, const do
     KernelTimer timer("k_mr_finalize", st);
     if (n_dst > 0) {   // a rank's share of the planes: CTA-level compaction of the owned pixels, owner-writes
         // tile rows per CTA: ~256 owned pixels per 256-thread CTA (a rank owns about total / n_planes of the pixels)
-        const bool small_share = !nothing && (long long)total * 6 <= n_planes;
-        const int fx = small_share ? 32 : 16;
+        // (measured on a C3 share: 32 rows beat 16 from a third of the planes down — 0.62 -> 0.58 ms at 1/4 — and 64 rows lose
+        // again at 1/8, 0.45 -> 0.53 ms: too few CTAs)
+        const int fx = (!nothing && (long long)total * 3 <= n_planes) ? 32 : 16;
         dim3 grid(ceil_div(M, 64), ceil_div(N, fx));
 #define GPA_MRFINS2(SS, TT)                                                                       \
         do {                                                                                          \
