@@ -49,3 +49,35 @@ def test_frame_series_matches_single_frame_api_and_oracle():
     assert flips.mean() < 1e-3
     near = ndi.binary_dilation(flips, iterations=2)
     assert np.abs(res[1]["u"] - u_ref).max(axis=0)[~near].max() < DISP_TOL
+
+
+@pytest.mark.parametrize("streams,graphs", [(2, False), (1, True), (3, True)])
+def test_stream_pool_and_graph_replay_equal_the_plain_pipeline(streams, graphs):
+    """FramePipeline.submit spreads frames over CUDA streams (each with its own scratch) and can replay the per-frame chain
+    as one CUDA graph per stream: both must return exactly what the plain call returns, frame after frame."""
+    import torch
+    from pygpa_b200 import engine
+    dev = engine.require_cuda()
+    shape = (128, 256)
+    ks = synth.primary_ks(0.1, 7.0, 3)
+    base = synth.smooth_random_field(shape, 0.05, seed=5)
+    frames = [torch.from_numpy(synth.lattice_image(shape, ks, base * (1 + 0.1 * t), noise=0.1, seed=200 + t)).to(dev)
+              for t in range(7)]
+    plain = batch.FramePipeline(shape, ks, device=dev)
+    want = [{k: v.clone() for k, v in plain(f).items()} for f in frames]
+    pool = batch.FramePipeline(shape, ks, device=dev, streams=streams, graphs=graphs)
+    for t, f in enumerate(frames):
+        res = pool.submit(f)
+        pool.join()
+        torch.cuda.synchronize()
+        for k in ("u", "corrected"):
+            assert torch.equal(res[k], want[t][k]), (t, k)
+    if graphs:
+        assert all(slot is not None for slot in pool._slots[:min(streams, len(frames) // 2)])
+    # several frames in flight at once, joined at the end
+    outs = [{k: v.clone() for k, v in pool.submit(f).items()} if graphs else pool.submit(f) for f in frames[:streams]]
+    pool.join()
+    torch.cuda.synchronize()
+    if not graphs:
+        for t, res in enumerate(outs):
+            assert torch.equal(res["u"], want[t]["u"])

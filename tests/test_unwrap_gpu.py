@@ -160,3 +160,30 @@ def test_solver_helper_mirrors(shape):
     wwx, wwy = rng.random((n, m - 1)), rng.random((n - 1, m))
     p = rng.normal(size=shape)
     assert np.allclose(PU.applyQ(p, wwx, wwy), ref_numpy._apply_q(p, wwx, wwy), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (512, 512), (1024, 1024), (2048, 2048), (4096, 4096), (300, 256), (256, 258), (512, 770)])
+def test_pipelined_dct_kernels_agree_with_the_one_cta_per_pair_kernels(shape):
+    """The pipelined K2 kernels (bulk-copy prefetch, TMA column strips, <r, z> from the DCT coefficients, fused direction
+    update) against the kernels they replace (gpa_set_dct_pipeline(0)): transforms to rounding, PCG iterates to 1e-11,
+    same iteration count.  (Both are compared with scipy / the oracle elsewhere in this file.)"""
+    from pygpa_b200 import _lib
+    lib = _lib.load()
+    psi, w = _case(shape, 11 + sum(shape), 0.05)
+    dev = solvers.require_cuda()
+    x, wd = solvers.to_device_f64(psi, dev), solvers.to_device_f64(w, dev)
+    got = {}
+    try:
+        for mode in (0, 1):
+            lib.gpa_set_dct_pipeline(mode)
+            f = solvers.dctn(x)
+            b = solvers.dctn(f, inverse=True)
+            phi, it = solvers.unwrap(psi=x, weight=wd, kmax=12, return_iters=True)
+            got[mode] = (f.cpu().numpy(), b.cpu().numpy(), phi.cpu().numpy(), it)
+    finally:
+        lib.gpa_set_dct_pipeline(1)
+    scale = np.abs(got[0][0]).max()
+    assert np.abs(got[0][0] - got[1][0]).max() < 1e-13 * scale
+    assert np.abs(got[1][1] - psi).max() < 1e-12
+    assert got[0][3] == got[1][3]
+    assert np.abs(got[0][2] - got[1][2]).max() < 1e-11 * max(1.0, np.abs(got[0][2]).max())
