@@ -15,7 +15,7 @@ TWO_PI = 2.0 * np.pi
 
 __all__ = [
     "wrap_to_pi", "gaussian_transfer", "lockin_fixed", "candidate_axes", "wfr_sweep",
-    "wfr_sweep_klist", "wfr4", "wfr4_allowed", "fit_plane", "iterate_GPA", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
+    "wfr_sweep_klist", "wfr2_grad", "wfr4", "wfr4_allowed", "fit_plane", "iterate_GPA", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
     "reconstruct_u_inv", "reconstruct_u_inv_from_phases", "invert_u_overlap",
     "undistort_image", "extract_displacement_field", "fixed_reference_pipeline",
 ]
@@ -135,6 +135,41 @@ def wfr_sweep(image, sigma, kx, ky, kw, kstep, grad_mode=None, want_grad=True,
     out = wfr_sweep_klist(image, sigma, klist, (kx, ky), grad_mode, want_grad, return_diag)
     out['wxs'], out['wys'] = wxs, wys
     return out
+
+
+def wfr2_grad(image, sigma, kx, ky, kw, kstep, grad=None):
+    """geometric_phase_analysis.py:722-760: like wfr_sweep, but the gradient function (None = np.gradient, 'diff' =
+    np.diff with a NaN appended — axis 1 first there, :739-743 — or a callable) is applied to the phase of every
+    candidate's RE-REFERENCED lock-in and wrapped per candidate.  Returns dict(lockin, w (2,N,M), grad, kidx)."""
+    image = np.asarray(image, dtype=np.float64)
+    shape = image.shape
+    transfer = gaussian_transfer(shape, sigma)
+    x = np.arange(shape[0])[:, None]
+    y = np.arange(shape[1])[None, :]
+    if isinstance(grad, str) and grad == 'diff':
+        def grad_func(phase):
+            return np.stack([np.diff(phase, axis=1, append=np.nan), np.diff(phase, axis=0, append=np.nan)], axis=-1)
+    elif grad is None:
+        def grad_func(phase):
+            return np.stack(np.gradient(phase), axis=-1)
+    else:
+        grad_func = grad
+    lockin = np.zeros(shape, dtype=np.complex128)
+    w = np.zeros(shape + (2,))
+    g_out = np.zeros(shape + (2,))
+    kidx = np.full(shape, -1, dtype=np.int32)
+    wxs, wys = candidate_axes(kx, ky, kw, kstep)
+    for ix, wx in enumerate(wxs):
+        for iy, wy in enumerate(wys):
+            sf = np.fft.ifft2(np.fft.fft2(image * np.exp(TWO_PI * 1j * (x * wx + y * wy))) * transfer)
+            sf = sf * np.exp(-TWO_PI * 1j * ((wx - kx) * x + (wy - ky) * y))
+            g = wrap_to_pi(grad_func(-np.angle(sf)) * 2) / 2
+            take = np.abs(sf) > np.abs(lockin)
+            lockin[take] = sf[take]
+            w[take] = (wx, wy)
+            g_out[take] = g[take]
+            kidx[take] = ix * len(wys) + iy
+    return {'lockin': lockin, 'w': np.moveaxis(w, -1, 0), 'grad': g_out, 'kidx': kidx}
 
 
 def wfr4_allowed(klist, dk):

@@ -9,8 +9,8 @@ tests/test_cuGPA.py:46-49).
 Differences, all deliberate (DESIGN.md "Deviations"):
   * arithmetic is fp32 with a Gaussian truncated at 4.5 sigma instead of complex128 FFTs:
     phases agree to < 1e-3 rad, the selected k-vector is identical except at near-ties;
-  * ``grad`` may be None or 'diff'; a callable cannot run inside the fused kernel and
-    raises NotImplementedError (there is no CPU fallback);
+  * ``grad`` None and 'diff' run inside the fused kernel; a callable gets NumPy arrays (there is no CuPy here) and is
+    applied, unfused, to the phase image of every distinct winning candidate (see _grad_by_winner);
   * ``cuGPA()`` returns a CuPy array only when CuPy is importable, else a NumPy array.
 """
 from __future__ import annotations
@@ -29,9 +29,53 @@ def _grad_mode(grad):
         return engine.GRAD_CENTRAL
     if isinstance(grad, str) and grad == 'diff':
         return engine.GRAD_FORWARD
-    raise NotImplementedError(
-        "grad must be None (np.gradient) or 'diff'; a user callable cannot be fused into the "
-        "CUDA sweep and pygpa_b200 has no CPU fallback")
+    if callable(grad):
+        return None          # unfused: _grad_by_winner
+    raise ValueError("grad must be None (np.gradient), 'diff' or a callable")
+
+
+def _grad_by_winner(image, sigma, kx, ky, kw, kstep, grad_func, rereference, want_w=True):
+    """Sweep with a user gradient function.  The reference applies grad_func to the phase image of EVERY candidate and
+    keeps, per pixel, the value of the last candidate that won (cuGPA.py:66-82, geometric_phase_analysis.py:745-757) —
+    i.e. of the final winner.  A callable cannot run inside the fused kernel, so: arg-max sweep on the GPU, then ONE
+    fixed lock-in (gpa_lockin_fixed) per DISTINCT winning candidate, grad_func on its phase image on the host, and
+    the pixels that candidate won are filled.  rereference: True = geometric_phase_analysis.wfr2_grad (gradient of the
+    re-referenced phase, wrapped per candidate), False = cuGPA.wfr2_grad_opt (raw phase + 2 pi (w - k), wrapped at
+    the end).  grad_func gets a NumPy float64 array (CuPy does not exist here) and returns an (N, M, 2) array or a
+    pair of (N, M) arrays."""
+    device = engine.require_cuda()
+    img = engine.image_to_device(image, device)
+    plan = _plan_for(img.shape, sigma, kx, ky, kw, kstep, device)
+    res = plan.run(img, (kx, ky), engine.GRAD_NONE, out_f64=True, want_w=want_w, want_kidx=True)
+    host = {k: _to_host(res[k]) for k in ("lockin", "w", "kidx") if res.get(k) is not None}
+    torch.cuda.current_stream().synchronize()
+    out = {k: v.numpy() for k, v in host.items()}
+    kidx = out.pop("kidx")
+    n, m = kidx.shape
+    wxs, wys = plan.wx, plan.wy
+    xx, yy = np.ogrid[0:n, 0:m]
+    grad = np.zeros((n, m, 2))
+    two_pi = 2 * np.pi
+
+    def wrap(v):
+        return (v + np.pi) % two_pi - np.pi
+    for c in np.unique(kidx[kidx >= 0]):
+        wx, wy = float(wxs[c // wys.size]), float(wys[c % wys.size])
+        sf_t = _to_host(engine.lockin_fixed(img, (wx, wy), sigma, out_f64=True))
+        torch.cuda.current_stream().synchronize()
+        sf = sf_t.numpy()
+        if rereference:
+            sf = sf * np.exp(-2j * np.pi * ((wx - kx) * xx + (wy - ky) * yy))
+        g = grad_func(-np.angle(sf))
+        g = np.stack(g, axis=-1) if isinstance(g, (tuple, list)) else np.asarray(g)
+        if rereference:
+            g = wrap(g * 2) / 2
+        else:
+            g = g + two_pi * np.array([wx - kx, wy - ky])
+        t = kidx == c
+        grad[t] = g[t]
+    out["grad"] = grad if rereference else wrap(2 * grad) / 2
+    return out
 
 
 def _to_host(t):
@@ -102,12 +146,16 @@ def cuGPA(image, kvec, sigma=22):
 def wfr2_grad_opt(image, sigma, kx, ky, kw, kstep, grad=None):
     """Adaptive GPA: dict with 'lockin' (N,M) c16, 'w' (2,N,M) f8, 'grad' (N,M,2) f8
     (cuGPA.py:41-87)."""
+    if _grad_mode(grad) is None:
+        return _grad_by_winner(image, sigma, kx, ky, kw, kstep, grad, rereference=False)
     return _sweep(image, sigma, kx, ky, kw, kstep, _grad_mode(grad), want_w=True)
 
 
 def wfr2_grad_single(image, sigma, kx, ky, kw, kstep, grad=None):
     """cuGPA.py:90-133: like wfr2_grad_opt without 'w' (the reference's arithmetic is promoted
     to double by NumPy/CuPy type rules, so the outputs are float64 / complex128 there too)."""
+    if _grad_mode(grad) is None:
+        return _grad_by_winner(image, sigma, kx, ky, kw, kstep, grad, rereference=False, want_w=False)
     return _sweep(image, sigma, kx, ky, kw, kstep, _grad_mode(grad), want_w=False)
 
 
@@ -120,6 +168,8 @@ def wfr2_only_lockin(image, sigma, kvec, kw, kstep):
 def wfr2_only_grad(image, sigma, kvec, kw, kstep, grad=None):
     """cuGPA.py:161-202: only the phase gradient (N, M, 2)."""
     kx, ky = kvec
+    if _grad_mode(grad) is None:
+        return _grad_by_winner(image, sigma, kx, ky, kw, kstep, grad, rereference=False, want_w=False)['grad']
     return _sweep(image, sigma, kx, ky, kw, kstep, _grad_mode(grad), want_w=False)['grad']
 
 

@@ -50,12 +50,22 @@ def wfr2_grad_opt(image, sigma, kx, ky, kw, kstep):
 
 
 def wfr2_grad(image, sigma, kx, ky, kw, kstep, grad=None):
-    """geometric_phase_analysis.py:722-760.  The reference computes the gradient of the
-    RE-REFERENCED lock-in of every candidate and wraps it per candidate; the winner's value
-    is the same as wfr2_grad_opt's, which is what runs here (grad=None only)."""
-    if grad is not None:
-        raise NotImplementedError("wfr2_grad on B200 supports grad=None only")
-    return _sweep(image, sigma, kx, ky, kw, kstep, engine.GRAD_CENTRAL, want_w=True)
+    """geometric_phase_analysis.py:722-760.  The reference computes the gradient of the RE-REFERENCED lock-in of every
+    candidate and wraps it per candidate.  grad=None: the winner's value is the same as wfr2_grad_opt's, which is what
+    runs (fused).  grad='diff' (np.diff with a NaN appended; note the reference pairs axis 1 with the first gradient
+    component here, unlike cuGPA) and a callable run unfused: one fixed lock-in per distinct winning candidate and the
+    gradient function on the host (cuGPA._grad_by_winner)."""
+    if grad is None:
+        return _sweep(image, sigma, kx, ky, kw, kstep, engine.GRAD_CENTRAL, want_w=True)
+    if isinstance(grad, str):
+        if grad != 'diff':
+            raise ValueError("grad must be None, 'diff' or a callable")
+
+        def grad(phase):          # verbatim from the reference (:739-743)
+            dbdx = np.diff(phase, axis=1, append=np.nan)
+            dbdy = np.diff(phase, axis=0, append=np.nan)
+            return np.stack([dbdx, dbdy], axis=-1)
+    return _cu._grad_by_winner(image, sigma, kx, ky, kw, kstep, grad, rereference=True)
 
 
 def optwfr2(image, sigma, kx, ky, kw, kstep):

@@ -46,8 +46,9 @@ def test_candidate_axes_match_oracle_expression():
 def test_grad_argument_handling():
     assert cuGPA._grad_mode(None) == engine.GRAD_CENTRAL
     assert cuGPA._grad_mode('diff') == engine.GRAD_FORWARD
-    with pytest.raises(NotImplementedError):
-        cuGPA._grad_mode(lambda p: np.gradient(p))
+    assert cuGPA._grad_mode(lambda p: np.gradient(p)) is None      # a callable runs unfused (cuGPA._grad_by_winner)
+    with pytest.raises(ValueError):
+        cuGPA._grad_mode('central')
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -36,6 +36,21 @@ def test_sweep_bit_identical(ref, case):
         assert np.array_equal(r[key], o[key]), key
 
 
+@pytest.mark.parametrize("grad", [None, 'diff', 'callable'])
+def test_wfr2_grad_all_gradient_modes(ref, case, grad, capsys):
+    """geometric_phase_analysis.py:722-760 with grad = None / 'diff' / a callable (here: one-sided differences)."""
+    gpa, _ = ref
+    k = case["ks"][0]
+
+    def one_sided(phase):
+        return np.stack([np.diff(phase, axis=0, prepend=phase[:1]), np.diff(phase, axis=1, prepend=phase[:, :1])], axis=-1)
+    arg = one_sided if grad == 'callable' else grad
+    r = gpa.wfr2_grad(case["img"], case["sigma"], k[0], k[1], case["kw"], case["kstep"], grad=arg)
+    o = oracle.wfr2_grad(case["img"], case["sigma"], k[0], k[1], case["kw"], case["kstep"], grad=arg)
+    for key in ("lockin", "w", "grad"):
+        assert np.array_equal(r[key], o[key], equal_nan=True), key
+
+
 def test_tail_and_lstsq(ref, case):
     gpa, pu = ref
     gs = [oracle.wfr_sweep(case["img"], case["sigma"], k[0], k[1], case["kw"], case["kstep"],

@@ -63,8 +63,42 @@ def test_forward_difference_gradient_mode(noisy_case):
     check_sweep(got, ref)
     only = cuGPA.wfr2_only_grad(c["img"], c["sigma"], tuple(k), c["kw"], c["kstep"], grad='diff')
     assert np.array_equal(np.isnan(only), np.isnan(got["grad"]))
-    with pytest.raises(NotImplementedError):
-        cuGPA.wfr2_grad_opt(c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"], grad=np.gradient)
+
+
+def _grad_close(a, b, tol=1e-3):
+    """phase gradients are defined modulo pi (geometric_phase_analysis.py:812); NaNs must coincide"""
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    d = np.abs(a - b)
+    d = np.minimum(d, np.abs(d - np.pi))
+    return np.nanmax(d) < tol
+
+
+def test_gradient_callable_and_wfr2_grad_modes(noisy_case):
+    """grad=<callable> (cuGPA.py:66-67) and geometric_phase_analysis.wfr2_grad(grad='diff' | callable) (:722-760) run
+    unfused — one fixed lock-in per distinct winning candidate, the gradient function on the host — and must give what
+    the reference's per-candidate loop gives wherever the same candidate wins."""
+    c = noisy_case
+    k = c["ks"][0]
+    args = (c["img"], c["sigma"], k[0], k[1], c["kw"], c["kstep"])
+    fused = cuGPA.wfr2_grad_opt(*args)
+    unfused = cuGPA.wfr2_grad_opt(*args, grad=np.gradient)              # np.gradient returns the pair cp.gradient does
+    assert np.array_equal(fused["lockin"], unfused["lockin"]) and np.array_equal(fused["w"], unfused["w"])
+    assert _grad_close(fused["grad"], unfused["grad"])
+    assert _grad_close(cuGPA.wfr2_only_grad(c["img"], c["sigma"], tuple(k), c["kw"], c["kstep"], grad=np.gradient), fused["grad"])
+    assert set(cuGPA.wfr2_grad_single(*args, grad=np.gradient)) == {"lockin", "grad"}
+
+    def one_sided(phase):
+        return np.stack([np.diff(phase, axis=0, prepend=phase[:1]), np.diff(phase, axis=1, prepend=phase[:, :1])], axis=-1)
+    for grad in (None, 'diff', one_sided):
+        ref = oracle.wfr2_grad(*args, grad=grad)
+        got = GPA.wfr2_grad(*args, grad=grad)
+        same = np.all(got["w"] == ref["w"], axis=0)
+        assert same.mean() > 0.999
+        assert got["grad"].shape == c["img"].shape + (2,)
+        assert _grad_close(np.where(same[..., None], got["grad"], 0), np.where(same[..., None], ref["grad"], 0))
+        assert np.abs(np.angle(got["lockin"][same] * np.conj(ref["lockin"][same]))).max() < 1e-3
+    with pytest.raises(ValueError):
+        GPA.wfr2_grad(*args, grad='central')
 
 
 def test_config2_quarter_size_near_tie_accounting():
