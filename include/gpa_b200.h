@@ -373,6 +373,11 @@ int gpa_lawler_workspace_bytes(int N, int M, int edge, size_t* bytes);
 int gpa_invert_u(const double* u, int N, int M, double scale, int iters, int edge, double* out,
                  void* ws, size_t ws_bytes, void* stream);
 
+/* invert_u(us, iters, edge) of the reference (geometric_phase_analysis.py:248-259): out (2, N, M), u_it <- (scale u)(r),
+ * then `iters` times u_it <- (scale u)(r - edge + u_it) — the `- edge` enters the iterations only, as there. */
+int gpa_invert_u_plain(const double* u, int N, int M, double scale, int iters, int edge, double* out,
+                       void* ws, size_t ws_bytes, void* stream);
+
 /* out (N, M) = cubic-spline resampling of img at (r + u_inv[0], c + u_inv[1]), 0 outside the frame
  * (scipy mode='constant', cval=0). */
 int gpa_resample_image(const double* img, int N, int M, const double* u_inv, double* out,

@@ -16,7 +16,7 @@ TWO_PI = 2.0 * np.pi
 __all__ = [
     "wrap_to_pi", "gaussian_transfer", "lockin_fixed", "candidate_axes", "wfr_sweep",
     "wfr_sweep_klist", "wfr2_grad", "wfr4", "wfr4_allowed", "fit_plane", "iterate_GPA", "phase_unwrap", "phase_unwrap_prediff", "weighted_lstsq",
-    "reconstruct_u_inv", "reconstruct_u_inv_from_phases", "invert_u_overlap",
+    "reconstruct_u_inv", "reconstruct_u_inv_from_phases", "invert_u", "invert_u_overlap",
     "undistort_image", "extract_displacement_field", "fixed_reference_pipeline",
 ]
 
@@ -367,6 +367,16 @@ def invert_u_overlap(us, iters=35, edge=0, mode='nearest'):
     cur = [ndi.map_coordinates(c, [gx, gy], mode=mode) for c in us]
     for _ in range(iters):      # iters-1 plain rounds + the final one (cval is inert)
         cur = [ndi.map_coordinates(c, [gx + cur[0], gy + cur[1]], mode=mode) for c in us]
+    return np.stack(cur)
+
+
+def invert_u(us, iters=35, edge=0, mode='nearest'):
+    """geometric_phase_analysis.py:248-259: the variant on the (N, M) grid; `- edge` enters the iterations only."""
+    us = np.asarray(us, dtype=np.float64)
+    gx, gy = np.mgrid[:us.shape[1], :us.shape[2]]
+    cur = [ndi.map_coordinates(c, [gx, gy], mode=mode) for c in us]
+    for _ in range(iters):
+        cur = [ndi.map_coordinates(c, [gx + cur[0] - edge, gy + cur[1] - edge], mode=mode) for c in us]
     return np.stack(cur)
 
 

@@ -102,6 +102,7 @@ SIGNATURES = {
                                               c_void_p, c_size_t, c_void_p]),
     "gpa_lawler_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "gpa_invert_u": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpa_invert_u_plain": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_resample_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpa_undistort_image": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

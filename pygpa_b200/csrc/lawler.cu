@@ -214,15 +214,16 @@ __device__ __forceinline__ T spline_eval(const T* __restrict__ coef, int Np, int
 }
 
 // whole fixed-point inversion of one output pixel in registers:
-//   u_it <- u(r);  repeat iters times: u_it <- u(r + u_it)         (geometric_phase_analysis.py:291-299)
-__global__ void __launch_bounds__(256) k_invert_u(const double2* __restrict__ coef, int Np, int Mp, int N, int M,
-                                                  int edge, int iters, double* __restrict__ out) {
-    const int on = N + 2 * edge, om = M + 2 * edge;
+//   u_it <- u(r - e0);  repeat iters times: u_it <- u(r - e1 + u_it),  r on an (on, om) grid
+// invert_u_overlap (geometric_phase_analysis.py:291-299): e0 = e1 = edge on the grown grid (N + 2 edge, M + 2 edge);
+// invert_u (:255-258): e0 = 0, e1 = edge on the (N, M) grid (the reference's `- edge` only enters the iterations).
+__global__ void __launch_bounds__(256) k_invert_u(const double2* __restrict__ coef, int Np, int Mp, int on, int om,
+                                                  int e0, int e1, int iters, double* __restrict__ out) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (r >= on || c >= om) return;
-    const double x = (double)(r - edge) + kPad, y = (double)(c - edge) + kPad;   // padded-array coordinates
-    double2 u = spline_eval<kNearest>(coef, Np, Mp, x, y);
+    const double x = (double)(r - e1) + kPad, y = (double)(c - e1) + kPad;   // padded-array coordinates
+    double2 u = spline_eval<kNearest>(coef, Np, Mp, (double)(r - e0) + kPad, (double)(c - e0) + kPad);
     for (int it = 0; it < iters; ++it) u = spline_eval<kNearest>(coef, Np, Mp, x + u.x, y + u.y);
     out[(size_t)r * om + c] = u.x;
     out[(size_t)on * om + (size_t)r * om + c] = u.y;
@@ -283,8 +284,8 @@ extern "C" int gpa_lawler_workspace_bytes(int N, int M, int edge, size_t* bytes)
     return GPA_OK;
 }
 
-extern "C" int gpa_invert_u(const double* u, int N, int M, double scale, int iters, int edge, double* out,
-                            void* ws, size_t ws_bytes, void* stream) {
+static int invert_u_impl(const double* u, int N, int M, double scale, int iters, int edge, bool overlap, double* out,
+                         void* ws, size_t ws_bytes, void* stream) {
     GPA_REQUIRE(u && out && ws, "null pointer argument");
     GPA_REQUIRE(N >= 1 && M >= 1 && iters >= 0 && edge >= 0, "bad argument");
     const int Np = N + 2 * kPad, Mp = M + 2 * kPad;
@@ -306,11 +307,22 @@ extern "C" int gpa_invert_u(const double* u, int N, int M, double scale, int ite
     }
     {
         KernelTimer t("k_invert_u", st);
-        dim3 grid(ceil_div(M + 2 * edge, 32), ceil_div(N + 2 * edge, 8));
-        k_invert_u<<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(coef), Np, Mp, N, M, edge, iters, out);
+        const int on = overlap ? N + 2 * edge : N, om = overlap ? M + 2 * edge : M;
+        dim3 grid(ceil_div(om, 32), ceil_div(on, 8));
+        k_invert_u<<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(coef), Np, Mp, on, om, overlap ? edge : 0, edge, iters, out);
     }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
+}
+
+extern "C" int gpa_invert_u(const double* u, int N, int M, double scale, int iters, int edge, double* out,
+                            void* ws, size_t ws_bytes, void* stream) {
+    return invert_u_impl(u, N, M, scale, iters, edge, true, out, ws, ws_bytes, stream);
+}
+
+extern "C" int gpa_invert_u_plain(const double* u, int N, int M, double scale, int iters, int edge, double* out,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    return invert_u_impl(u, N, M, scale, iters, edge, false, out, ws, ws_bytes, stream);
 }
 
 extern "C" int gpa_resample_image(const double* img, int N, int M, const double* u_inv, double* out,

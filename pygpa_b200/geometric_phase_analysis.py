@@ -227,12 +227,15 @@ def invert_u_overlap(us, iters=35, edge=0, mode='nearest'):
 
 
 def invert_u(us, iters=35, edge=0, mode='nearest'):
-    """geometric_phase_analysis.py:248-259.  For edge = 0 (the only value for which the reference's
-    coordinate arithmetic is consistent) this equals invert_u_overlap: one initial evaluation and
-    `iters` fixed-point rounds."""
-    if edge != 0:
-        raise NotImplementedError("invert_u with edge != 0 is not supported; use invert_u_overlap")
-    return invert_u_overlap(us, iters=iters, edge=0, mode=mode)
+    """geometric_phase_analysis.py:248-259: one evaluation of us on the pixel grid, then `iters` fixed-point rounds
+    u_it <- us(r - edge + u_it) (the reference subtracts `edge` in the iterations only; reproduced as is)."""
+    if mode != 'nearest':
+        raise NotImplementedError("the B200 Lawler-Fujita kernel implements scipy mode='nearest' (the reference default)")
+    dev = engine.require_cuda()
+    us = np.asarray(us, dtype=np.float64)
+    if us.ndim != 3 or us.shape[0] != 2:
+        raise ValueError("us must have shape (2, N, M)")
+    return _host(solvers.invert_u(solvers.to_device_f64(us, dev), iters=iters, edge=edge, overlap=False))
 
 
 def undistort_image(deformed, u):

@@ -263,13 +263,16 @@ def _lawler_ws(n, m, edge, device):
     return workspace(nbytes.value, device)
 
 
-def invert_u(u, iters=35, edge=0, scale=1.0):
-    """Fixed-point inverse of the displacement field (2, N, M) -> (2, N+2e, M+2e), on the device."""
+def invert_u(u, iters=35, edge=0, scale=1.0, overlap=True):
+    """Fixed-point inverse of the displacement field (2, N, M), on the device: invert_u_overlap -> (2, N+2e, M+2e);
+    overlap=False: the reference's invert_u -> (2, N, M), `- edge` in the iterations only."""
     lib = _lib.load()
     n, m = int(u.shape[1]), int(u.shape[2])
     ws = _lawler_ws(n, m, edge, u.device)
-    out = torch.empty((2, n + 2 * edge, m + 2 * edge), dtype=torch.float64, device=u.device)
-    _lib.check(lib.gpa_invert_u(_ptr(u), n, m, float(scale), int(iters), int(edge), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    e_out = edge if overlap else 0
+    out = torch.empty((2, n + 2 * e_out, m + 2 * e_out), dtype=torch.float64, device=u.device)
+    fn = lib.gpa_invert_u if overlap else lib.gpa_invert_u_plain
+    _lib.check(fn(_ptr(u), n, m, float(scale), int(iters), int(edge), _ptr(out), _ptr(ws), ws.numel(), _stream()))
     _count(9)
     return out
 

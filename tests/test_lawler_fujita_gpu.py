@@ -21,6 +21,10 @@ def test_golden_fixture():
     assert np.abs(got - g["out_invert_edge3_it5"]).max() < 1e-9
     assert np.abs(GPA.undistort_image(img, u) - g["out_undistorted"]).max() < 1e-9
     assert np.abs(GPA.invert_u(u, iters=7) - oracle.invert_u_overlap(u, iters=7)).max() < 1e-9
+    for edge in (0, 3):        # the reference's invert_u: `- edge` in the iterations only (geometric_phase_analysis.py:257)
+        got = GPA.invert_u(u, iters=6, edge=edge)
+        assert got.shape == u.shape
+        assert np.abs(got - oracle.invert_u(u, iters=6, edge=edge)).max() < 1e-9
     with pytest.raises(NotImplementedError):
         GPA.invert_u_overlap(u, mode='reflect')
 

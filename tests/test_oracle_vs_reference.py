@@ -82,3 +82,13 @@ def test_lawler_fujita(ref, case):
     gpa, _ = ref
     u = synth.gaussian_bump(case["img"].shape)
     assert np.array_equal(gpa.undistort_image(case["img"], u), oracle.undistort_image(case["img"], u))
+
+
+def test_invert_u_with_edge(ref):
+    """geometric_phase_analysis.py:248-259, including edge != 0 (subtracted in the iterations only)."""
+    gpa, _ = ref
+    rng = np.random.default_rng(5)
+    x, y = np.mgrid[:40, :52]
+    u = np.stack([2.0 * np.sin(x / 9.0) * np.cos(y / 11.0), 1.5 * np.cos(x / 7.0)]) + 0.05 * rng.normal(size=(2, 40, 52))
+    for edge in (0, 2):
+        assert np.array_equal(gpa.invert_u(u, iters=6, edge=edge), oracle.invert_u(u, iters=6, edge=edge))
