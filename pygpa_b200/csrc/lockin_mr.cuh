@@ -1143,6 +1143,17 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
             if (s_new[i][j] != 0x7f7fffff) s_blk[i][j] = max(s_blk[i][j] == 0x7f7fffff ? 0 : s_blk[i][j], s_new[i][j]);
         }
         __syncthreads();
+        // ... and nothing else: the running winners start again from zero, so that pass 1 meets the candidates in
+        // ascending order and an exact tie goes to the lowest index, as in the reference's strict `>` loop
+        // (geometric_phase_analysis.py:806).  Keeping the bootstrap winners flipped a handful of exactly tied pixels
+        // per 2048^2 frame (caught by bench.py's N-GPU vs 1-GPU key comparison).
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) best[h][p] = 0.f;
+#pragma unroll
+            for (int p = 0; p < kP / IPR; ++p) bidx[h][p] = 0u;
+        }
     }
     }       // pass
 #pragma unroll

@@ -129,3 +129,27 @@ def test_config3_split_vs_single_stage_differences_are_near_ties(c3_runs):
     assert len(differ) < 2e-4 * a.size
     pts = [tuple(map(int, p)) for p in differ[:200]]
     _classify(c3_runs["gabor"], {"split": a, "direct": d}, pts, c3_runs["ny"])
+
+
+def test_c3_pruned_keys_bit_identical_to_unpruned_all_peaks():
+    """Exact pruning at the benchmarked size, every peak: 12.6 M pixels x 1 681 candidates contain a handful of EXACT
+    amplitude ties between different candidates, which the reference's strict `>` gives to the first candidate
+    (geometric_phase_analysis.py:806) — any change of the order in which a tile meets its candidates (the round-2 bootstrap
+    pass did, before its winners were discarded) shows up here and nowhere at 512^2."""
+    import torch
+    from pygpa_b200 import engine, synth
+    dev = engine.require_cuda()
+    cfg = synth.make_config("C3")
+    img = engine.image_to_device(cfg["image"], dev)
+    for k in cfg["ks"]:
+        wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
+        plan = engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev)
+        try:
+            engine.set_pruning(False)
+            ref = plan.run(img, k)["key"].clone()
+        finally:
+            engine.set_pruning(True)
+        got = plan.run(img, k)["key"]
+        assert torch.equal(ref, got), int((ref != got).sum())
+        del plan
+    engine.release_workspaces()
