@@ -1128,8 +1128,9 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
                 const float a2 = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
                 if (a2 > best[h][p]) {
                     best[h][p] = a2;
-                    const unsigned field = IMASK << ((p % IPR) * IB);
-                    bidx[h][p / IPR] = (bidx[h][p / IPR] & ~field) | (cr & field);
+                    const unsigned field = IMASK << ((p % IPR) * IB);      // a constant once the loop is unrolled
+                    // bit-field insert as ONE lop3 ((a & ~c) | (b & c)) — the compiler emitted three per output
+                    asm("lop3.b32 %0, %0, %1, %2, 0xD8;" : "+r"(bidx[h][p / IPR]) : "r"(cr), "r"(field));
                 }
             }
         }
