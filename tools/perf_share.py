@@ -21,7 +21,7 @@ plans = []
 for k in ks:
     wxs, wys = engine.grid_axes(k[0], k[1], cfg["kw"], cfg["kstep"])
     plans.append(engine.SweepPlan(img.shape, wxs, wys, cfg["sigma"], device=dev, private_ws=True))
-names = ("k_mr_pass1", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize")
+names = ("k_mr_pass1a", "k_mr_pass1b", "k_mr_pass2a", "k_mr_pass2b", "k_mr_order", "k_mr_interp", "k_mr_finalize")
 
 
 def read():
