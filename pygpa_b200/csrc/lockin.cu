@@ -335,14 +335,13 @@ static int fill_interp(TapTable& t, const float* bx, const float* by, int Rb, in
 
 // Split pass 1, anchor stage (once per call): the anchor plane n_planes / 2 filtered by G_1 at the full rate,
 // decimated, with its carrier masked to the frame body (part 0) and to the wrapped columns (part 1).
-template <int S>
-static int launch_anchor_y(const MrGeometry& g, const float* img, const TapTable& t1y, cudaStream_t st) {
+template <int S, int W1>
+static int launch_anchor_y_w(const MrGeometry& g, const float* img, const TapTable& t1y, cudaStream_t st) {
     MrPass1Params p;
     p.img = img; p.phy = g.phy; p.p1 = g.a_y; p.plane_stride = (size_t)g.rows_a * g.pitch_e;
     p.N = g.N; p.M = g.M; p.Md = g.MdE; p.pitch_d = g.pitch_e; p.n_rows_filled = g.n_rows_filled;
     p.Rax = g.row_shift; p.Ray = g.col_shift; p.J = g.J1y; p.plane0 = g.n_planes / 2; p.pstep = 0;
     p.count = 2; p.planes_per_cta = 2;
-    constexpr int W1 = 8;
     const size_t n_samp1 = (size_t)S * (W1 * kP + g.J1y + kAhead + 1);
     const size_t smem = (n_samp1 * 33 + 1) * sizeof(float) + 2 * n_samp1 * sizeof(float2);
     GPA_REQUIRE(smem <= 227 * 1024, "split pass 1: stage-A filter too long for shared memory (%zu bytes)", smem);
@@ -352,6 +351,27 @@ static int launch_anchor_y(const MrGeometry& g, const float* img, const TapTable
     k_mr_pass1<S, W1, true><<<grid, W1 * 32, smem, st>>>(p, t1y);
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
+}
+
+// The anchor stage is ONE plane per peak: a latency-bound launch of a few hundred CTAs (two per SM), replicated on every
+// rank of a sharded sweep.  The column tile W1 * 16 is chosen among 8 / 9 / 10 / 12 warps so that the grid needs the fewest
+// waves (C3: 69 x 5 = 345 CTAs = 2 waves with 8 warps, 69 x 4 = 276 = 1 wave with 9: 61 -> 3x us per peak).
+template <int S>
+static int launch_anchor_y(const MrGeometry& g, const float* img, const TapTable& t1y, cudaStream_t st) {
+    const int rows = ceil_div(g.n_rows_filled, 32), slots = 2 * 148;
+    int best_w = 8;
+    long best_cost = -1;
+    for (int w : {8, 9, 10, 12}) {
+        const long ctas = (long)rows * ceil_div(g.pitch_e, w * kP);
+        const long cost = ((ctas + slots - 1) / slots) * 100000L * w + ctas;     // waves x CTA length, then fewer CTAs
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
+    }
+    switch (best_w) {
+        case 9: return launch_anchor_y_w<S, 9>(g, img, t1y, st);
+        case 10: return launch_anchor_y_w<S, 10>(g, img, t1y, st);
+        case 12: return launch_anchor_y_w<S, 12>(g, img, t1y, st);
+        default: return launch_anchor_y_w<S, 8>(g, img, t1y, st);
+    }
 }
 
 template <int S>
