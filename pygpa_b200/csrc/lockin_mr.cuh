@@ -243,7 +243,7 @@ struct MrPass2Params {
     size_t plane_stride;
     const float2* phx;     // [n_rows][n_alloc], padded-row carrier
     float2* p2;            // [chunk][n_cand][Nd][Md]
-    float* pmax;           // [chunk][n_cand][nbx][nby]: max |P2|^2 over blocks of kPmB x kPmB coarse cells
+    float* pmax;           // [chunk][nbx][nby][n_cand]: max |P2|^2 over blocks of kPmB x kPmB coarse cells (candidate-minor)
     int Nd, Md, pitch_d, n_alloc, J, plane0, pstep, n_cand, row_c, row_p, nbx, nby;   // nbx, nby: ALLOCATED block grid
 };
 
@@ -321,8 +321,8 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
 #pragma unroll
             for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
             if ((lane & (kPmB - 1)) == 0 && prm.pmax != nullptr)
-                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
-                         (my0 + lane) / kPmB] = a2max[hb];
+                prm.pmax[(((size_t)pl * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby + (my0 + lane) / kPmB) * prm.n_cand + c] =
+                    a2max[hb];      // candidate-minor: the survivor search / plane ordering read it with lanes over candidates
         }
         cp_async_wait_all();
         group_sync();     // this group's next carrier is complete; the current one is no longer read
@@ -408,8 +408,8 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
 #pragma unroll
             for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
             if ((lane & (kPmB - 1)) == 0 && prm.pmax != nullptr)
-                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
-                         (my0 + lane) / kPmB] = a2max[hb];
+                prm.pmax[(((size_t)pl * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby + (my0 + lane) / kPmB) * prm.n_cand + c] =
+                    a2max[hb];      // candidate-minor: the survivor search / plane ordering read it with lanes over candidates
         }
         cp_async_wait_all();
         group_sync();
@@ -611,8 +611,8 @@ k_mr_pass2b(const MrPass2bParams prm, const __grid_constant__ TapTable taps) {
 #pragma unroll
             for (int o = kPmB / 2; o > 0; o >>= 1) a2max[hb] = fmaxf(a2max[hb], __shfl_xor_sync(0xffffffffu, a2max[hb], o));
             if ((lane & (kPmB - 1)) == 0)
-                prm.pmax[(((size_t)pl * prm.n_cand + c) * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby +
-                         (my0 + lane) / kPmB] = a2max[hb];
+                prm.pmax[(((size_t)pl * prm.nbx + ((mx0 + warp * kP) / kPmB + hb)) * prm.nby + (my0 + lane) / kPmB) * prm.n_cand + c] =
+                    a2max[hb];      // candidate-minor: the survivor search / plane ordering read it with lanes over candidates
         }
         cp_async_wait_all();
         __syncthreads();      // the next candidate's rows are complete; this one's are no longer read
@@ -715,20 +715,22 @@ __global__ void __launch_bounds__(256) k_mr_order(const float* __restrict__ pmax
     const int r_lo = x0 / S - kMrHL, c_lo = y0 / S - kMrHL;
     const int bx0 = (r_lo >= 0 ? r_lo : r_lo - (kPmB - 1)) / kPmB, bx1 = (r_lo + CX - 1 >= 0 ? r_lo + CX - 1 : r_lo + CX - kPmB) / kPmB;
     const int by0 = (c_lo >= 0 ? c_lo : c_lo - (kPmB - 1)) / kPmB, by1 = (c_lo + CY - 1 >= 0 ? c_lo + CY - 1 : c_lo + CY - kPmB) / kPmB;
+    // wrapped offsets of the window's bound blocks, once per CTA (they used to be two integer divisions per loaded value)
+    __shared__ int s_off[64];
+    const int nwx = bx1 - bx0 + 1, nwy = by1 - by0 + 1, nw = nwx * nwy;      // <= (SBX + 2) (SBY + 2) <= 60
+    if ((int)threadIdx.x < nw) {
+        int wx = (bx0 + (int)threadIdx.x / nwy) % nbx, wy = (by0 + (int)threadIdx.x % nwy) % nby;
+        if (wx < 0) wx += nbx;
+        if (wy < 0) wy += nby;
+        s_off[threadIdx.x] = (wx * nby_alloc + wy) * n_cand;
+    }
+    __syncthreads();
     // one warp per plane, lanes over candidates
     for (int pl = warp; pl < count; pl += 8) {
         float m = 0.f;
         for (int c = lane; c < n_cand; c += 32) {
-            const float* __restrict__ pm = pmax + ((size_t)pl * n_cand + c) * nbx_alloc * nby_alloc;
-            for (int bx = bx0; bx <= bx1; ++bx) {
-                int wx = bx % nbx;
-                if (wx < 0) wx += nbx;
-                for (int by = by0; by <= by1; ++by) {
-                    int wy = by % nby;
-                    if (wy < 0) wy += nby;
-                    m = fmaxf(m, __ldg(pm + wx * nby_alloc + wy));
-                }
-            }
+            const float* __restrict__ pm = pmax + (size_t)pl * n_cand * nbx_alloc * nby_alloc + c;      // [plane][bx][by][cand]
+            for (int w = 0; w < nw; ++w) m = fmaxf(m, __ldg(pm + s_off[w]));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -801,6 +803,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
     __shared__ int s_cnt, s_needboot;
     __shared__ int s_boot[SBX * SBY];     // bootstrap: per bound block the candidate with the largest bound (bound bits | candidate)
     __shared__ int s_new[SBX][SBY];       // block minima of this plane's best so far
+    __shared__ int s_woff[(SBX + 2) * (SBY + 2)];
     __shared__ unsigned short s_list[kMaxPruneCand];
     __shared__ unsigned s_mask[kMaxPruneCand];      // per survivor: bound blocks of the tile in which it can still win
     static_assert(SBX * SBY <= 32, "one mask bit per bound block of the tile");
@@ -855,6 +858,13 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
             s_needboot = nb;
         }
         if (threadIdx.x < SBX * SBY) s_boot[threadIdx.x] = 0;
+        if (threadIdx.x < (SBX + 2) * (SBY + 2)) {     // element offsets of the window's bound blocks in pmax[plane][bx][by][cand]
+            const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;
+            int wx = (bx0 + (int)threadIdx.x / (SBY + 2)) % prm.nbx, wy = (by0 + (int)threadIdx.x % (SBY + 2)) % prm.nby;
+            if (wx < 0) wx += prm.nbx;
+            if (wy < 0) wy += prm.nby;
+            s_woff[threadIdx.x] = (wx * prm.nby_alloc + wy) * prm.n_cand;
+        }
         __syncthreads();
     }
     const bool boot = prune && s_needboot != 0;
@@ -1004,7 +1014,7 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
         for (int i = 0; i < SBX; ++i)
 #pragma unroll
             for (int j = 0; j < SBY; ++j) thr[i][j] = __int_as_float(s_blk[i][j]);
-        const int bx0 = (x0 / S) / kPmB - 1, by0 = (y0 / S) / kPmB - 1;      // window: one block around the tile's blocks
+        // window: one block around the tile's blocks; its wrapped offsets were computed once per CTA (s_woff)
         constexpr int MAXR = (kMaxPruneCand + 255) / 256;
         unsigned keep_bits[MAXR];      // per round: this lane's mask (0 = dropped)
         const int rounds = (prm.n_cand + 255) / 256;
@@ -1018,19 +1028,12 @@ k_mr_interp(const MrInterpParams prm, const __grid_constant__ TapTable taps, con
 #pragma unroll
                 for (int b = 0; b < SBX * SBY; ++b) bnd[b] = 0.f;
                 if (c < prm.n_cand) {
-                    const float* __restrict__ pm = prm.pmax + ((size_t)pl * prm.n_cand + c) * prm.nbx_alloc * prm.nby_alloc;
+                    const float* __restrict__ pm = prm.pmax + (size_t)pl * prm.n_cand * prm.nbx_alloc * prm.nby_alloc + c;   // [plane][bx][by][cand]
                     float m[SBX + 2][SBY + 2];
 #pragma unroll
-                    for (int i = 0; i < SBX + 2; ++i) {
-                        int wx = (bx0 + i) % prm.nbx;
-                        if (wx < 0) wx += prm.nbx;
+                    for (int i = 0; i < SBX + 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < SBY + 2; ++j) {
-                            int wy = (by0 + j) % prm.nby;
-                            if (wy < 0) wy += prm.nby;
-                            m[i][j] = __ldg(pm + wx * prm.nby_alloc + wy);
-                        }
-                    }
+                        for (int j = 0; j < SBY + 2; ++j) m[i][j] = __ldg(pm + s_woff[i * (SBY + 2) + j]);
 #pragma unroll
                     for (int i = 0; i < SBX; ++i)
 #pragma unroll
