@@ -90,7 +90,10 @@ k_mr_pass1(const MrPass1Params prm, const __grid_constant__ TapTable taps) {
         float2 acc[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
-        for (int q = 0; q < S; ++q) {
+        // ANCHOR, halo part (pl = 1): its carrier is zero on every frame-body column, so a CTA whose samples all lie inside
+        // the frame (four in five at C3) has nothing to filter and stores zeros
+        const bool skip = ANCHOR && pl == 1 && S * m0 - prm.Ray >= 0 && S * m0 - prm.Ray + n_samp <= M;
+        for (int q = 0; q < S && !skip; ++q) {
             const float* colq = col + q * SP;
             const float2* phq = ph + q;
             fir_phase<kP>(acc, taps, q * J, J, [&](int j) {
@@ -296,7 +299,19 @@ k_mr_pass2(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
         float2 acc[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
-        for (int q = 0; q < S; ++q) {
+        // Anchor stage of the split (pmax == nullptr): the halo-masked carrier is zero on every row of the frame body, so the
+        // group that owns it has nothing to filter in four CTAs out of five and leaves the SM to the other group.
+        unsigned live = 1u;
+        if (prm.pmax == nullptr) {
+            unsigned nz = 0u;
+            for (int j = tig; j < n_samp; j += GT) {
+                const float2 v = sph[slot * n_samp + j];
+                nz |= (v.x != 0.f) | (v.y != 0.f);
+            }
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(live) : "r"(nz), "r"(group + 1), "n"(GT) : "memory");
+        }
+        for (int q = 0; q < S && live; ++q) {
             const float2* colq = col + q * kLanes;
             const float2* phq = ph + q;
             fir_phase<kP>(acc, taps, q * J, J, [&](int j) { return cmul(colq[j * (S * kLanes)], phq[j * S]); });
@@ -374,8 +389,20 @@ k_mr_pass2s(const MrPass2Params prm, const __grid_constant__ TapTable taps) {
         float2 acc[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p) acc[p] = make_float2(0.f, 0.f);
+        // Anchor stage of the split (pmax == nullptr): the halo-masked carrier is zero on every row of the frame body, so the
+        // group that owns it has nothing to filter in four CTAs out of five and leaves the SM to the other group.
+        unsigned live = 1u;
+        if (prm.pmax == nullptr) {
+            unsigned nz = 0u;
+            for (int j = tig; j < n_samp; j += GT) {
+                const float2 v = sph[slot * n_samp + j];
+                nz |= (v.x != 0.f) | (v.y != 0.f);
+            }
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(live) : "r"(nz), "r"(group + 1), "n"(GT) : "memory");
+        }
 #pragma unroll 1
-        for (int q = 0; q < S; ++q) {
+        for (int q = 0; q < S && live; ++q) {
             const float2* colq = col + q * kLanes;
             const float2* phq = ph + q;
             float2 g[JT];
