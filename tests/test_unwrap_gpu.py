@@ -162,7 +162,8 @@ def test_solver_helper_mirrors(shape):
     assert np.allclose(PU.applyQ(p, wwx, wwy), ref_numpy._apply_q(p, wwx, wwy), rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("shape", [(256, 256), (512, 512), (1024, 1024), (2048, 2048), (4096, 4096), (300, 256), (256, 258), (512, 770)])
+@pytest.mark.parametrize("shape", [(256, 256), (512, 512), (1024, 1024), (2048, 2048), (4096, 4096), (300, 256), (256, 258), (512, 770),
+                                   (301, 512), (257, 256), (512, 301)])
 def test_pipelined_dct_kernels_agree_with_the_one_cta_per_pair_kernels(shape):
     """The pipelined K2 kernels (bulk-copy prefetch, TMA column strips, <r, z> from the DCT coefficients, fused direction
     update) against the kernels they replace (gpa_set_dct_pipeline(0)): transforms to rounding, PCG iterates to 1e-11,
