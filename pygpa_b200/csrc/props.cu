@@ -29,31 +29,41 @@ struct Grad2JParams {
     double nmperpixel;
 };
 
-template <int DM>
+// FULL (d == DM) and WRAP as template parameters: no launch-uniform branch is left around the loads, so the DM weights and DM
+// gradient pairs of a pixel are all in flight before the first is used (as in k_lstsq: the runtime switches serialised them).
+template <int DM, bool FULL, bool WRAP>
 __global__ void __launch_bounds__(256) k_grad2J(const Grad2JParams p) {
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= p.N || c >= p.M) return;
+    const int d = FULL ? DM : p.d;
     const size_t pix = (size_t)r * p.M + c;
     const size_t npix = (size_t)p.N * p.M;
+    double wv[DM];
+    double2 gv[DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) {
+        wv[i] = 0.0;
+        gv[i] = make_double2(0.0, 0.0);
+        if (i < d) {
+            wv[i] = p.w[(size_t)i * p.wn * p.wm + (size_t)r * p.wm + c];
+            gv[i] = *reinterpret_cast<const double2*>(p.grads + ((size_t)p.order[i] * npix + pix) * 2);
+        }
+    }
     double a0[DM], a1[DM], y[2][DM], x[2][2];
 #pragma unroll
     for (int i = 0; i < DM; ++i) {
-        if (i < p.d) {
-            const double w = p.w[(size_t)i * p.wn * p.wm + (size_t)r * p.wm + c];
-            const double2 g = *reinterpret_cast<const double2*>(p.grads + ((size_t)p.order[i] * npix + pix) * 2);
-            double b0 = g.x - p.sub[i][0], b1 = g.y - p.sub[i][1];
-            if (p.do_wrap) {
-                b0 = wrap_pi(b0);
-                b1 = wrap_pi(b1);
-            }
-            a0[i] = w * p.K[i][0];
-            a1[i] = w * p.K[i][1];
-            y[0][i] = w * b0;
-            y[1][i] = w * b1;
+        double b0 = gv[i].x - p.sub[i][0], b1 = gv[i].y - p.sub[i][1];
+        if (WRAP) {
+            b0 = wrap_pi(b0);
+            b1 = wrap_pi(b1);
         }
+        a0[i] = wv[i] * p.K[i][0];
+        a1[i] = wv[i] * p.K[i][1];
+        y[0][i] = wv[i] * b0;
+        y[1][i] = wv[i] * b1;
     }
-    lsq_solve2<2, DM>(a0, a1, y, p.d, x);
+    lsq_solve2<2, DM>(a0, a1, y, d, x);
     // J[i][j] = d u_i / d x_j: right-hand side j (gradient along axis j) gives column j
     const double id = p.add_identity ? 1.0 : 0.0;
     double2* out = reinterpret_cast<double2*>(p.J + pix * 4);
@@ -107,8 +117,16 @@ extern "C" int gpa_phasegradient_to_j(const double* grads, const double* weights
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KernelTimer t("k_grad2J", st);
     dim3 grid(ceil_div(M, 64), ceil_div(N, 4));
-    if (d <= 3) k_grad2J<3><<<grid, 256, 0, st>>>(p);
-    else k_grad2J<kMaxD><<<grid, 256, 0, st>>>(p);
+    if (d == 3) {
+        if (do_wrap) k_grad2J<3, true, true><<<grid, 256, 0, st>>>(p);
+        else k_grad2J<3, true, false><<<grid, 256, 0, st>>>(p);
+    } else if (d < 3) {
+        if (do_wrap) k_grad2J<3, false, true><<<grid, 256, 0, st>>>(p);
+        else k_grad2J<3, false, false><<<grid, 256, 0, st>>>(p);
+    } else {
+        if (do_wrap) k_grad2J<kMaxD, false, true><<<grid, 256, 0, st>>>(p);
+        else k_grad2J<kMaxD, false, false><<<grid, 256, 0, st>>>(p);
+    }
     GPA_CHECK_CUDA(cudaGetLastError());
     return GPA_OK;
 }
