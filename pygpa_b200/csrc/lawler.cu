@@ -36,7 +36,7 @@ struct PrefilterArgs {
     double gain;            // (1 - z)(1 - 1/z) = 6 per axis pass
 };
 
-constexpr int kSegLen = 64;     // outputs per thread along the filter axis
+constexpr int kSegLen = 32;     // outputs per thread along the filter axis (64 left the GPU a quarter full at 2048^2)
 constexpr int kWarm = 40;       // warm-up samples of a segment's recursion: |pole|^40 = 1.3e-23
 
 // The recursions c+[i] = s[i] + z c+[i-1] and c[i] = z (c[i+1] - c+[i]) forget their start after
@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(128) k_prefilter_causal(const PrefilterArgs a)
     const int i1 = min(i0 + kSegLen, n);
     double prev;
     int i;
-    if (i0 == 0) {
-        // exact causal initial condition (scipy _init_causal_reflect / _init_causal_mirror)
+    if (i0 <= kWarm) {
+        // exact causal initial condition (scipy _init_causal_reflect / _init_causal_mirror); segments that begin within
+        // kWarm samples of the start run the recursion up from sample 0 without storing
         const int terms = n < kInitTerms ? n : kInitTerms;
         if (a.boundary == kNearest) {
             const double zn = pow(z, (double)n);
@@ -87,10 +88,15 @@ __global__ void __launch_bounds__(128) k_prefilter_causal(const PrefilterArgs a)
             }
             prev = acc / (1.0 - zn1 * zn1);
         }
-        out[0] = prev;
-        i = 1;
+        if (i0 == 0) {
+            out[0] = prev;
+            i = 1;
+        } else {
+            for (int t = 1; t < i0; ++t) prev = fma(z, prev, s(t));
+            i = i0;
+        }
     } else {
-        const int w0 = i0 - kWarm;           // i0 >= kSegLen > kWarm
+        const int w0 = i0 - kWarm;           // > 0
         prev = s(w0) / (1.0 - z);
         for (int t = w0 + 1; t < i0; ++t) prev = fma(z, prev, s(t));
         i = i0;
