@@ -1,8 +1,10 @@
 // K2 row transforms, pipelined form (round 2): persistent CTAs, the next pair of rows arrives by ONE bulk copy
 // (cp.async.bulk global -> shared, mbarrier completion; SASS UBLKCP) while the current pair is transformed.
 //
-// Same arithmetic as k_dct2_rows_pow2 / k_idct2_rows_pow2 (unwrap.cu): Makhoul permutation, two rows per complex FFT,
-// radix-2 / radix-4 head stage + radix-8 Stockham stages with the same twiddle derivation, so the results are bit-identical.
+// Same algorithm as k_dct2_rows_pow2 / k_idct2_rows_pow2 (unwrap.cu): Makhoul permutation, two rows per complex FFT,
+// radix-2 / radix-4 head stage + radix-8 Stockham stages.  The twiddles w2, w4 come from squaring w1 and the Makhoul factors
+// from one value per thread times constant rotations, so the results agree with those kernels to rounding (1e-16 relative on
+// the transforms, 1e-13 on PCG iterates; tests/test_unwrap_gpu.py compares the two), not bit for bit.
 // What changed is the data movement:
 //   * the raw rows land in a staging buffer; the permutation (forward) / the DCT-III pre-twiddle (inverse) is folded into
 //     the loads of the first FFT stage, so there is no separate "load + permute" pass and no thread ever waits on DRAM;
