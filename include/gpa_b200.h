@@ -337,8 +337,9 @@ int gpa_fit_plane_huber(const double* img, int n, int m, double f_scale, int max
  * iteration, as the reference).  *iterations (host, optional) receives the iteration count and
  * forces a stream synchronisation.
  * ------------------------------------------------------------------------------------------ */
-/* K2 row transforms of the DCT: 1 (default) = pipelined kernels (persistent CTAs, the next pair of rows arrives by
- * cp.async.bulk while the current pair is transformed), 0 = one CTA per pair of rows.  Results are bit-identical. */
+/* K2 transforms of the PCG: 1 (default) = pipelined kernels (persistent CTAs; rows prefetched by cp.async.bulk, 4-column strips
+ * by TMA boxes; <r, z> from the DCT coefficients in the column stage; p = z + beta p fused into the last inverse pass),
+ * 0 = one CTA per pair of rows / per strip of 8 columns.  The two agree to rounding (1e-13 on PCG iterates). */
 int gpa_set_dct_pipeline(int on);
 
 /* Device mirrors of the reference's solver helpers, all float64:
